@@ -1,0 +1,111 @@
+/*
+ * lhb200.h — C ABI of liblhb200.so: the B200-native (sm_100a) replacement for Lighthouse's two
+ * compute-bound hot paths.  Plain pointers and sizes only; no exceptions or panics cross this boundary.
+ *
+ * Citations are file:line under sigp/lighthouse v5.3.0 (/root/reference).  The Rust-side bindings a
+ * Lighthouse maintainer would add are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Every entry point returns an int32 status: LHB200_OK (0) or a negative LHB200_E* code;
+ *     lhb200_last_error() gives a thread-local human-readable message.  Results go to out-params.
+ *   - "Host" entry points take caller-owned host buffers that are only read during the call (they mirror
+ *     the borrowed Cow<'a, ..> data of bls::SignatureSet / &self of TreeHash); nothing is retained.
+ *   - "dev_" entry points take device pointers (inputs already resident in HBM) and an optional
+ *     cudaStream_t passed as void* (NULL = the library's stream); they return after enqueueing unless
+ *     documented otherwise.
+ *   - There is NO CPU fallback: without a usable sm_100 device every compute entry point returns
+ *     LHB200_ENODEV.
+ */
+#ifndef LHB200_H
+#define LHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LHB200_API __attribute__((visibility("default")))
+#else
+#define LHB200_API
+#endif
+
+#define LHB200_OK 0
+#define LHB200_ENODEV (-1)   /* no CUDA device / init not called / init failed */
+#define LHB200_EINVAL (-2)   /* bad argument (null pointer, inconsistent sizes, malformed SSZ offsets) */
+#define LHB200_ECUDA (-3)    /* CUDA runtime error (message in lhb200_last_error) */
+#define LHB200_ENOMEM (-4)   /* device or pinned allocation failed */
+#define LHB200_EDECODE (-5)  /* a serialized point failed to decode (bls::Error::InvalidByteLength/BlstError) */
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+
+/* Bind the calling process to CUDA device `device` (one process per GPU), create the library stream and
+ * scratch arenas and upload constant tables.  Idempotent for the same device. */
+LHB200_API int32_t lhb200_init(int32_t device);
+LHB200_API void lhb200_shutdown(void);
+LHB200_API const char* lhb200_last_error(void);
+/* Pinned host memory for callers that want zero-staging H2D (the e2e bench uses it). */
+LHB200_API int32_t lhb200_pinned_alloc(void** out, uint64_t nbytes);
+LHB200_API int32_t lhb200_pinned_free(void* p);
+/* Number of kernel launches issued by this library since init (bench.py's "gpu_launches"). */
+LHB200_API uint64_t lhb200_launch_count(void);
+
+/* ---- tree-hash path --------------------------------------------------------------------------- */
+
+/* ethereum_hashing::hash32_concat over n independent 64-byte inputs (consensus/merkle_proof/src/lib.rs:91,
+ * :380-384): out[i] = SHA256(in[64i .. 64i+64]). */
+LHB200_API int32_t lhb200_hash_pairs(const uint8_t* in, uint8_t* out, uint64_t n);
+LHB200_API int32_t lhb200_dev_hash_pairs(const void* d_in, void* d_out, uint64_t n, void* stream);
+
+/* tree_hash::merkle_root / merkleize with a chunk limit of 2^depth (crypto/bls/src/macros.rs:24,
+ * SURVEY Appendix B): zero-pads every level with ZERO_HASHES[level]; n_chunks == 0 gives ZERO_HASHES[depth].
+ * n_chunks must be <= 2^depth. */
+LHB200_API int32_t lhb200_merkleize(const uint8_t* chunks, uint64_t n_chunks, uint32_t depth, uint8_t out[32]);
+/* d_chunks must be 16-byte aligned; d_out32 receives the 32-byte root (device memory). */
+LHB200_API int32_t lhb200_dev_merkleize(const void* d_chunks, uint64_t n_chunks, uint32_t depth, void* d_out32, void* stream);
+
+/* tree_hash::mix_in_length(root, len) = SHA256(root || le64(len) || 0^24). */
+LHB200_API int32_t lhb200_mix_in_length(const uint8_t root[32], uint64_t len, uint8_t out[32]);
+
+/* ZERO_HASHES[depth] (ethereum_hashing::ZERO_HASHES, merkle_proof/src/lib.rs:166), depth <= 64. */
+LHB200_API int32_t lhb200_zero_hash(uint32_t depth, uint8_t out[32]);
+
+/* hash_tree_root(List[Validator, 2^40]) from n 121-byte SSZ validators (consensus/types/src/validator.rs:25-35;
+ * beacon_state.rs:363).  lhb200_validator_roots writes the n per-validator roots instead. */
+LHB200_API int32_t lhb200_validators_root(const uint8_t* ssz, uint64_t n, uint8_t out[32]);
+LHB200_API int32_t lhb200_validator_roots(const uint8_t* ssz, uint64_t n, uint8_t* out_roots);
+
+/* BeaconState::update_tree_hash_cache / tree_hash_root for the Deneb variant, mainnet preset, cold (no cached
+ * nodes) — consensus/types/src/beacon_state.rs:2031-2038, fields :343-484.  `ssz` is the SSZ encoding of
+ * BeaconStateDeneb.  field_roots (28*32 bytes) is optional (NULL to skip). */
+LHB200_API int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* field_roots);
+
+/* Device-resident variant: stage once (H2D into the library's aligned HBM layout), then hash
+ * as often as wanted without touching the host link.  The handle owns device memory until released. */
+typedef struct lhb200_state lhb200_state;
+LHB200_API int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state** out);
+LHB200_API int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t* field_roots);
+/* Same as lhb200_state_root but only enqueues; the root lands in device memory (returned pointer valid until
+ * the next call on this handle).  Used by bench.py to time kernels with CUDA events. */
+LHB200_API int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root);
+/* Leaf-range sharding for multi-GPU: keep only validators/balances/... in [first, first+count)
+ * (must be a power-of-two aligned range) and produce the 32-byte subtree roots of the big lists. */
+LHB200_API int32_t lhb200_state_release(lhb200_state* st);
+/* Algorithmic work of the last root computed on this handle: number of hash32_concat units. */
+LHB200_API uint64_t lhb200_state_hash_units(const lhb200_state* st);
+
+/* MerkleTree::create(leaves, depth) + generate_proof(index, depth) (consensus/merkle_proof/src/lib.rs:68-99,
+ * :290-324): root and the bottom-up branch (depth * 32 bytes).  n <= 2^depth, depth <= 32. */
+LHB200_API int32_t lhb200_merkle_tree_proof(const uint8_t* leaves, uint64_t n, uint32_t depth, uint64_t index, uint8_t root[32],
+                                 uint8_t* branch);
+/* verify_merkle_proof / merkle_root_from_branch batch (merkle_proof/src/lib.rs:357-389): for each i,
+ * ok[i] = (fold(leaf_i, branch_i, depth, index_i) == root_i).  branches: n * depth * 32 bytes. */
+LHB200_API int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branches, uint32_t depth,
+                                    const uint64_t* indices, const uint8_t* roots, uint64_t n, uint8_t* ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LHB200_H */

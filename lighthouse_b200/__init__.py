@@ -1,0 +1,10 @@
+"""lighthouse_b200 — B200-native (sm_100a) batch BLS12-381 verification and SSZ SHA-256 merkleization
+behind Lighthouse's `bls::SignatureSet` / `tree_hash::TreeHash` surfaces.  See DESIGN.md.
+
+Importing the package loads liblhb200.so (fails loudly if it has not been built); nothing here falls back
+to CPU arithmetic.
+"""
+from . import _ffi  # noqa: F401  (raises ImportError if the CUDA library is missing)
+from ._ffi import init, Lhb200Error  # noqa: F401
+
+__all__ = ["init", "Lhb200Error", "tree_hash", "merkle_proof", "bls"]

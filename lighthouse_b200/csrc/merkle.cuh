@@ -1,0 +1,316 @@
+// merkle.cuh — SSZ merkleization kernels (sm_100a).  See DESIGN.md §"Tree-hash path".
+//
+// Kernel inventory:
+//   k_hash_pairs ........ n independent hash32_concat (ethereum_hashing::hash32_concat batch)
+//   k_validator_roots ... 121-byte SSZ Validator -> 32-byte root (8 hashes / validator, validator.rs:25-35)
+//   k_record_roots ...... small fixed records: 48-B pubkey (bls/src/macros.rs:18-25), 72-B Eth1Data
+//   k_merkle_reduce ..... multi-segment tile reduce: every CTA folds up to 2^11 chunks of one segment
+//                         (up to 11 tree levels) and writes one node; virtual zero padding via ZERO_HASHES
+//   k_hash_program ...... small DAG interpreter (zero ladders, mix_in_length, small containers, top tree)
+#pragma once
+#include "sha256.cuh"
+
+namespace lhb200 {
+
+constexpr int MAX_ZERO_DEPTH = 64;
+// ZERO_HASHES[d] in word form (merkle_proof/src/lib.rs:166).  Filled by k_init_zero_hashes at init.
+__device__ uint32_t g_zero_words[MAX_ZERO_DEPTH + 1][8];
+
+__global__ void k_init_zero_hashes() {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t cur[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = 0;
+    for (int d = 0; d <= MAX_ZERO_DEPTH; d++) {
+        for (int i = 0; i < 8; i++) g_zero_words[d][i] = cur[i];
+        hash_pair(cur, cur, cur);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hash_pairs(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                    uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t l[8], r[8], o[8];
+    load_chunk(in + 64 * i, l);
+    load_chunk(in + 64 * i + 32, r);
+    hash_pair_inl(l, r, o);
+    store_chunk(out + 32 * i, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Validator roots.  One CTA stages 256 validators (30 976 contiguous bytes, 16-B aligned because the
+// staged list base is 256-B aligned and 256*121 is a multiple of 16) into shared memory with coalesced
+// uint4 loads, then each thread builds its validator's 8 leaves and folds them (8 hashes).
+constexpr int VAL_SSZ = 121;
+constexpr int VAL_PER_CTA = 256;
+
+__device__ __forceinline__ uint32_t be_word(const uint8_t* p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+// little-endian u64 field -> first two SHA words of its (zero padded) chunk
+__device__ __forceinline__ void le64_words(const uint8_t* p, uint32_t& w0, uint32_t& w1) {
+    w0 = be_word(p);
+    w1 = be_word(p + 4);
+}
+
+__global__ void __launch_bounds__(VAL_PER_CTA) k_validator_roots(const uint8_t* __restrict__ ssz, uint64_t n,
+                                                                 uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t sm[VAL_PER_CTA * VAL_SSZ];
+    const uint64_t first = (uint64_t)blockIdx.x * VAL_PER_CTA;
+    const uint64_t cnt = min((uint64_t)VAL_PER_CTA, n - first);
+    const uint32_t nbytes = (uint32_t)cnt * VAL_SSZ;
+    const uint8_t* src = ssz + first * VAL_SSZ;
+    {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(sm);
+        const uint32_t nvec = nbytes / 16;
+        for (uint32_t i = threadIdx.x; i < nvec; i += VAL_PER_CTA) d4[i] = __ldg(s4 + i);
+        for (uint32_t i = nvec * 16 + threadIdx.x; i < nbytes; i += VAL_PER_CTA) sm[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x >= cnt) return;
+    const uint8_t* v = sm + threadIdx.x * VAL_SSZ;
+
+    uint32_t a[8], b[8], h01[8], h23[8];
+    // leaf0 = H(pubkey[0:32] || pubkey[32:48] || 0^16)
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = be_word(v + 4 * i);
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = be_word(v + 32 + 4 * i);
+    b[4] = b[5] = b[6] = b[7] = 0;
+    hash_pair(a, b, a);
+    // leaf1 = withdrawal_credentials
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = be_word(v + 48 + 4 * i);
+    hash_pair(a, b, h01);
+    // leaf2 = effective_balance, leaf3 = slashed
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = b[i] = 0;
+    le64_words(v + 80, a[0], a[1]);
+    b[0] = (uint32_t)v[88] << 24;
+    hash_pair(a, b, h23);
+    hash_pair(h01, h23, h01);  // h0123
+    // leaf4..7 = activation_eligibility, activation, exit, withdrawable epochs
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = b[i] = 0;
+    le64_words(v + 89, a[0], a[1]);
+    le64_words(v + 97, b[0], b[1]);
+    hash_pair(a, b, h23);  // h45
+    a[0] = a[1] = b[0] = b[1] = 0;
+    le64_words(v + 105, a[0], a[1]);
+    le64_words(v + 113, b[0], b[1]);
+    hash_pair(a, b, a);      // h67
+    hash_pair(h23, a, h23);  // h4567
+    hash_pair(h01, h23, h01);
+    store_chunk(out + 32 * (first + threadIdx.x), h01);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small fixed-size records -> roots.  kind 0: 48-byte pubkey.  kind 1: 72-byte Eth1Data {H256,u64,H256}.
+__global__ void __launch_bounds__(128) k_record_roots(const uint8_t* __restrict__ in, uint64_t n, int kind,
+                                                      uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a[8], b[8];
+    if (kind == 0) {
+        const uint8_t* p = in + 48 * i;
+        for (int k = 0; k < 8; k++) a[k] = be_word(p + 4 * k);
+        for (int k = 0; k < 4; k++) b[k] = be_word(p + 32 + 4 * k);
+        b[4] = b[5] = b[6] = b[7] = 0;
+        hash_pair(a, b, a);
+    } else {
+        const uint8_t* p = in + 72 * i;
+        uint32_t c[8];
+        for (int k = 0; k < 8; k++) a[k] = be_word(p + 4 * k);
+        for (int k = 0; k < 8; k++) b[k] = 0;
+        le64_words(p + 32, b[0], b[1]);
+        hash_pair(a, b, a);  // H(deposit_root, deposit_count)
+        for (int k = 0; k < 8; k++) c[k] = be_word(p + 40 + 4 * k);
+        for (int k = 0; k < 8; k++) b[k] = 0;
+        hash_pair(c, b, c);  // H(block_hash, zero chunk)
+        hash_pair(a, c, a);
+    }
+    store_chunk(out + 32 * i, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-segment tile reduce.
+struct MerkleSeg {
+    const uint8_t* in;   // n_in chunks (32 B each, 16-B aligned); roots of height-`level_in` subtrees
+    uint8_t* out;        // ceil(n_in / 2^tile_log) chunks
+    uint64_t n_in;
+    uint32_t level_in;   // height of the input nodes above the segment's leaves (selects ZERO_HASHES row)
+    uint32_t tile_log;   // levels folded by one CTA, 1..11
+    uint32_t cta_begin;  // first CTA index serving this segment
+    uint32_t n_tiles;
+};
+constexpr int MAX_SEGS = 24;
+struct MerkleSegTable {
+    int n;
+    MerkleSeg s[MAX_SEGS];
+};
+constexpr int REDUCE_THREADS = 256;
+constexpr int MAX_TILE_LOG = 11;  // 256 threads x 8 chunks
+
+// fold (l, r) where the right node may be virtual padding
+__device__ __forceinline__ void fold(uint32_t l[8], const uint32_t r[8], bool r_valid, uint32_t zlevel) {
+    uint32_t rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rr[i] = r_valid ? r[i] : g_zero_words[zlevel][i];
+    hash_pair(l, rr, l);
+}
+
+__global__ void __launch_bounds__(REDUCE_THREADS) k_merkle_reduce(const __grid_constant__ MerkleSegTable tab) {
+    __shared__ uint32_t sm[2][REDUCE_THREADS][8];
+    int si = 0;
+#pragma unroll 1
+    for (int k = 1; k < tab.n; k++)
+        if (blockIdx.x >= tab.s[k].cta_begin) si = k;
+    const MerkleSeg& sg = tab.s[si];
+    const uint32_t tile = blockIdx.x - sg.cta_begin;
+    const uint32_t tl = sg.tile_log;
+    const uint32_t t = tl < 3 ? tl : 3;  // levels folded privately by each thread
+    const uint32_t nthr_a = 1u << (tl - t);
+    const uint64_t n_in = sg.n_in;
+    const uint32_t tid = threadIdx.x;
+
+    // ---- phase A: each active thread folds 2^t consecutive chunks straight from global memory
+    if (tid < nthr_a) {
+        const uint64_t base = ((uint64_t)tile << tl) + ((uint64_t)tid << t);
+        const uint32_t cnt = base >= n_in ? 0u : (uint32_t)min((uint64_t)(1u << t), n_in - base);
+        if (cnt > 0) {
+            uint32_t nd[4][8];
+            uint32_t c = cnt;
+            if (t == 0) {
+                load_chunk(sg.in + 32 * base, nd[0]);
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    if (p < (1 << (t - 1)) && 2u * p < c) {
+                        uint32_t r[8];
+                        load_chunk(sg.in + 32 * (base + 2 * p), nd[p]);
+                        const bool rv = 2u * p + 1 < c;
+                        if (rv) load_chunk(sg.in + 32 * (base + 2 * p + 1), r);
+                        fold(nd[p], r, rv, sg.level_in);
+                    }
+                }
+                c = (c + 1) >> 1;
+                if (t >= 2) {
+#pragma unroll
+                    for (int p = 0; p < 2; p++)
+                        if (p < (1 << (t - 2)) && 2u * p < c) {
+                            if (p) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) nd[1][i] = nd[2][i];
+                            }
+                            fold(nd[p], nd[2 * p + 1], 2u * p + 1 < c, sg.level_in + 1);
+                        }
+                    c = (c + 1) >> 1;
+                }
+                if (t >= 3) fold(nd[0], nd[1], 1 < c, sg.level_in + 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) sm[0][tid][i] = nd[0][i];
+        }
+    }
+    // ---- phase B: remaining tl - t levels through shared memory, compacting active threads each level
+    int cur = 0;
+    uint32_t width = nthr_a;                   // nodes of this tile at the current level
+    uint32_t lvl = t;                          // level (relative to segment input) of the nodes in sm[cur]
+    while (width > 1) {
+        __syncthreads();
+        const uint32_t half = width >> 1;
+        // number of valid nodes at `lvl` over the whole segment
+        const uint64_t valid_total = (n_in + ((1ull << lvl) - 1)) >> lvl;
+        if (tid < half) {
+            const uint64_t gl = (uint64_t)tile * width + 2 * tid;  // global index of the left child
+            if (gl < valid_total) {
+                uint32_t l[8], r[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { l[i] = sm[cur][2 * tid][i]; r[i] = sm[cur][2 * tid + 1][i]; }
+                fold(l, r, gl + 1 < valid_total, sg.level_in + lvl);
+#pragma unroll
+                for (int i = 0; i < 8; i++) sm[cur ^ 1][tid][i] = l[i];
+            }
+        }
+        cur ^= 1;
+        width = half;
+        lvl++;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint64_t valid_total = (n_in + ((1ull << tl) - 1)) >> tl;
+        if (tile < valid_total) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = sm[cur][0][i];
+            store_chunk(sg.out + 32ull * tile, o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hash program: a DAG of hash32_concat ops over 32-byte nodes anywhere in device memory, executed wave by
+// wave by one CTA.  Operand with bit 63 clear: device address of a 16-B aligned 32-byte node.
+// Operand with bit 63 set: ZERO_HASHES[operand & 0xff].
+struct HashOp {
+    uint64_t dst, a, b;
+};
+constexpr uint64_t OP_ZERO_FLAG = 1ull << 63;
+constexpr int PROG_THREADS = 128;
+
+__device__ __forceinline__ void load_operand(uint64_t op, uint32_t w[8]) {
+    if (op & OP_ZERO_FLAG) {
+        const uint32_t d = (uint32_t)(op & 0xff);
+        for (int i = 0; i < 8; i++) w[i] = g_zero_words[d][i];
+    } else {
+        // plain (coherent) loads: nodes may have been written earlier in this same launch
+        const uint4* p = reinterpret_cast<const uint4*>(op);
+        uint4 x = p[0], y = p[1];
+        w[0] = bswap32(x.x); w[1] = bswap32(x.y); w[2] = bswap32(x.z); w[3] = bswap32(x.w);
+        w[4] = bswap32(y.x); w[5] = bswap32(y.y); w[6] = bswap32(y.z); w[7] = bswap32(y.w);
+    }
+}
+
+__global__ void __launch_bounds__(PROG_THREADS) k_hash_program(const HashOp* __restrict__ ops,
+                                                               const int32_t* __restrict__ wave_begin,
+                                                               int n_waves) {
+    for (int w = 0; w < n_waves; w++) {
+        const int lo = wave_begin[w], hi = wave_begin[w + 1];
+        for (int k = lo + threadIdx.x; k < hi; k += PROG_THREADS) {
+            const HashOp op = ops[k];
+            uint32_t l[8], r[8];
+            load_operand(op.a, l);
+            load_operand(op.b, r);
+            hash_pair(l, r, l);
+            store_chunk(reinterpret_cast<uint8_t*>(op.dst), l);
+        }
+        __syncthreads();
+    }
+}
+
+// verify_merkle_proof batch (merkle_proof/src/lib.rs:357-389): one thread folds one branch bottom-up.
+__global__ void __launch_bounds__(128) k_verify_branches(const uint8_t* __restrict__ leaves,
+                                                         const uint8_t* __restrict__ branches, uint32_t depth,
+                                                         const uint64_t* __restrict__ indices,
+                                                         const uint8_t* __restrict__ roots, uint64_t n,
+                                                         uint8_t* __restrict__ ok) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t cur[8], sib[8];
+    load_chunk(leaves + 32 * i, cur);
+    const uint64_t idx = indices[i];
+    for (uint32_t d = 0; d < depth; d++) {
+        load_chunk(branches + 32 * (i * depth + d), sib);
+        if ((idx >> d) & 1) hash_pair(sib, cur, cur);
+        else hash_pair(cur, sib, cur);
+    }
+    load_chunk(roots + 32 * i, sib);
+    bool eq = true;
+    for (int k = 0; k < 8; k++) eq &= (cur[k] == sib[k]);
+    ok[i] = eq ? 1 : 0;
+}
+
+}  // namespace lhb200

@@ -1,0 +1,788 @@
+// merkle_host.cu — host driver + C ABI of the tree-hash path.
+//
+// Host code only plans (offset parsing, literal chunk packing, launch tables); every SHA-256 compression
+// runs on the device.  Mirrors, at the batch level, tree_hash::{merkle_root, mix_in_length, MerkleHasher},
+// merkle_proof::MerkleTree and BeaconState::update_tree_hash_cache (cold) — see include/lhb200.h.
+#include <string.h>
+#include <algorithm>
+#include <array>
+#include <memory>
+#include "ctx.h"
+#include "merkle.cuh"
+
+namespace lhb200 {
+
+static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline uint32_t ceil_log2(uint64_t x) {
+    uint32_t d = 0;
+    while ((1ull << d) < x) d++;
+    return d;
+}
+
+int32_t merkle_init() {
+    Ctx& c = ctx();
+    k_init_zero_hashes<<<1, 32, 0, c.stream>>>();
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    uint32_t words[MAX_ZERO_DEPTH + 1][8];
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    LHB_CUDA(cudaMemcpyFromSymbol(words, g_zero_words, sizeof words));
+    for (int d = 0; d <= MAX_ZERO_DEPTH; d++)
+        for (int i = 0; i < 8; i++) {
+            c.zero_hashes[d][4 * i + 0] = words[d][i] >> 24;
+            c.zero_hashes[d][4 * i + 1] = words[d][i] >> 16;
+            c.zero_hashes[d][4 * i + 2] = words[d][i] >> 8;
+            c.zero_hashes[d][4 * i + 3] = words[d][i];
+        }
+    return LHB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plan: everything needed to hash one object — leaf kernels, reduce passes, the tail hash program.
+// All device memory a plan touches lives in one arena: [staged inputs | scratch nodes | literals | slots].
+struct LeafLaunch {
+    int kind;  // 0 validator roots, 1 pubkey roots, 2 eth1data roots, 3 hash pairs
+    const uint8_t* in;
+    uint8_t* out;
+    uint64_t n;
+};
+
+struct Plan {
+    uint8_t* arena = nullptr;   // device base
+    size_t arena_bytes = 0;
+    size_t bump = 0;            // allocation cursor (bytes)
+    std::vector<uint8_t> lit;   // host literal block (32-byte chunks), copied to arena+lit_off
+    size_t lit_off = 0, lit_cap = 0;
+    std::vector<LeafLaunch> leaves;
+    std::vector<std::vector<MerkleSeg>> passes;
+    std::vector<HashOp> ops;
+    std::vector<int> op_wave;
+    std::vector<std::pair<uint64_t, int>> ready_wave;  // dst addr -> wave producing it (small; linear scan)
+    uint64_t hash_units = 0;
+    // tail program (device copies)
+    HashOp* d_ops = nullptr;
+    int32_t* d_waves = nullptr;
+    int n_waves = 0;
+    uint64_t root_addr = 0;
+
+    uint8_t* alloc(size_t nbytes) {  // device sub-allocation, 256-B aligned
+        size_t off = align_up(bump, 256);
+        bump = off + nbytes;
+        return arena ? arena + off : reinterpret_cast<uint8_t*>(off);
+    }
+    static uint64_t zero_op(uint32_t level) { return OP_ZERO_FLAG | level; }
+    uint64_t literal(const uint8_t chunk[32]) {
+        size_t i = lit.size();
+        lit.resize(i + 32);
+        memcpy(&lit[i], chunk, 32);
+        return reinterpret_cast<uint64_t>(arena + lit_off + i);
+    }
+    uint64_t literal_bytes(const uint8_t* p, size_t n) {  // zero-padded chunk from <=32 bytes
+        uint8_t c[32] = {0};
+        memcpy(c, p, n);
+        return literal(c);
+    }
+    uint64_t literal_u64(uint64_t v) {
+        uint8_t c[32] = {0};
+        for (int k = 0; k < 8; k++) c[k] = (uint8_t)(v >> (8 * k));
+        return literal(c);
+    }
+    int wave_of(uint64_t operand) const {
+        if (operand & OP_ZERO_FLAG) return -1;
+        for (auto it = ready_wave.rbegin(); it != ready_wave.rend(); ++it)
+            if (it->first == operand) return it->second;
+        return -1;  // staged data / literals / reduce outputs: ready before the program starts
+    }
+    uint64_t op_hash(uint64_t a, uint64_t b) {
+        uint64_t dst = reinterpret_cast<uint64_t>(alloc(32));
+        int w = std::max(wave_of(a), wave_of(b)) + 1;
+        ops.push_back({dst, a, b});
+        op_wave.push_back(w);
+        ready_wave.push_back({dst, w});
+        hash_units++;
+        return dst;
+    }
+    uint64_t mix_in_length(uint64_t root, uint64_t len) { return op_hash(root, literal_u64(len)); }
+    // merkleize k operands over next_pow2(k) leaves (container / small vectors), padding with zero hashes
+    uint64_t small_tree(std::vector<uint64_t> nodes, uint32_t depth) {
+        if (nodes.empty()) return zero_op(depth);
+        for (uint32_t l = 0; l < depth; l++) {
+            std::vector<uint64_t> nx;
+            for (size_t i = 0; i < nodes.size(); i += 2)
+                nx.push_back(op_hash(nodes[i], i + 1 < nodes.size() ? nodes[i + 1] : zero_op(l)));
+            nodes.swap(nx);
+        }
+        return nodes[0];
+    }
+    uint64_t container(const std::vector<uint64_t>& fields) {
+        return small_tree(fields, ceil_log2(fields.size()));
+    }
+    // merkleize n chunks resident at d_in (16-B aligned) with limit 2^depth
+    uint64_t merkle_list(const uint8_t* d_in, uint64_t n, uint32_t depth) {
+        if (n == 0) return zero_op(depth);
+        if (n <= 8) {
+            std::vector<uint64_t> nodes;
+            for (uint64_t i = 0; i < n; i++) nodes.push_back(reinterpret_cast<uint64_t>(d_in + 32 * i));
+            uint32_t d0 = std::min(depth, ceil_log2(n));
+            uint64_t r = small_tree(nodes, d0);
+            for (uint32_t l = d0; l < depth; l++) r = op_hash(r, zero_op(l));
+            return r;
+        }
+        uint32_t level = 0;
+        const uint8_t* in = d_in;
+        size_t p = 0;
+        while (n > 1 && level < depth) {
+            uint32_t tl = std::min<uint32_t>(MAX_TILE_LOG, depth - level);
+            tl = std::min<uint32_t>(tl, ceil_log2(n));  // do not fold past the single-root level here
+            uint64_t n_out = ceil_div(n, 1ull << tl);
+            uint8_t* out = alloc(n_out * 32);
+            if (passes.size() <= p) passes.resize(p + 1);
+            MerkleSeg sg;
+            sg.in = in; sg.out = out; sg.n_in = n; sg.level_in = level; sg.tile_log = tl;
+            sg.cta_begin = 0; sg.n_tiles = (uint32_t)n_out;
+            passes[p++].push_back(sg);
+            // hashes actually performed: nodes with a valid left child at each level
+            for (uint32_t l = 1; l <= tl; l++) hash_units += ceil_div(n, 1ull << l);
+            level += tl;
+            n = n_out;
+            in = out;
+        }
+        uint64_t r = reinterpret_cast<uint64_t>(in);
+        for (uint32_t l = level; l < depth; l++) r = op_hash(r, zero_op(l));
+        return r;
+    }
+    uint8_t* leaf_kernel(int kind, const uint8_t* in, uint64_t n) {
+        uint8_t* out = alloc(std::max<uint64_t>(n, 1) * 32);
+        if (n) leaves.push_back({kind, in, out, n});
+        static const int units[4] = {8, 1, 3, 1};
+        hash_units += (uint64_t)units[kind] * n;
+        return out;
+    }
+};
+
+// Enqueue a finished plan on `s`.  Literals must already be in the arena.
+static int32_t plan_enqueue(Plan& pl, cudaStream_t s) {
+    for (const LeafLaunch& L : pl.leaves) {
+        switch (L.kind) {
+            case 0:
+                k_validator_roots<<<(unsigned)ceil_div(L.n, VAL_PER_CTA), VAL_PER_CTA, 0, s>>>(L.in, L.n, L.out);
+                break;
+            case 1:
+                k_record_roots<<<(unsigned)ceil_div(L.n, 128), 128, 0, s>>>(L.in, L.n, 0, L.out);
+                break;
+            case 2:
+                k_record_roots<<<(unsigned)ceil_div(L.n, 128), 128, 0, s>>>(L.in, L.n, 1, L.out);
+                break;
+            default:
+                k_hash_pairs<<<(unsigned)ceil_div(L.n, 256), 256, 0, s>>>(L.in, L.out, L.n);
+        }
+        count_launch();
+    }
+    for (auto& pass : pl.passes) {
+        for (size_t i = 0; i < pass.size(); i += MAX_SEGS) {
+            MerkleSegTable tab;
+            tab.n = (int)std::min<size_t>(MAX_SEGS, pass.size() - i);
+            uint32_t ctas = 0;
+            for (int k = 0; k < tab.n; k++) {
+                tab.s[k] = pass[i + k];
+                tab.s[k].cta_begin = ctas;
+                ctas += tab.s[k].n_tiles;
+            }
+            k_merkle_reduce<<<ctas, REDUCE_THREADS, 0, s>>>(tab);
+            count_launch();
+        }
+    }
+    if (pl.n_waves > 0) {
+        k_hash_program<<<1, PROG_THREADS, 0, s>>>(pl.d_ops, pl.d_waves, pl.n_waves);
+        count_launch();
+    }
+    LHB_CUDA(cudaGetLastError());
+    return LHB200_OK;
+}
+
+// Sort ops by wave, build wave table; returns host blobs to upload.
+static void plan_finalize_program(Plan& pl, std::vector<HashOp>& ops_sorted, std::vector<int32_t>& waves) {
+    int nw = 0;
+    for (int w : pl.op_wave) nw = std::max(nw, w + 1);
+    std::vector<std::vector<HashOp>> by(nw);
+    for (size_t i = 0; i < pl.ops.size(); i++) by[pl.op_wave[i]].push_back(pl.ops[i]);
+    waves.assign(1, 0);
+    for (int w = 0; w < nw; w++) {
+        for (auto& o : by[w]) ops_sorted.push_back(o);
+        waves.push_back((int32_t)ops_sorted.size());
+    }
+    pl.n_waves = nw;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A "session": dry-run the planner to size the arena, allocate, then plan for real.  `build` must be
+// deterministic in its allocation sequence.
+template <class F>
+static int32_t build_plan(Plan& pl, uint8_t* arena, size_t arena_bytes, size_t lit_cap, F&& build) {
+    pl = Plan();
+    pl.arena = arena;
+    pl.arena_bytes = arena_bytes;
+    pl.lit_cap = lit_cap;
+    pl.lit_off = 0;
+    pl.bump = lit_cap;  // literals first
+    build(pl);
+    if (pl.lit.size() > lit_cap) {
+        set_error("internal: literal block overflow (%zu > %zu)", pl.lit.size(), lit_cap);
+        return LHB200_EINVAL;
+    }
+    return LHB200_OK;
+}
+
+// upload literals + program; program blobs live at the end of the arena
+static int32_t plan_upload(Plan& pl, cudaStream_t s, std::vector<HashOp>& ops_sorted, std::vector<int32_t>& waves,
+                           void* h_stage) {
+    // h_stage: pinned host staging of at least lit + ops + waves bytes
+    uint8_t* h = static_cast<uint8_t*>(h_stage);
+    size_t o = 0;
+    if (!pl.lit.empty()) {
+        memcpy(h + o, pl.lit.data(), pl.lit.size());
+        LHB_CUDA(cudaMemcpyAsync(pl.arena + pl.lit_off, h + o, pl.lit.size(), cudaMemcpyHostToDevice, s));
+        o += align_up(pl.lit.size(), 256);
+    }
+    if (!ops_sorted.empty()) {
+        size_t nb = ops_sorted.size() * sizeof(HashOp);
+        pl.d_ops = reinterpret_cast<HashOp*>(pl.alloc(nb));
+        memcpy(h + o, ops_sorted.data(), nb);
+        LHB_CUDA(cudaMemcpyAsync(pl.d_ops, h + o, nb, cudaMemcpyHostToDevice, s));
+        o += align_up(nb, 256);
+        size_t wb = waves.size() * sizeof(int32_t);
+        pl.d_waves = reinterpret_cast<int32_t*>(pl.alloc(wb));
+        memcpy(h + o, waves.data(), wb);
+        LHB_CUDA(cudaMemcpyAsync(pl.d_waves, h + o, wb, cudaMemcpyHostToDevice, s));
+    }
+    return LHB200_OK;
+}
+
+// Generic runner for "one input blob -> one root" host entry points.
+//   stage(plan, d_in) describes the work given the device copy of the input.
+template <class F>
+static int32_t run_simple(const uint8_t* h_in, size_t in_bytes, uint8_t out[32], F&& describe) {
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    // pass 1: dry run to size
+    Plan dry;
+    const size_t lit_cap = 4096;
+    size_t in_pad = align_up(in_bytes + 32, 256);
+    uint64_t root_dry = 0;
+    build_plan(dry, nullptr, 0, lit_cap, [&](Plan& p) {
+        uint8_t* d_in = p.alloc(in_pad);
+        root_dry = describe(p, d_in);
+    });
+    size_t prog_bytes = align_up(dry.ops.size() * sizeof(HashOp), 256) + align_up((dry.ops.size() + 2) * 4, 256) + 512;
+    size_t need = align_up(dry.bump, 256) + prog_bytes + 256;
+    uint8_t* arena = static_cast<uint8_t*>(dev_scratch(need));
+    if (!arena) return LHB200_ENOMEM;
+    size_t stage_bytes = in_bytes + lit_cap + prog_bytes + 1024;
+    uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(stage_bytes));
+    if (!hst) return LHB200_ENOMEM;
+    Plan pl;
+    uint64_t root = 0;
+    uint8_t* d_in = nullptr;
+    int32_t rc = build_plan(pl, arena, need, lit_cap, [&](Plan& p) {
+        d_in = p.alloc(in_pad);
+        root = describe(p, d_in);
+    });
+    if (rc) return rc;
+    // H2D input (zero the padding tail so packed lists see zero-filled last chunks)
+    LHB_CUDA(cudaMemsetAsync(d_in + in_bytes / 256 * 256, 0, in_pad - in_bytes / 256 * 256, c.stream));
+    if (in_bytes) {
+        cudaPointerAttributes at;
+        bool pinned = cudaPointerGetAttributes(&at, h_in) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const void* src = h_in;
+        if (!pinned) {
+            memcpy(hst, h_in, in_bytes);
+            src = hst;
+        }
+        LHB_CUDA(cudaMemcpyAsync(d_in, src, in_bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    std::vector<HashOp> ops_sorted;
+    std::vector<int32_t> waves;
+    plan_finalize_program(pl, ops_sorted, waves);
+    rc = plan_upload(pl, c.stream, ops_sorted, waves, hst + align_up(in_bytes, 256));
+    if (rc) return rc;
+    rc = plan_enqueue(pl, c.stream);
+    if (rc) return rc;
+    if (root & OP_ZERO_FLAG) {
+        LHB_CUDA(cudaStreamSynchronize(c.stream));
+        memcpy(out, c.zero_hashes[root & 0xff], 32);
+        return LHB200_OK;
+    }
+    uint8_t* h_out = hst + stage_bytes - 64;
+    LHB_CUDA(cudaMemcpyAsync(h_out, reinterpret_cast<void*>(root), 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(out, h_out, 32);
+    return LHB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Deneb BeaconState (mainnet preset).  Fixed-part offsets: see DESIGN.md §3 / oracle for the derivation.
+namespace deneb {
+constexpr uint32_t FIXED = 2736653;
+constexpr uint32_t O_GENESIS_TIME = 0, O_GVR = 8, O_SLOT = 40, O_FORK = 48, O_LBH = 64, O_BLOCK_ROOTS = 176,
+                   O_STATE_ROOTS = 262320, O_HIST_OFF = 524464, O_ETH1_DATA = 524468, O_VOTES_OFF = 524540,
+                   O_DEPOSIT_INDEX = 524544, O_VAL_OFF = 524552, O_BAL_OFF = 524556, O_RANDAO = 524560,
+                   O_SLASHINGS = 2621712, O_PP_OFF = 2687248, O_CP_OFF = 2687252, O_JUST = 2687256,
+                   O_PJC = 2687257, O_CJC = 2687297, O_FC = 2687337, O_INACT_OFF = 2687377, O_CSC = 2687381,
+                   O_NSC = 2712005, O_LEPH_OFF = 2736629, O_NWI = 2736633, O_NWVI = 2736641, O_HS_OFF = 2736649;
+constexpr uint32_t SYNC_COMMITTEE_BYTES = 513 * 48;
+}  // namespace deneb
+
+static inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+}  // namespace lhb200
+
+struct lhb200_state {
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    lhb200::Plan plan;
+    uint64_t field_ops[28];
+    uint64_t root_op = 0;
+    uint8_t* d_result = nullptr;  // 29 * 32 bytes: root + field roots gathered
+};
+
+namespace lhb200 {
+
+struct StageCopy {
+    size_t src_off, nbytes;
+    uint8_t* dst;
+    size_t pad_to;  // zero-fill up to this many bytes at dst
+};
+
+// Describe the whole Deneb state.  `s` = host SSZ (read for offsets and small literal fields only).
+// Big fields are placed in the arena by `place(src_off, nbytes)` which records an H2D copy.
+static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vector<StageCopy>* copies,
+                              uint64_t field_ops[28], uint64_t* root_op) {
+    using namespace deneb;
+    if (len < FIXED) { set_error("BeaconStateDeneb SSZ shorter than its fixed part"); return LHB200_EINVAL; }
+    const uint32_t o_hist = rd32(s + O_HIST_OFF), o_votes = rd32(s + O_VOTES_OFF), o_val = rd32(s + O_VAL_OFF),
+                   o_bal = rd32(s + O_BAL_OFF), o_pp = rd32(s + O_PP_OFF), o_cp = rd32(s + O_CP_OFF),
+                   o_inact = rd32(s + O_INACT_OFF), o_leph = rd32(s + O_LEPH_OFF), o_hs = rd32(s + O_HS_OFF);
+    if (o_hist != FIXED || !(o_hist <= o_votes && o_votes <= o_val && o_val <= o_bal && o_bal <= o_pp &&
+                             o_pp <= o_cp && o_cp <= o_inact && o_inact <= o_leph && o_leph <= o_hs && o_hs <= len)) {
+        set_error("BeaconStateDeneb SSZ: inconsistent variable-part offsets");
+        return LHB200_EINVAL;
+    }
+    const uint64_t n_hist = (o_votes - o_hist) / 32, n_votes = (o_val - o_votes) / 72, n_val = (o_bal - o_val) / 121,
+                   n_bal = (o_pp - o_bal) / 8, n_pp = o_cp - o_pp, n_cp = o_inact - o_cp,
+                   n_inact = (o_leph - o_inact) / 8, leph_len = o_hs - o_leph, n_hs = (len - o_hs) / 64;
+    if ((o_votes - o_hist) % 32 || (o_val - o_votes) % 72 || (o_bal - o_val) % 121 || (o_pp - o_bal) % 8 ||
+        (o_leph - o_inact) % 8 || (len - o_hs) % 64 || leph_len < 584 || leph_len > 584 + 32 ||
+        rd32(s + o_leph + 436) != 584 || n_votes > 2048 || n_hist > (1u << 24) || n_hs > (1u << 24)) {
+        set_error("BeaconStateDeneb SSZ: malformed variable part");
+        return LHB200_EINVAL;
+    }
+    auto place = [&](size_t src_off, size_t nbytes) -> uint8_t* {
+        size_t padded = align_up(nbytes + 32, 256);
+        uint8_t* d = p.alloc(padded);
+        if (copies) copies->push_back({src_off, nbytes, d, padded});
+        return d;
+    };
+    auto chunk = [&](uint32_t off) { return p.literal(s + off); };
+    uint64_t* f = field_ops;
+    f[0] = p.literal_u64(rd64(s + O_GENESIS_TIME));
+    f[1] = chunk(O_GVR);
+    f[2] = p.literal_u64(rd64(s + O_SLOT));
+    f[3] = p.container({p.literal_bytes(s + O_FORK, 4), p.literal_bytes(s + O_FORK + 4, 4),
+                        p.literal_u64(rd64(s + O_FORK + 8))});
+    f[4] = p.container({p.literal_u64(rd64(s + O_LBH)), p.literal_u64(rd64(s + O_LBH + 8)), chunk(O_LBH + 16),
+                        chunk(O_LBH + 48), chunk(O_LBH + 80)});
+    f[5] = p.merkle_list(place(O_BLOCK_ROOTS, 8192 * 32), 8192, 13);
+    f[6] = p.merkle_list(place(O_STATE_ROOTS, 8192 * 32), 8192, 13);
+    f[7] = p.mix_in_length(p.merkle_list(place(o_hist, n_hist * 32), n_hist, 24), n_hist);
+    f[8] = p.container({chunk(O_ETH1_DATA), p.literal_u64(rd64(s + O_ETH1_DATA + 32)), chunk(O_ETH1_DATA + 40)});
+    f[9] = p.mix_in_length(p.merkle_list(p.leaf_kernel(2, place(o_votes, n_votes * 72), n_votes), n_votes, 11), n_votes);
+    f[10] = p.literal_u64(rd64(s + O_DEPOSIT_INDEX));
+    f[11] = p.mix_in_length(p.merkle_list(p.leaf_kernel(0, place(o_val, n_val * 121), n_val), n_val, 40), n_val);
+    f[12] = p.mix_in_length(p.merkle_list(place(o_bal, n_bal * 8), ceil_div(n_bal * 8, 32), 38), n_bal);
+    f[13] = p.merkle_list(place(O_RANDAO, 65536 * 32), 65536, 16);
+    f[14] = p.merkle_list(place(O_SLASHINGS, 8192 * 8), 2048, 11);
+    f[15] = p.mix_in_length(p.merkle_list(place(o_pp, n_pp), ceil_div(n_pp, 32), 35), n_pp);
+    f[16] = p.mix_in_length(p.merkle_list(place(o_cp, n_cp), ceil_div(n_cp, 32), 35), n_cp);
+    f[17] = p.literal_bytes(s + O_JUST, 1);
+    f[18] = p.container({p.literal_u64(rd64(s + O_PJC)), chunk(O_PJC + 8)});
+    f[19] = p.container({p.literal_u64(rd64(s + O_CJC)), chunk(O_CJC + 8)});
+    f[20] = p.container({p.literal_u64(rd64(s + O_FC)), chunk(O_FC + 8)});
+    f[21] = p.mix_in_length(p.merkle_list(place(o_inact, n_inact * 8), ceil_div(n_inact * 8, 32), 38), n_inact);
+    for (int k = 0; k < 2; k++) {
+        uint8_t* roots = p.leaf_kernel(1, place(k ? O_NSC : O_CSC, SYNC_COMMITTEE_BYTES), 513);
+        f[22 + k] = p.container({p.merkle_list(roots, 512, 9), reinterpret_cast<uint64_t>(roots + 512 * 32)});
+    }
+    {
+        const uint8_t* h = s + o_leph;
+        std::vector<uint64_t> bloom;
+        for (int i = 0; i < 8; i++) bloom.push_back(p.literal(h + 116 + 32 * i));
+        const uint64_t extra_len = leph_len - 584;
+        f[24] = p.container({p.literal(h), p.literal_bytes(h + 32, 20), p.literal(h + 52), p.literal(h + 84),
+                             p.small_tree(bloom, 3), p.literal(h + 372), p.literal_u64(rd64(h + 404)),
+                             p.literal_u64(rd64(h + 412)), p.literal_u64(rd64(h + 420)), p.literal_u64(rd64(h + 428)),
+                             p.mix_in_length(p.literal_bytes(h + 584, extra_len), extra_len), p.literal(h + 440),
+                             p.literal(h + 472), p.literal(h + 504), p.literal(h + 536),
+                             p.literal_u64(rd64(h + 568)), p.literal_u64(rd64(h + 576))});
+    }
+    f[25] = p.literal_u64(rd64(s + O_NWI));
+    f[26] = p.literal_u64(rd64(s + O_NWVI));
+    f[27] = p.mix_in_length(p.merkle_list(p.leaf_kernel(3, place(o_hs, n_hs * 64), n_hs), n_hs, 24), n_hs);
+    *root_op = p.container(std::vector<uint64_t>(f, f + 28));
+    return LHB200_OK;
+}
+
+__global__ void k_gather_nodes(const HashOp* __restrict__ srcs, int n, uint8_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    load_operand(srcs[i].a, w);
+    store_chunk(out + 32 * i, w);
+}
+
+}  // namespace lhb200
+
+using namespace lhb200;
+
+extern "C" {
+
+int32_t lhb200_hash_pairs(const uint8_t* in, uint8_t* out, uint64_t n) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!in || !out) { set_error("null buffer"); return LHB200_EINVAL; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(n * 96 + 512));
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(n * 96));
+    if (!d || !h) return LHB200_ENOMEM;
+    memcpy(h, in, n * 64);
+    LHB_CUDA(cudaMemcpyAsync(d, h, n * 64, cudaMemcpyHostToDevice, c.stream));
+    uint8_t* d_out = d + align_up(n * 64, 256);
+    k_hash_pairs<<<(unsigned)ceil_div(n, 256), 256, 0, c.stream>>>(d, d_out, n);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(h + n * 64, d_out, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(out, h + n * 64, n * 32);
+    return LHB200_OK;
+}
+
+int32_t lhb200_dev_hash_pairs(const void* d_in, void* d_out, uint64_t n, void* stream) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!d_in || !d_out || (reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) {
+        set_error("device buffers must be non-null and 16-byte aligned");
+        return LHB200_EINVAL;
+    }
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+    k_hash_pairs<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(static_cast<const uint8_t*>(d_in),
+                                                           static_cast<uint8_t*>(d_out), n);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    return LHB200_OK;
+}
+
+int32_t lhb200_merkleize(const uint8_t* chunks, uint64_t n_chunks, uint32_t depth, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    if (!out || (n_chunks && !chunks) || depth > 64 || (depth < 64 && n_chunks > (1ull << depth))) {
+        set_error("merkleize: bad arguments (n_chunks must be <= 2^depth, depth <= 64)");
+        return LHB200_EINVAL;
+    }
+    return run_simple(chunks, n_chunks * 32, out,
+                      [&](Plan& p, uint8_t* d_in) { return p.merkle_list(d_in, n_chunks, depth); });
+}
+
+int32_t lhb200_dev_merkleize(const void* d_chunks, uint64_t n_chunks, uint32_t depth, void* d_out32, void* stream) {
+    LHB_REQUIRE_READY();
+    if (!d_out32 || (n_chunks && !d_chunks) || (reinterpret_cast<uintptr_t>(d_chunks) & 15) ||
+        (reinterpret_cast<uintptr_t>(d_out32) & 15) || depth > 64 || (depth < 64 && n_chunks > (1ull << depth))) {
+        set_error("dev_merkleize: bad arguments");
+        return LHB200_EINVAL;
+    }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+    Plan dry;
+    uint64_t root = 0;
+    auto describe = [&](Plan& p) { root = p.merkle_list(static_cast<const uint8_t*>(d_chunks), n_chunks, depth); };
+    build_plan(dry, nullptr, 0, 256, describe);
+    size_t prog = align_up(dry.ops.size() * sizeof(HashOp), 256) + align_up((dry.ops.size() + 2) * 4, 256) + 512;
+    size_t need = align_up(dry.bump, 256) + prog + 256;
+    uint8_t* arena = static_cast<uint8_t*>(dev_scratch(need));
+    uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(prog + 1024));
+    if (!arena || !hst) return LHB200_ENOMEM;
+    Plan pl;
+    int32_t rc = build_plan(pl, arena, need, 256, describe);
+    if (rc) return rc;
+    std::vector<HashOp> ops_sorted;
+    std::vector<int32_t> waves;
+    plan_finalize_program(pl, ops_sorted, waves);
+    rc = plan_upload(pl, s, ops_sorted, waves, hst);
+    if (rc) return rc;
+    rc = plan_enqueue(pl, s);
+    if (rc) return rc;
+    if (root & OP_ZERO_FLAG) {
+        memcpy(hst + prog, c.zero_hashes[root & 0xff], 32);
+        LHB_CUDA(cudaMemcpyAsync(d_out32, hst + prog, 32, cudaMemcpyHostToDevice, s));
+    } else {
+        LHB_CUDA(cudaMemcpyAsync(d_out32, reinterpret_cast<void*>(root), 32, cudaMemcpyDeviceToDevice, s));
+    }
+    // the scratch arena and pinned staging are reused by the next call: finish before returning
+    LHB_CUDA(cudaStreamSynchronize(s));
+    return LHB200_OK;
+}
+
+int32_t lhb200_mix_in_length(const uint8_t root[32], uint64_t len, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    if (!root || !out) return LHB200_EINVAL;
+    return run_simple(root, 32, out, [&](Plan& p, uint8_t* d_in) {
+        return p.mix_in_length(reinterpret_cast<uint64_t>(d_in), len);
+    });
+}
+
+int32_t lhb200_zero_hash(uint32_t depth, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    if (depth > 64 || !out) return LHB200_EINVAL;
+    memcpy(out, ctx().zero_hashes[depth], 32);
+    return LHB200_OK;
+}
+
+int32_t lhb200_validators_root(const uint8_t* ssz, uint64_t n, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    if (!out || (n && !ssz) || n > (1ull << 40)) return LHB200_EINVAL;
+    return run_simple(ssz, n * 121, out, [&](Plan& p, uint8_t* d_in) {
+        return p.mix_in_length(p.merkle_list(p.leaf_kernel(0, d_in, n), n, 40), n);
+    });
+}
+
+int32_t lhb200_validator_roots(const uint8_t* ssz, uint64_t n, uint8_t* out_roots) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!ssz || !out_roots) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    size_t in_pad = align_up(n * 121, 256);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(in_pad + n * 32 + 256));
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(n * 121 + n * 32));
+    if (!d || !h) return LHB200_ENOMEM;
+    memcpy(h, ssz, n * 121);
+    LHB_CUDA(cudaMemcpyAsync(d, h, n * 121, cudaMemcpyHostToDevice, c.stream));
+    k_validator_roots<<<(unsigned)ceil_div(n, VAL_PER_CTA), VAL_PER_CTA, 0, c.stream>>>(d, n, d + in_pad);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(h + n * 121, d + in_pad, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(out_roots, h + n * 121, n * 32);
+    return LHB200_OK;
+}
+
+int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state** out) {
+    LHB_REQUIRE_READY();
+    if (!ssz || !out) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const size_t lit_cap = 16384;
+    Plan dry;
+    uint64_t fops[28], rop;
+    int32_t rc = LHB200_OK;
+    build_plan(dry, nullptr, 0, lit_cap, [&](Plan& p) { rc = describe_deneb(p, ssz, len, nullptr, fops, &rop); });
+    if (rc) return rc;
+    size_t prog = align_up(dry.ops.size() * sizeof(HashOp), 256) + align_up((dry.ops.size() + 2) * 4, 256) + 512;
+    size_t need = align_up(dry.bump, 256) + prog + 29 * 32 + 29 * sizeof(HashOp) + 1024;
+    std::unique_ptr<lhb200_state> st(new lhb200_state());
+    LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->arena), need));
+    st->arena_bytes = need;
+    std::vector<StageCopy> copies;
+    rc = build_plan(st->plan, st->arena, need, lit_cap, [&](Plan& p) {
+        rc = describe_deneb(p, ssz, len, &copies, st->field_ops, &st->root_op);
+    });
+    if (rc) { cudaFree(st->arena); return rc; }
+    // H2D: per-field copies into the aligned layout.  Pinned caller memory goes straight to the copy engine;
+    // pageable memory is bounced through the pinned staging slab.
+    cudaPointerAttributes at;
+    bool pinned = cudaPointerGetAttributes(&at, ssz) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const uint8_t* src = ssz;
+    std::vector<HashOp> ops_sorted;
+    std::vector<int32_t> waves;
+    plan_finalize_program(st->plan, ops_sorted, waves);
+    size_t stage_bytes = (pinned ? 0 : len) + lit_cap + prog + 29 * sizeof(HashOp) + 2048;
+    uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(stage_bytes));
+    if (!hst) { cudaFree(st->arena); return LHB200_ENOMEM; }
+    size_t ho = 0;
+    if (!pinned) {
+        memcpy(hst, ssz, len);
+        src = hst;
+        ho = align_up(len, 256);
+    }
+    for (const StageCopy& cp : copies) {
+        size_t z0 = cp.nbytes / 256 * 256;
+        LHB_CUDA(cudaMemsetAsync(cp.dst + z0, 0, cp.pad_to - z0, c.stream));
+        if (cp.nbytes)
+            LHB_CUDA(cudaMemcpyAsync(cp.dst, src + cp.src_off, cp.nbytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    rc = plan_upload(st->plan, c.stream, ops_sorted, waves, hst + ho);
+    if (rc) { cudaFree(st->arena); return rc; }
+    // gather table: root + 28 field roots -> contiguous result block
+    HashOp gath[29];
+    gath[0] = {0, st->root_op, 0};
+    for (int i = 0; i < 28; i++) gath[i + 1] = {0, st->field_ops[i], 0};
+    uint8_t* h_g = hst + stage_bytes - 29 * sizeof(HashOp) - 64;
+    memcpy(h_g, gath, sizeof gath);
+    uint8_t* d_g = st->plan.alloc(sizeof gath);
+    st->d_result = st->plan.alloc(29 * 32);
+    LHB_CUDA(cudaMemcpyAsync(d_g, h_g, sizeof gath, cudaMemcpyHostToDevice, c.stream));
+    st->plan.root_addr = reinterpret_cast<uint64_t>(d_g);
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    *out = st.release();
+    return LHB200_OK;
+}
+
+int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root) {
+    LHB_REQUIRE_READY();
+    if (!st) return LHB200_EINVAL;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+    int32_t rc = plan_enqueue(st->plan, s);
+    if (rc) return rc;
+    k_gather_nodes<<<1, 32, 0, s>>>(reinterpret_cast<const HashOp*>(st->plan.root_addr), 29, st->d_result);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    if (d_root) *d_root = st->d_result;
+    return LHB200_OK;
+}
+
+int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t* field_roots) {
+    LHB_REQUIRE_READY();
+    if (!st || !out) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    int32_t rc = lhb200_state_root_enqueue(st, c.stream, nullptr);
+    if (rc) return rc;
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(29 * 32));
+    if (!h) return LHB200_ENOMEM;
+    LHB_CUDA(cudaMemcpyAsync(h, st->d_result, 29 * 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(out, h, 32);
+    if (field_roots) memcpy(field_roots, h + 32, 28 * 32);
+    return LHB200_OK;
+}
+
+int32_t lhb200_state_release(lhb200_state* st) {
+    if (!st) return LHB200_OK;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (st->arena) cudaFree(st->arena);
+    delete st;
+    return LHB200_OK;
+}
+
+uint64_t lhb200_state_hash_units(const lhb200_state* st) { return st ? st->plan.hash_units : 0; }
+
+int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* field_roots) {
+    LHB_REQUIRE_READY();
+    lhb200_state* st = nullptr;
+    int32_t rc = lhb200_state_stage_deneb(ssz, len, &st);
+    if (rc) return rc;
+    rc = lhb200_state_root(st, out, field_roots);
+    lhb200_state_release(st);
+    return rc;
+}
+
+int32_t lhb200_merkle_tree_proof(const uint8_t* leaves, uint64_t n, uint32_t depth, uint64_t index, uint8_t root[32],
+                                 uint8_t* branch) {
+    LHB_REQUIRE_READY();
+    if (!root || (depth && !branch) || (n && !leaves) || depth > 32 || n > (1ull << depth) ||
+        (depth < 64 && index >= (1ull << depth))) {
+        set_error("merkle_tree_proof: bad arguments");
+        return LHB200_EINVAL;
+    }
+    // Level-by-level device build (every level materialised so siblings can be read back), then gather.
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    std::vector<uint64_t> cnt(depth + 1);
+    cnt[0] = n;
+    size_t total = align_up(std::max<uint64_t>(n, 1) * 32, 256);
+    for (uint32_t l = 1; l <= depth; l++) {
+        cnt[l] = ceil_div(cnt[l - 1], 2);
+        total += align_up(std::max<uint64_t>(cnt[l], 1) * 32, 256);
+    }
+    size_t gath_bytes = (depth + 1) * sizeof(HashOp);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(total + gath_bytes + (depth + 1) * 32 + 1024));
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(n * 32 + gath_bytes + (depth + 1) * 32 + 512));
+    if (!d || !h) return LHB200_ENOMEM;
+    if (n) {
+        memcpy(h, leaves, n * 32);
+        LHB_CUDA(cudaMemcpyAsync(d, h, n * 32, cudaMemcpyHostToDevice, c.stream));
+    }
+    std::vector<uint8_t*> lvl(depth + 1);
+    size_t off = 0;
+    for (uint32_t l = 0; l <= depth; l++) {
+        lvl[l] = d + off;
+        off += align_up(std::max<uint64_t>(cnt[l], 1) * 32, 256);
+    }
+    for (uint32_t l = 0; l < depth && cnt[l] > 0; l++) {
+        if (cnt[l] == 1 && l > 0 && cnt[l + 1] == 1) {
+            // lone node climbing a zero ladder: still one hash per level
+        }
+        MerkleSegTable tab;
+        tab.n = 1;
+        tab.s[0].in = lvl[l]; tab.s[0].out = lvl[l + 1]; tab.s[0].n_in = cnt[l]; tab.s[0].level_in = l;
+        tab.s[0].tile_log = 1; tab.s[0].cta_begin = 0; tab.s[0].n_tiles = (uint32_t)cnt[l + 1];
+        k_merkle_reduce<<<(unsigned)cnt[l + 1], REDUCE_THREADS, 0, c.stream>>>(tab);
+        count_launch();
+    }
+    LHB_CUDA(cudaGetLastError());
+    std::vector<HashOp> gath(depth + 1);
+    gath[0] = {0, n ? reinterpret_cast<uint64_t>(lvl[depth]) : (OP_ZERO_FLAG | depth), 0};
+    uint64_t idx = index;
+    for (uint32_t l = 0; l < depth; l++) {
+        uint64_t sib = idx ^ 1;
+        gath[l + 1] = {0, sib < cnt[l] ? reinterpret_cast<uint64_t>(lvl[l] + 32 * sib) : (OP_ZERO_FLAG | l), 0};
+        idx >>= 1;
+    }
+    uint8_t* h_g = h + align_up(n * 32, 256);
+    memcpy(h_g, gath.data(), gath_bytes);
+    uint8_t* d_g = d + total;
+    uint8_t* d_res = d_g + align_up(gath_bytes, 256);
+    LHB_CUDA(cudaMemcpyAsync(d_g, h_g, gath_bytes, cudaMemcpyHostToDevice, c.stream));
+    k_gather_nodes<<<(depth + 32) / 32, 32, 0, c.stream>>>(reinterpret_cast<const HashOp*>(d_g), depth + 1, d_res);
+    count_launch();
+    uint8_t* h_res = h_g + align_up(gath_bytes, 256);
+    LHB_CUDA(cudaMemcpyAsync(h_res, d_res, (depth + 1) * 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(root, h_res, 32);
+    if (depth) memcpy(branch, h_res + 32, depth * 32);
+    return LHB200_OK;
+}
+
+int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branches, uint32_t depth,
+                                    const uint64_t* indices, const uint8_t* roots, uint64_t n, uint8_t* ok) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!leaves || !indices || !roots || !ok || (depth && !branches)) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    size_t b_leaves = align_up(n * 32, 256), b_br = align_up(n * depth * 32 + 32, 256), b_idx = align_up(n * 8, 256),
+           b_roots = align_up(n * 32, 256), b_ok = align_up(n, 256);
+    size_t tot = b_leaves + b_br + b_idx + b_roots + b_ok;
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(tot));
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(tot));
+    if (!d || !h) return LHB200_ENOMEM;
+    memcpy(h, leaves, n * 32);
+    if (depth) memcpy(h + b_leaves, branches, n * depth * 32);
+    memcpy(h + b_leaves + b_br, indices, n * 8);
+    memcpy(h + b_leaves + b_br + b_idx, roots, n * 32);
+    LHB_CUDA(cudaMemcpyAsync(d, h, tot - b_ok, cudaMemcpyHostToDevice, c.stream));
+    k_verify_branches<<<(unsigned)ceil_div(n, 128), 128, 0, c.stream>>>(
+        d, d + b_leaves, depth, reinterpret_cast<const uint64_t*>(d + b_leaves + b_br), d + b_leaves + b_br + b_idx, n,
+        d + tot - b_ok);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(h + tot - b_ok, d + tot - b_ok, n, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(ok, h + tot - b_ok, n);
+    return LHB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""Host-side mirror of the tree_hash / ethereum_hashing surface Lighthouse's types call
+(tree_hash::{merkle_root, mix_in_length, BYTES_PER_CHUNK}, ethereum_hashing::{hash32_concat, ZERO_HASHES},
+BeaconState::update_tree_hash_cache — /root/reference/consensus/types/src/beacon_state.rs:2031-2038).
+Every function dispatches to the CUDA library through the C ABI; there is no CPU arithmetic here.
+"""
+import ctypes as C
+
+from . import _ffi
+from ._ffi import lib, check, buf
+
+BYTES_PER_CHUNK = 32
+HASHSIZE = 32
+VALIDATOR_SSZ_BYTES = 121
+
+
+def hash32_concat(a: bytes, b: bytes) -> bytes:
+    assert len(a) == 32 and len(b) == 32
+    return hash_pairs(a + b)
+
+
+def hash_pairs(data: bytes) -> bytes:
+    """n x 64 bytes -> n x 32 bytes (batch of ethereum_hashing::hash32_concat)."""
+    assert len(data) % 64 == 0
+    n = len(data) // 64
+    out = C.create_string_buffer(max(n * 32, 1))
+    p, keep = buf(data)
+    check(lib.lhb200_hash_pairs(p, out, n), "lhb200_hash_pairs")
+    return out.raw[: n * 32]
+
+
+def zero_hash(depth: int) -> bytes:
+    out = C.create_string_buffer(32)
+    check(lib.lhb200_zero_hash(depth, out), "lhb200_zero_hash")
+    return out.raw
+
+
+def merkleize_chunks(chunks: bytes, depth: int) -> bytes:
+    """merkleize(chunks, limit = 2**depth)."""
+    assert len(chunks) % 32 == 0
+    out = C.create_string_buffer(32)
+    p, keep = buf(chunks)
+    check(lib.lhb200_merkleize(p, len(chunks) // 32, depth, out), "lhb200_merkleize")
+    return out.raw
+
+
+def merkle_root(data: bytes, minimum_leaf_count: int = 0) -> bytes:
+    """tree_hash::merkle_root(bytes, minimum_leaf_count): zero-pad to whole chunks, tree height from
+    max(next_pow2(#chunks), next_pow2(minimum_leaf_count)) (used at crypto/bls/src/macros.rs:24)."""
+    n = max((len(data) + 31) // 32, 1)
+    padded = data + b"\0" * (n * 32 - len(data))
+    leaves = max(n, minimum_leaf_count, 1)
+    depth = (leaves - 1).bit_length()
+    return merkleize_chunks(padded, depth)
+
+
+def mix_in_length(root: bytes, length: int) -> bytes:
+    out = C.create_string_buffer(32)
+    p, keep = buf(root)
+    check(lib.lhb200_mix_in_length(p, length, out), "lhb200_mix_in_length")
+    return out.raw
+
+
+def validators_root(ssz: bytes) -> bytes:
+    """hash_tree_root(List[Validator, 2**40]) from concatenated 121-byte SSZ validators."""
+    assert len(ssz) % VALIDATOR_SSZ_BYTES == 0
+    out = C.create_string_buffer(32)
+    p, keep = buf(ssz)
+    check(lib.lhb200_validators_root(p, len(ssz) // VALIDATOR_SSZ_BYTES, out), "lhb200_validators_root")
+    return out.raw
+
+
+def validator_roots(ssz: bytes) -> bytes:
+    n = len(ssz) // VALIDATOR_SSZ_BYTES
+    out = C.create_string_buffer(max(32 * n, 1))
+    p, keep = buf(ssz)
+    check(lib.lhb200_validator_roots(p, n, out), "lhb200_validator_roots")
+    return out.raw[: 32 * n]
+
+
+def beacon_state_root_deneb(ssz, want_field_roots=False):
+    """BeaconState::update_tree_hash_cache (cold) for BeaconStateDeneb SSZ bytes."""
+    out = C.create_string_buffer(32)
+    fr = C.create_string_buffer(28 * 32) if want_field_roots else None
+    p, keep = buf(ssz)
+    n = len(ssz) if isinstance(ssz, (bytes, bytearray)) else keep.nbytes
+    check(lib.lhb200_beacon_state_root_deneb(p, n, out, fr), "lhb200_beacon_state_root_deneb")
+    if want_field_roots:
+        return out.raw, [fr.raw[32 * i: 32 * i + 32] for i in range(28)]
+    return out.raw
+
+
+class ResidentState:
+    """A BeaconStateDeneb staged once into HBM and hashed from there."""
+
+    def __init__(self, ssz):
+        self._h = C.c_void_p()
+        p, keep = buf(ssz)
+        n = len(ssz) if isinstance(ssz, (bytes, bytearray)) else keep.nbytes
+        check(lib.lhb200_state_stage_deneb(p, n, C.byref(self._h)), "lhb200_state_stage_deneb")
+
+    def root(self, want_field_roots=False):
+        out = C.create_string_buffer(32)
+        fr = C.create_string_buffer(28 * 32) if want_field_roots else None
+        check(lib.lhb200_state_root(self._h, out, fr), "lhb200_state_root")
+        if want_field_roots:
+            return out.raw, [fr.raw[32 * i: 32 * i + 32] for i in range(28)]
+        return out.raw
+
+    def enqueue(self, stream=None):
+        d = C.c_void_p()
+        check(lib.lhb200_state_root_enqueue(self._h, stream, C.byref(d)), "lhb200_state_root_enqueue")
+        return d.value
+
+    @property
+    def hash_units(self):
+        return lib.lhb200_state_hash_units(self._h)
+
+    def release(self):
+        if self._h:
+            lib.lhb200_state_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -1,0 +1,535 @@
+/*
+ * oracle/ssz_sha256.c — TEST INFRASTRUCTURE ONLY (CPU oracle / CPU baseline).
+ *
+ * Plain-C restatement of the SHA-256 Merkle `tree_hash_root` path of sigp/lighthouse v5.3.0.
+ * Nothing in lighthouse_b200/ (the product) may link, import or call this file; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * The arithmetic of this path lives in crates that are NOT vendored under /root/reference
+ * (Cargo.lock pins): ethereum_hashing 0.6.0 (sha2 0.10.8 / ring 0.17.8), tree_hash 0.6.0,
+ * tree_hash_derive 0.6.0, milhouse 0.1.0, ssz_types 0.6.0.  Their published algorithm (FIPS 180-4
+ * SHA-256 + the consensus-spec SSZ merkleization rules) is restated here and anchored on the
+ * reference's own call sites and vectors:
+ *   hash32_concat / ZERO_HASHES ........ consensus/merkle_proof/src/lib.rs:1,91,166
+ *   MerkleTree::create .................. consensus/merkle_proof/src/lib.rs:68-99
+ *   merkle_root_from_branch ............. consensus/merkle_proof/src/lib.rs:372-389
+ *   Validator (8 leaves) ................ consensus/types/src/validator.rs:25-35
+ *   48/96-byte BLS blob roots ........... crypto/bls/src/macros.rs:4-27
+ *   BeaconState (Deneb, 28 fields) ...... consensus/types/src/beacon_state.rs:339-490, :2031-2038
+ *   ExecutionPayloadHeaderDeneb ......... consensus/types/src/execution_payload_header.rs:46-87
+ *   mainnet sizes ....................... consensus/types/src/eth_spec.rs:389-430
+ * Pinned by (tests/test_oracle_merkle.py): hashlib SHA-256, the genesis_validators_root embedded in the
+ * reference's vendored mainnet/sepolia/gnosis genesis.ssz.zip, and deposit_message_root/deposit_data_root
+ * of validator_manager/test_vectors.  Full Deneb BeaconState root: parity unpinned in-tree (only EF
+ * ssz_static pins it; not on disk) — pinned transitively through the per-field rules above.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#include <cpuid.h>
+#endif
+
+#define EXPORT __attribute__((visibility("default")))
+
+
+/* ------------------------------------------------------------------ tiny pthread parallel-for
+ * (the image has no libgomp).  Mirrors rayon::join fan-out in milhouse / blst's pool: static ranges. */
+#include <pthread.h>
+#include <unistd.h>
+static int g_threads = 1;
+typedef void (*range_fn)(uint64_t lo, uint64_t hi, void *ctx);
+struct par_job { range_fn fn; void *ctx; uint64_t lo, hi; };
+static void *par_tramp(void *p) { struct par_job *j = (struct par_job *)p; j->fn(j->lo, j->hi, j->ctx); return 0; }
+void orc_par_for(uint64_t n, uint64_t min_grain, range_fn fn, void *ctx) {
+    int t = g_threads;
+    if (t < 1) t = 1;
+    if (n < min_grain * 2 || t == 1) { fn(0, n, ctx); return; }
+    if ((uint64_t)t > n / min_grain) t = (int)(n / min_grain);
+    pthread_t th[256]; struct par_job jb[256];
+    if (t > 256) t = 256;
+    for (int i = 0; i < t; i++) {
+        jb[i].fn = fn; jb[i].ctx = ctx; jb[i].lo = n * i / t; jb[i].hi = n * (i + 1) / t;
+        if (i) pthread_create(&th[i], 0, par_tramp, &jb[i]);
+    }
+    par_tramp(&jb[0]);
+    for (int i = 1; i < t; i++) pthread_join(th[i], 0);
+}
+EXPORT int orc_num_threads(void) { return g_threads; }
+EXPORT int orc_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+EXPORT void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+
+/* ------------------------------------------------------------------ SHA-256 (FIPS 180-4) */
+static const uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+static const uint32_t IV256[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,
+                                  0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+
+static inline uint32_t ror32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+static void compress_plain(uint32_t st[8], const uint8_t blk[64]) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++)
+        w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) |
+               blk[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = ror32(w[i - 15], 7) ^ ror32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = ror32(w[i - 2], 17) ^ ror32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    for (int i = 0; i < 64; i++) {
+        uint32_t S1 = ror32(e, 6) ^ ror32(e, 11) ^ ror32(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = h + S1 + ch + K256[i] + w[i];
+        uint32_t S0 = ror32(a, 2) ^ ror32(a, 13) ^ ror32(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+#if defined(__x86_64__)
+/* SHA-NI path: what ethereum_hashing selects on this class of CPU (lighthouse/src/main.rs:15,41 checks
+ * have_sha_extensions()).  Used so the CPU baseline is not handicapped; verified against compress_plain. */
+__attribute__((target("sha,sse4.1,ssse3"))) static void compress_shani(uint32_t st[8], const uint8_t blk[64]) {
+    const __m128i MASK = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i TMP = _mm_loadu_si128((const __m128i *)&st[0]);
+    __m128i STATE1 = _mm_loadu_si128((const __m128i *)&st[4]);
+    TMP = _mm_shuffle_epi32(TMP, 0xB1);          /* CDAB */
+    STATE1 = _mm_shuffle_epi32(STATE1, 0x1B);    /* EFGH */
+    __m128i STATE0 = _mm_alignr_epi8(TMP, STATE1, 8); /* ABEF */
+    STATE1 = _mm_blend_epi16(STATE1, TMP, 0xF0);      /* CDGH */
+    __m128i ABEF_SAVE = STATE0, CDGH_SAVE = STATE1;
+    __m128i M[4];
+    for (int i = 0; i < 4; i++) M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(blk + 16 * i)), MASK);
+    for (int r = 0; r < 16; r++) {
+        __m128i MSG = _mm_add_epi32(M[r & 3], _mm_loadu_si128((const __m128i *)&K256[4 * r]));
+        STATE1 = _mm_sha256rnds2_epu32(STATE1, STATE0, MSG);
+        if (r >= 3 && r < 15) { /* finish w[4(r+1)..] = msg2(msg1(M[r+1]) + alignr(M[r],M[r-1]), M[r]) */
+            __m128i T = _mm_alignr_epi8(M[r & 3], M[(r - 1) & 3], 4);
+            M[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(M[(r + 1) & 3], T), M[r & 3]);
+        }
+        MSG = _mm_shuffle_epi32(MSG, 0x0E);
+        STATE0 = _mm_sha256rnds2_epu32(STATE0, STATE1, MSG);
+        if (r >= 1 && r < 13) M[(r - 1) & 3] = _mm_sha256msg1_epu32(M[(r - 1) & 3], M[r & 3]);
+    }
+    STATE0 = _mm_add_epi32(STATE0, ABEF_SAVE);
+    STATE1 = _mm_add_epi32(STATE1, CDGH_SAVE);
+    TMP = _mm_shuffle_epi32(STATE0, 0x1B);       /* FEBA */
+    STATE1 = _mm_shuffle_epi32(STATE1, 0xB1);    /* DCHG */
+    STATE0 = _mm_blend_epi16(TMP, STATE1, 0xF0); /* DCBA */
+    STATE1 = _mm_alignr_epi8(STATE1, TMP, 8);    /* ABEF */
+    _mm_storeu_si128((__m128i *)&st[0], STATE0);
+    _mm_storeu_si128((__m128i *)&st[4], STATE1);
+}
+#endif
+
+static int g_use_shani = -1;
+static void (*g_compress)(uint32_t *, const uint8_t *) = compress_plain;
+
+EXPORT int orc_sha_backend(int force_plain) {
+    /* returns 1 if SHA-NI is in use */
+    g_compress = compress_plain;
+    g_use_shani = 0;
+#if defined(__x86_64__)
+    if (!force_plain) {
+        unsigned a, b, c, d;
+        if (__get_cpuid_count(7, 0, &a, &b, &c, &d) && (b & (1u << 29))) {
+            g_compress = compress_shani;
+            g_use_shani = 1;
+        }
+    }
+#endif
+    return g_use_shani;
+}
+
+static inline void ensure_backend(void) {
+    if (g_use_shani < 0) orc_sha_backend(0);
+}
+
+static void put_be32(uint8_t *p, uint32_t v) {
+    p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v;
+}
+
+/* generic SHA-256 of a byte string (ethereum_hashing::hash) */
+EXPORT void orc_sha256(const uint8_t *msg, uint64_t len, uint8_t out[32]) {
+    ensure_backend();
+    uint32_t st[8];
+    memcpy(st, IV256, sizeof st);
+    uint64_t i = 0;
+    for (; i + 64 <= len; i += 64) g_compress(st, msg + i);
+    uint8_t blk[128];
+    memset(blk, 0, sizeof blk);
+    uint64_t rem = len - i;
+    memcpy(blk, msg + i, rem);
+    blk[rem] = 0x80;
+    int nb = (rem + 9 > 64) ? 2 : 1;
+    uint64_t bits = len * 8;
+    for (int k = 0; k < 8; k++) blk[64 * nb - 1 - k] = (uint8_t)(bits >> (8 * k));
+    g_compress(st, blk);
+    if (nb == 2) g_compress(st, blk + 64);
+    for (int k = 0; k < 8; k++) put_be32(out + 4 * k, st[k]);
+}
+
+/* ethereum_hashing::hash32_concat(a, b) = SHA256(a || b): one data block + one constant padding block */
+static const uint8_t PAD64[64] = {0x80, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                  0,    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                  0,    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x02, 0x00};
+
+static inline void hash64(const uint8_t in[64], uint8_t out[32]) {
+    uint32_t st[8];
+    memcpy(st, IV256, sizeof st);
+    g_compress(st, in);
+    g_compress(st, PAD64);
+    for (int k = 0; k < 8; k++) put_be32(out + 4 * k, st[k]);
+}
+
+EXPORT void orc_hash32_concat(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+    ensure_backend();
+    uint8_t in[64];
+    memcpy(in, a, 32);
+    memcpy(in + 32, b, 32);
+    hash64(in, out);
+}
+
+struct hp_ctx { const uint8_t *in; uint8_t *out; };
+static void hp_range(uint64_t lo, uint64_t hi, void *c) {
+    struct hp_ctx *x = (struct hp_ctx *)c;
+    for (uint64_t i = lo; i < hi; i++) hash64(x->in + 64 * i, x->out + 32 * i);
+}
+EXPORT void orc_hash_pairs(const uint8_t *in, uint8_t *out, uint64_t n) {
+    ensure_backend();
+    struct hp_ctx c = {in, out};
+    orc_par_for(n, 2048, hp_range, &c);
+}
+
+/* ZERO_HASHES[d] : root of an all-zero subtree of height d (merkle_proof/src/lib.rs:166) */
+#define MAX_ZERO 65
+static uint8_t ZH[MAX_ZERO][32];
+static int zh_ready = 0;
+static void ensure_zero(void) {
+    ensure_backend();
+    if (zh_ready) return;
+    memset(ZH[0], 0, 32);
+    for (int d = 0; d + 1 < MAX_ZERO; d++) orc_hash32_concat(ZH[d], ZH[d], ZH[d + 1]);
+    zh_ready = 1;
+}
+EXPORT void orc_zero_hash(uint32_t depth, uint8_t out[32]) {
+    ensure_zero();
+    memcpy(out, ZH[depth], 32);
+}
+
+/* merkleize(chunks, limit=2^depth): pad every level's odd tail with zero[level]; empty => zero[depth].
+ * `work` (n*32 bytes scratch) may alias nothing. */
+EXPORT void orc_merkleize(const uint8_t *chunks, uint64_t n, uint32_t depth, uint8_t out[32]) {
+    ensure_zero();
+    if (n == 0) { memcpy(out, ZH[depth], 32); return; }
+    uint8_t *cur = (uint8_t *)malloc((size_t)(n + 1) * 32);
+    memcpy(cur, chunks, (size_t)n * 32);
+    uint64_t cnt = n;
+    for (uint32_t lvl = 0; lvl < depth; lvl++) {
+        if (cnt == 1) { /* lone node: climb with zero siblings */
+            orc_hash32_concat(cur, ZH[lvl], cur);
+            continue;
+        }
+        if (cnt & 1) { memcpy(cur + cnt * 32, ZH[lvl], 32); cnt++; }
+        uint64_t half = cnt / 2;
+        /* in-place is safe when processed in increasing order serially; for the parallel case use a copy */
+        if (half > 4096) {
+            uint8_t *nxt = (uint8_t *)malloc((size_t)(half + 1) * 32);
+            struct hp_ctx c = {cur, nxt};
+            orc_par_for(half, 2048, hp_range, &c);
+            free(cur);
+            cur = nxt;
+        } else {
+            for (uint64_t i = 0; i < half; i++) {
+                uint8_t tmp[32];
+                hash64(cur + 64 * i, tmp);
+                memcpy(cur + 32 * i, tmp, 32);
+            }
+        }
+        cnt = half;
+    }
+    memcpy(out, cur, 32);
+    free(cur);
+}
+
+EXPORT void orc_mix_in_length(const uint8_t root[32], uint64_t len, uint8_t out[32]) {
+    uint8_t l[32];
+    memset(l, 0, 32);
+    for (int k = 0; k < 8; k++) l[k] = (uint8_t)(len >> (8 * k));
+    orc_hash32_concat(root, l, out);
+}
+
+static uint32_t ceil_log2(uint64_t x) {
+    uint32_t d = 0;
+    while (((uint64_t)1 << d) < x) d++;
+    return d;
+}
+
+/* packed basic list/vector: bytes are the little-endian serialisation; last chunk zero padded */
+EXPORT void orc_merkleize_bytes(const uint8_t *bytes, uint64_t nbytes, uint32_t depth, uint8_t out[32]) {
+    uint64_t n = (nbytes + 31) / 32;
+    uint8_t *buf = (uint8_t *)calloc((size_t)(n ? n : 1), 32);
+    memcpy(buf, bytes, (size_t)nbytes);
+    orc_merkleize(buf, n, depth, out);
+    free(buf);
+}
+
+/* 48-byte pubkey root: merkle_root of 2 chunks (crypto/bls/src/macros.rs:18-25) */
+static void pubkey_root(const uint8_t pk[48], uint8_t out[32]) {
+    uint8_t in[64];
+    memset(in, 0, 64);
+    memcpy(in, pk, 48);
+    hash64(in, out);
+}
+EXPORT void orc_pubkey_root(const uint8_t pk[48], uint8_t out[32]) { ensure_backend(); pubkey_root(pk, out); }
+
+/* Validator: 121-byte SSZ -> 8 leaves -> root (consensus/types/src/validator.rs:25-35) */
+static void validator_root(const uint8_t *v, uint8_t out[32]) {
+    uint8_t leaf[8][32];
+    memset(leaf, 0, sizeof leaf);
+    pubkey_root(v, leaf[0]);
+    memcpy(leaf[1], v + 48, 32);
+    memcpy(leaf[2], v + 80, 8);
+    leaf[3][0] = v[88];
+    memcpy(leaf[4], v + 89, 8);
+    memcpy(leaf[5], v + 97, 8);
+    memcpy(leaf[6], v + 105, 8);
+    memcpy(leaf[7], v + 113, 8);
+    uint8_t l1[4][32], l2[2][32];
+    for (int i = 0; i < 4; i++) hash64((const uint8_t *)leaf + 64 * i, l1[i]);
+    for (int i = 0; i < 2; i++) hash64((const uint8_t *)l1 + 64 * i, l2[i]);
+    hash64((const uint8_t *)l2, out);
+}
+EXPORT void orc_validator_root(const uint8_t v[121], uint8_t out[32]) { ensure_backend(); validator_root(v, out); }
+
+static void vr_range(uint64_t lo, uint64_t hi, void *c) {
+    struct hp_ctx *x = (struct hp_ctx *)c;
+    for (uint64_t i = lo; i < hi; i++) validator_root(x->in + 121 * i, x->out + 32 * i);
+}
+EXPORT void orc_validator_roots(const uint8_t *ssz, uint64_t n, uint8_t *out) {
+    ensure_backend();
+    struct hp_ctx c = {ssz, out};
+    orc_par_for(n, 512, vr_range, &c);
+}
+
+/* List[Validator, 2^40] */
+EXPORT void orc_validators_root(const uint8_t *ssz, uint64_t n, uint8_t out[32]) {
+    uint8_t *roots = (uint8_t *)malloc((size_t)(n ? n : 1) * 32);
+    orc_validator_roots(ssz, n, roots);
+    uint8_t r[32];
+    orc_merkleize(roots, n, 40, r);
+    orc_mix_in_length(r, n, out);
+    free(roots);
+}
+
+/* container of k field roots -> merkleize over next_pow2(k) */
+static void container_root(uint8_t (*leaves)[32], uint32_t k, uint8_t out[32]) {
+    orc_merkleize(&leaves[0][0], k, ceil_log2(k), out);
+}
+
+static void u64_chunk(const uint8_t *p, uint8_t out[32]) { memset(out, 0, 32); memcpy(out, p, 8); }
+static uint32_t rd32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+static void checkpoint_root(const uint8_t *p, uint8_t out[32]) { /* {epoch u64, root H256} */
+    uint8_t l[2][32];
+    u64_chunk(p, l[0]);
+    memcpy(l[1], p + 8, 32);
+    container_root(l, 2, out);
+}
+static void eth1_data_root(const uint8_t *p, uint8_t out[32]) { /* {H256, u64, H256} (eth1_data.rs:27) */
+    uint8_t l[3][32];
+    memcpy(l[0], p, 32);
+    u64_chunk(p + 32, l[1]);
+    memcpy(l[2], p + 40, 32);
+    container_root(l, 3, out);
+}
+static void sync_committee_root(const uint8_t *p, uint8_t out[32]) { /* {Vector[pubkey,512], pubkey} */
+    uint8_t *pk = (uint8_t *)malloc(512 * 32);
+    for (int i = 0; i < 512; i++) pubkey_root(p + 48 * i, pk + 32 * i);
+    uint8_t l[2][32];
+    orc_merkleize(pk, 512, 9, l[0]);
+    pubkey_root(p + 48 * 512, l[1]);
+    container_root(l, 2, out);
+    free(pk);
+}
+
+/* ExecutionPayloadHeaderDeneb: 17 fields (execution_payload_header.rs:46-87) */
+static int exec_header_root(const uint8_t *p, uint64_t len, uint8_t out[32]) {
+    if (len < 584) return -1;
+    uint8_t l[17][32];
+    memset(l, 0, sizeof l);
+    memcpy(l[0], p, 32);                       /* parent_hash */
+    memcpy(l[1], p + 32, 20);                  /* fee_recipient (Address) */
+    memcpy(l[2], p + 52, 32);                  /* state_root */
+    memcpy(l[3], p + 84, 32);                  /* receipts_root */
+    orc_merkleize(p + 116, 8, 3, l[4]);        /* logs_bloom: 256 B = 8 chunks */
+    memcpy(l[5], p + 372, 32);                 /* prev_randao */
+    memcpy(l[6], p + 404, 8);                  /* block_number */
+    memcpy(l[7], p + 412, 8);                  /* gas_limit */
+    memcpy(l[8], p + 420, 8);                  /* gas_used */
+    memcpy(l[9], p + 428, 8);                  /* timestamp */
+    uint32_t off = rd32(p + 436);              /* extra_data offset */
+    memcpy(l[11], p + 440, 32);                /* base_fee_per_gas (u256 LE) */
+    memcpy(l[12], p + 472, 32);                /* block_hash */
+    memcpy(l[13], p + 504, 32);                /* transactions_root */
+    memcpy(l[14], p + 536, 32);                /* withdrawals_root */
+    memcpy(l[15], p + 568, 8);                 /* blob_gas_used */
+    memcpy(l[16], p + 576, 8);                 /* excess_blob_gas */
+    if (off != 584 || len - off > 32) return -2;
+    uint8_t r[32];
+    orc_merkleize_bytes(p + off, len - off, 0, r); /* List[u8,32]: one chunk */
+    orc_mix_in_length(r, len - off, l[10]);
+    container_root(l, 17, out);
+    return 0;
+}
+
+#define DENEB_FIXED 2736653u
+
+/* hash_tree_root(BeaconStateDeneb) from its SSZ bytes (mainnet preset). field_roots (28*32) optional. */
+EXPORT int orc_beacon_state_root_deneb(const uint8_t *s, uint64_t len, uint8_t out[32], uint8_t *field_roots) {
+    ensure_zero();
+    if (len < DENEB_FIXED) return -1;
+    uint8_t f[28][32];
+    memset(f, 0, sizeof f);
+    uint32_t o_hist = rd32(s + 524464), o_votes = rd32(s + 524540), o_val = rd32(s + 524552),
+             o_bal = rd32(s + 524556), o_pp = rd32(s + 2687248), o_cp = rd32(s + 2687252),
+             o_inact = rd32(s + 2687377), o_leph = rd32(s + 2736629), o_hs = rd32(s + 2736649);
+    if (o_hist != DENEB_FIXED || !(o_hist <= o_votes && o_votes <= o_val && o_val <= o_bal && o_bal <= o_pp &&
+                                   o_pp <= o_cp && o_cp <= o_inact && o_inact <= o_leph && o_leph <= o_hs &&
+                                   o_hs <= len))
+        return -2;
+    u64_chunk(s + 0, f[0]);
+    memcpy(f[1], s + 8, 32);
+    u64_chunk(s + 40, f[2]);
+    { /* Fork {[u8;4],[u8;4],u64} (fork.rs:26) */
+        uint8_t l[3][32];
+        memset(l, 0, sizeof l);
+        memcpy(l[0], s + 48, 4);
+        memcpy(l[1], s + 52, 4);
+        memcpy(l[2], s + 56, 8);
+        container_root(l, 3, f[3]);
+    }
+    { /* BeaconBlockHeader {slot, proposer_index, parent_root, state_root, body_root} */
+        uint8_t l[5][32];
+        u64_chunk(s + 64, l[0]);
+        u64_chunk(s + 72, l[1]);
+        memcpy(l[2], s + 80, 32);
+        memcpy(l[3], s + 112, 32);
+        memcpy(l[4], s + 144, 32);
+        container_root(l, 5, f[4]);
+    }
+    orc_merkleize(s + 176, 8192, 13, f[5]);
+    orc_merkleize(s + 262320, 8192, 13, f[6]);
+    { /* historical_roots: List[H256, 2^24] */
+        uint64_t n = (o_votes - o_hist) / 32;
+        uint8_t r[32];
+        orc_merkleize(s + o_hist, n, 24, r);
+        orc_mix_in_length(r, n, f[7]);
+    }
+    eth1_data_root(s + 524468, f[8]);
+    { /* eth1_data_votes: List[Eth1Data, 2048] */
+        uint64_t n = (o_val - o_votes) / 72;
+        uint8_t *r = (uint8_t *)malloc((size_t)(n ? n : 1) * 32), t[32];
+        for (uint64_t i = 0; i < n; i++) eth1_data_root(s + o_votes + 72 * i, r + 32 * i);
+        orc_merkleize(r, n, 11, t);
+        orc_mix_in_length(t, n, f[9]);
+        free(r);
+    }
+    u64_chunk(s + 524544, f[10]);
+    orc_validators_root(s + o_val, (o_bal - o_val) / 121, f[11]);
+    { /* balances: List[u64, 2^40] -> chunk depth 38 */
+        uint64_t n = (o_pp - o_bal) / 8;
+        uint8_t r[32];
+        orc_merkleize_bytes(s + o_bal, n * 8, 38, r);
+        orc_mix_in_length(r, n, f[12]);
+    }
+    orc_merkleize(s + 524560, 65536, 16, f[13]);
+    orc_merkleize_bytes(s + 2621712, 65536, 11, f[14]); /* slashings: 8192 u64 = 2048 chunks */
+    { /* participation: List[u8, 2^40] -> chunk depth 35 */
+        uint64_t n = o_cp - o_pp;
+        uint8_t r[32];
+        orc_merkleize_bytes(s + o_pp, n, 35, r);
+        orc_mix_in_length(r, n, f[15]);
+        n = o_inact - o_cp;
+        orc_merkleize_bytes(s + o_cp, n, 35, r);
+        orc_mix_in_length(r, n, f[16]);
+    }
+    f[17][0] = s[2687256]; /* Bitvector[4] */
+    checkpoint_root(s + 2687257, f[18]);
+    checkpoint_root(s + 2687297, f[19]);
+    checkpoint_root(s + 2687337, f[20]);
+    {
+        uint64_t n = (o_leph - o_inact) / 8;
+        uint8_t r[32];
+        orc_merkleize_bytes(s + o_inact, n * 8, 38, r);
+        orc_mix_in_length(r, n, f[21]);
+    }
+    sync_committee_root(s + 2687381, f[22]);
+    sync_committee_root(s + 2712005, f[23]);
+    if (exec_header_root(s + o_leph, o_hs - o_leph, f[24])) return -3;
+    u64_chunk(s + 2736633, f[25]);
+    u64_chunk(s + 2736641, f[26]);
+    { /* historical_summaries: List[{H256,H256}, 2^24] */
+        uint64_t n = (len - o_hs) / 64;
+        uint8_t *r = (uint8_t *)malloc((size_t)(n ? n : 1) * 32), t[32];
+        orc_hash_pairs(s + o_hs, r, n);
+        orc_merkleize(r, n, 24, t);
+        orc_mix_in_length(t, n, f[27]);
+        free(r);
+    }
+    if (field_roots) memcpy(field_roots, f, sizeof f);
+    container_root(f, 28, out);
+    return 0;
+}
+
+/* merkle_root_from_branch (consensus/merkle_proof/src/lib.rs:372-389) */
+EXPORT void orc_merkle_root_from_branch(const uint8_t leaf[32], const uint8_t *branch, uint32_t depth, uint64_t index,
+                                        uint8_t out[32]) {
+    uint8_t cur[32];
+    memcpy(cur, leaf, 32);
+    for (uint32_t i = 0; i < depth; i++) {
+        if ((index >> i) & 1) orc_hash32_concat(branch + 32 * i, cur, cur);
+        else orc_hash32_concat(cur, branch + 32 * i, cur);
+    }
+    memcpy(out, cur, 32);
+}
+
+/* MerkleTree::create(leaves, depth).hash() + generate_proof(index, depth) (merkle_proof/src/lib.rs:68-99,290-324).
+ * Returns the root and the bottom-up branch of `depth` siblings. */
+EXPORT void orc_merkle_tree_proof(const uint8_t *leaves, uint64_t n, uint32_t depth, uint64_t index, uint8_t root[32],
+                                  uint8_t *branch) {
+    ensure_zero();
+    uint8_t *cur = (uint8_t *)malloc((size_t)(n + 2) * 32);
+    memcpy(cur, leaves, (size_t)n * 32);
+    uint64_t cnt = n, idx = index;
+    for (uint32_t lvl = 0; lvl < depth; lvl++) {
+        uint64_t sib = idx ^ 1;
+        if (sib < cnt) memcpy(branch + 32 * lvl, cur + 32 * sib, 32);
+        else memcpy(branch + 32 * lvl, ZH[lvl], 32);
+        if (cnt & 1) { memcpy(cur + cnt * 32, ZH[lvl], 32); cnt++; }
+        uint64_t half = cnt / 2;
+        for (uint64_t i = 0; i < half; i++) {
+            uint8_t tmp[32];
+            hash64(cur + 64 * i, tmp);
+            memcpy(cur + 32 * i, tmp, 32);
+        }
+        cnt = half;
+        idx >>= 1;
+    }
+    if (n == 0) memcpy(root, ZH[depth], 32);
+    else memcpy(root, cur, 32);
+    free(cur);
+}
+

@@ -1,0 +1,158 @@
+"""GPU parity tests for the tree-hash path: CUDA library (through the C ABI) vs the CPU oracle and the
+reference's golden vectors.  Bit-exact (32-byte digests)."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rb(rng, n):
+    return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+
+
+def test_zero_hashes(gpu):
+    from lighthouse_b200 import tree_hash as T
+    for d in range(0, 65):
+        assert T.zero_hash(d) == O.zero_hash(d)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 256, 257, 10_000])
+def test_hash_pairs(gpu, n):
+    from lighthouse_b200 import tree_hash as T
+    d = rb(np.random.default_rng(n), 64 * n)
+    got = T.hash_pairs(d)
+    assert got == O.hash_pairs(d)
+    assert got[:32] == hashlib.sha256(d[:64]).digest()
+
+
+@pytest.mark.parametrize("n,depth", [(0, 0), (0, 7), (1, 0), (1, 1), (1, 40), (2, 1), (3, 2), (5, 3), (7, 30), (8, 3),
+                                     (9, 4), (9, 40), (16, 4), (17, 5), (255, 8), (256, 8), (257, 9), (2047, 11),
+                                     (2048, 11), (2049, 12), (2049, 40), (4097, 13), (100_003, 17), (100_003, 38),
+                                     (1 << 16, 16), (300_000, 35)])
+def test_merkleize_vs_oracle(gpu, n, depth):
+    from lighthouse_b200 import tree_hash as T
+    c = rb(np.random.default_rng(n * 977 + depth), 32 * n)
+    assert T.merkleize_chunks(c, depth) == O.merkleize(c, depth)
+
+
+def test_merkle_root_and_mix_in_length(gpu):
+    from lighthouse_b200 import tree_hash as T
+    rng = np.random.default_rng(5)
+    pk, sig = rb(rng, 48), rb(rng, 96)
+    assert T.merkle_root(pk, 0) == O.merkleize_bytes(pk, 1)       # 48-byte blob (bls/src/macros.rs:18-25)
+    assert T.merkle_root(sig, 0) == O.merkleize_bytes(sig, 2)     # 96-byte blob: 3 chunks padded to 4
+    r = rb(rng, 32)
+    for ln in (0, 1, 500_000, (1 << 40) - 1):
+        assert T.mix_in_length(r, ln) == hashlib.sha256(r + struct.pack("<Q", ln) + b"\0" * 24).digest()
+
+
+@pytest.mark.parametrize("net", ["sepolia", "gnosis", "mainnet"])
+def test_genesis_validators_root_golden(gpu, net):
+    """hash_tree_root(validators) of the reference's vendored genesis states == genesis_validators_root."""
+    from lighthouse_b200 import tree_hash as T
+    meta = O.golden_json("genesis_validators.json")[net]
+    ssz = O.golden_validators(net)
+    assert T.validators_root(ssz).hex() == meta["genesis_validators_root"]
+    assert T.validator_roots(ssz) == O.validator_roots(ssz)
+
+
+@pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 1000])
+def test_validators_root_ragged(gpu, n):
+    from lighthouse_b200 import tree_hash as T
+    from lighthouse_b200.synthetic import validators_ssz
+    ssz = validators_ssz(n, np.random.default_rng(n))
+    assert T.validators_root(ssz) == O.validators_root(ssz)
+
+
+def test_deposit_roots_golden(gpu):
+    from lighthouse_b200 import tree_hash as T
+    for d in O.golden_json("deposit_data.json"):
+        pk = bytes.fromhex(d["pubkey"]); wc = bytes.fromhex(d["withdrawal_credentials"])
+        amount = struct.pack("<Q", d["amount"]) + b"\0" * 24
+        sig = bytes.fromhex(d["signature"])
+        pk_root, sig_root = T.merkle_root(pk), T.merkle_root(sig)
+        assert T.merkleize_chunks(pk_root + wc + amount, 2).hex() == d["deposit_message_root"]
+        assert T.merkleize_chunks(pk_root + wc + amount + sig_root, 2).hex() == d["deposit_data_root"]
+
+
+@pytest.mark.parametrize("nv,kw", [(0, dict(all_default=True)), (1, {}), (300, dict(n_hist_roots=5, n_votes=7,
+                                                                                     n_summaries=3)),
+                                   (5000, dict(all_default=True)), (16_384, {}), (70_001, dict(extra_data_len=32))])
+def test_beacon_state_root_vs_oracle(gpu, nv, kw):
+    from lighthouse_b200 import tree_hash as T
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    ssz = beacon_state_deneb_ssz(nv, seed=nv + 1, **kw)
+    want_root, want_fields = O.beacon_state_root_deneb(ssz)
+    got_root, got_fields = T.beacon_state_root_deneb(ssz, want_field_roots=True)
+    for i, (g, w) in enumerate(zip(got_fields, want_fields)):
+        assert g == w, f"field {i} root differs"
+    assert got_root == want_root
+
+
+def test_beacon_state_full_size_resident(gpu):
+    """BASELINE configs[1]: 500k-validator Deneb state; resident handle re-hashes to the same digest
+    (idempotence) and matches the multi-threaded oracle."""
+    from lighthouse_b200 import tree_hash as T
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    ssz = beacon_state_deneb_ssz(500_000, seed=42)
+    O.set_threads(O.hw_threads())
+    want, _ = O.beacon_state_root_deneb(ssz)
+    O.set_threads(1)
+    st = T.ResidentState(ssz)
+    r1 = st.root()
+    r2 = st.root()
+    units = st.hash_units
+    st.release()
+    assert r1 == r2 == want
+    assert abs(units - 4_873_001) < 20_000, units  # SURVEY §8d algorithmic unit count (±small-field variation)
+
+
+def test_malformed_state_rejected(gpu):
+    from lighthouse_b200 import tree_hash as T, Lhb200Error
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    ssz = bytearray(beacon_state_deneb_ssz(10, seed=1))
+    ssz[524552:524556] = struct.pack("<I", 5)  # validators offset before the fixed part
+    with pytest.raises(Lhb200Error):
+        T.beacon_state_root_deneb(bytes(ssz))
+    with pytest.raises(Lhb200Error):
+        T.beacon_state_root_deneb(bytes(100))
+
+
+def test_merkle_tree_create_and_proofs(gpu):
+    """MerkleTree::create / generate_proof / verify_merkle_proof (merkle_proof/src/lib.rs tests :412-568)."""
+    from lighthouse_b200.merkle_proof import MerkleTree, verify_merkle_proof, verify_merkle_proofs
+    rng = np.random.default_rng(11)
+    for depth, n in [(0, 1), (1, 1), (1, 2), (3, 5), (5, 32), (12, 6), (17, 100), (32, 9), (4, 0)]:
+        leaves = [rb(rng, 32) for _ in range(n)]
+        t = MerkleTree.create(leaves, depth)
+        want_root = O.merkleize(b"".join(leaves), depth)
+        assert t.hash() == want_root
+        for idx in sorted({0, max(n - 1, 0), min(n, (1 << depth) - 1)}):
+            leaf, br = t.generate_proof(idx, depth)
+            wr, wb = O.merkle_tree_proof(leaves, depth, idx)
+            assert br == wb and wr == want_root
+            assert verify_merkle_proof(leaf, br, depth, idx, want_root)
+            if depth:
+                assert not verify_merkle_proof(leaf, br, depth, idx ^ 1, want_root) or br[0] == leaf
+                bad = [bytes(32)] + br[1:]
+                if bad != br:
+                    assert not verify_merkle_proof(leaf, bad, depth, idx, want_root)
+            assert not verify_merkle_proof(leaf, br[:-1], depth, idx, want_root) if depth else True
+    # depth 0: verify_merkle_proof(leaf, [], 0, idx, root) <=> leaf == root   (lib.rs:562-568)
+    x = rb(rng, 32)
+    assert verify_merkle_proof(x, [], 0, 0, x) and not verify_merkle_proof(x, [], 0, 0, rb(rng, 32))
+    # batch
+    leaves = [rb(rng, 32) for _ in range(300)]
+    t = MerkleTree.create(leaves, 10)
+    root = t.hash()
+    proofs = [t.generate_proof(i)[1] for i in range(0, 300, 37)]
+    idxs = list(range(0, 300, 37))
+    oks = verify_merkle_proofs([leaves[i] for i in idxs], proofs, 10, idxs, [root] * len(idxs))
+    assert all(oks)
+    oks = verify_merkle_proofs([leaves[i] for i in idxs], proofs, 10, [i + 1 for i in idxs], [root] * len(idxs))
+    assert not any(oks)
