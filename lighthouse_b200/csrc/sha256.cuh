@@ -10,16 +10,27 @@
 #pragma once
 #include <stdint.h>
 
+// LHB_HOSTSIM: the same code compiled for the host by the tests (never part of the product library).
+#ifdef LHB_HOSTSIM
+#define LHB_SHA_CONSTEXPR constexpr
+#define LHB_SHA_FN static inline
+#define LHB_SHA_NOINLINE static __attribute__((noinline))
+#else
+#define LHB_SHA_CONSTEXPR __host__ __device__ constexpr
+#define LHB_SHA_FN __device__ __forceinline__
+#define LHB_SHA_NOINLINE __device__ __noinline__
+#endif
+
 namespace lhb200 {
 
-__host__ __device__ constexpr uint32_t c_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+LHB_SHA_CONSTEXPR uint32_t c_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
 struct Sha256Consts {
     uint32_t k[64];
     uint32_t kw_pad[64];  // K[t] + W[t] for the constant 64-byte-message padding block
 };
 
-__host__ __device__ constexpr Sha256Consts make_sha256_consts() {
+LHB_SHA_CONSTEXPR Sha256Consts make_sha256_consts() {
     Sha256Consts c{};
     const uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
@@ -45,8 +56,13 @@ __host__ __device__ constexpr Sha256Consts make_sha256_consts() {
     return c;
 }
 
+#if defined(__CUDA_ARCH__)
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+#else
+static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static inline uint32_t bswap32(uint32_t x) { return __builtin_bswap32(x); }
+#endif
 
 #define LHB_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                         \
     {                                                                     \
@@ -59,7 +75,7 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
     }
 
 // One compression of a data block held in w[16] (big-endian-decoded words).  w is clobbered.
-__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+LHB_SHA_FN void sha256_compress(uint32_t st[8], uint32_t w[16]) {
     constexpr Sha256Consts C = make_sha256_consts();
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
@@ -87,7 +103,7 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
 }
 
 // Compression of the constant padding block that follows a 64-byte message.
-__device__ __forceinline__ void sha256_compress_pad64(uint32_t st[8]) {
+LHB_SHA_FN void sha256_compress_pad64(uint32_t st[8]) {
     constexpr Sha256Consts C = make_sha256_consts();
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
@@ -104,13 +120,13 @@ __device__ __forceinline__ void sha256_compress_pad64(uint32_t st[8]) {
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
-__device__ __forceinline__ void sha256_init(uint32_t st[8]) {
+LHB_SHA_FN void sha256_init(uint32_t st[8]) {
     st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
     st[4] = 0x510e527f; st[5] = 0x9b05688c; st[6] = 0x1f83d9ab; st[7] = 0x5be0cd19;
 }
 
 // hash32_concat on words: out = SHA256(l || r), all in big-endian-decoded word form.  out may alias l or r.
-__device__ __forceinline__ void hash_pair_inl(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
+LHB_SHA_FN void hash_pair_inl(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
     uint32_t w[16], st[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { w[i] = l[i]; w[8 + i] = r[i]; }
@@ -122,7 +138,7 @@ __device__ __forceinline__ void hash_pair_inl(const uint32_t l[8], const uint32_
 }
 
 // Out-of-line copy for cold code (tails, hash programs, expand_message_xmd) to bound code size.
-__device__ __noinline__ void hash_pair(const uint32_t* l, const uint32_t* r, uint32_t* out) {
+LHB_SHA_NOINLINE void hash_pair(const uint32_t* l, const uint32_t* r, uint32_t* out) {
     uint32_t a[8], b[8], o[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { a[i] = l[i]; b[i] = r[i]; }
@@ -131,6 +147,7 @@ __device__ __noinline__ void hash_pair(const uint32_t* l, const uint32_t* r, uin
     for (int i = 0; i < 8; i++) out[i] = o[i];
 }
 
+#ifndef LHB_HOSTSIM
 // 32-byte chunk <-> 8 big-endian-decoded words.  p must be 16-byte aligned.
 __device__ __forceinline__ void load_chunk(const uint8_t* p, uint32_t w[8]) {
     uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
@@ -143,6 +160,34 @@ __device__ __forceinline__ void store_chunk(uint8_t* p, const uint32_t w[8]) {
     uint4 y = make_uint4(bswap32(w[4]), bswap32(w[5]), bswap32(w[6]), bswap32(w[7]));
     reinterpret_cast<uint4*>(p)[0] = x;
     reinterpret_cast<uint4*>(p)[1] = y;
+}
+#endif  // !LHB_HOSTSIM
+
+// Generic SHA-256 of a short byte string (expand_message_xmd; not a throughput path).
+LHB_SHA_NOINLINE void sha256_block_oob(uint32_t* st, const uint8_t* blk) {
+    uint32_t w[16], s[8];
+    for (int i = 0; i < 16; i++)
+        w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) |
+               blk[4 * i + 3];
+    for (int i = 0; i < 8; i++) s[i] = st[i];
+    sha256_compress(s, w);
+    for (int i = 0; i < 8; i++) st[i] = s[i];
+}
+// msg length must be <= 183 bytes (3 blocks); out = 32 bytes
+LHB_SHA_FN void sha256_short(const uint8_t* msg, int len, uint8_t* out) {
+    uint8_t buf[192];
+    const int nblk = (len + 9 + 63) / 64;
+    for (int i = 0; i < nblk * 64; i++) buf[i] = i < len ? msg[i] : 0;
+    buf[len] = 0x80;
+    const uint32_t bits = (uint32_t)len * 8;
+    buf[nblk * 64 - 1] = (uint8_t)bits;
+    buf[nblk * 64 - 2] = (uint8_t)(bits >> 8);
+    uint32_t st[8];
+    sha256_init(st);
+    for (int b = 0; b < nblk; b++) sha256_block_oob(st, buf + 64 * b);
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = st[i] >> 24; out[4 * i + 1] = st[i] >> 16; out[4 * i + 2] = st[i] >> 8; out[4 * i + 3] = st[i];
+    }
 }
 
 }  // namespace lhb200

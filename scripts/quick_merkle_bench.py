@@ -8,7 +8,7 @@ lighthouse_b200.init(0)
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
 ssz = beacon_state_deneb_ssz(V, seed=42)
 st = T.ResidentState(ssz)
-s = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); s = ts.cuda_stream
 for _ in range(3): st.enqueue(s)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,142 @@
+// tests/hostsim/hostsim.cpp — TEST INFRASTRUCTURE: compiles the device math headers for the host
+// (LHB_HOSTSIM: PTX carry chains emulated in C) so `-m "not gpu"` tests can check the exact limb algorithms
+// against oracle/bls_ref.py without a GPU.  Never linked into liblhb200.so.
+#define LHB_HOSTSIM 1
+#include <string.h>
+#include "../../lighthouse_b200/csrc/bls/fp.cuh"
+#include "../../lighthouse_b200/csrc/bls/fp2.cuh"
+#include "../../lighthouse_b200/csrc/bls/ec.cuh"
+#include "../../lighthouse_b200/csrc/bls/h2c.cuh"
+#include "../../lighthouse_b200/csrc/bls/pairing.cuh"
+
+using namespace lhb200::bls;
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+static void fp_in(Fp& r, const uint8_t* be48) { Fp c; fp_from_be48(c, be48); fp_to_mont(r, c); }
+static void fp_out(uint8_t* be48, const Fp& a) { Fp c; fp_from_mont(c, a); fp_to_be48(be48, c); }
+static void fp2_out(uint8_t* b, const Fp2& a) { fp_out(b, a.c0); fp_out(b + 48, a.c1); }
+static void fp2_in(Fp2& r, const uint8_t* b) { fp_in(r.c0, b); fp_in(r.c1, b + 48); }
+
+// op: 0 mul 1 add 2 sub 3 inv 4 neg 5 sqrt(returns ok)   (canonical big-endian 48-byte in/out)
+EXPORT int hs_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fp x, y, r; fp_in(x, a); fp_in(y, b);
+    int ok = 1;
+    switch (op) {
+        case 0: fp_mul(r, x, y); break;
+        case 1: fp_add(r, x, y); break;
+        case 2: fp_sub(r, x, y); break;
+        case 3: fp_inv(r, x); break;
+        case 4: fp_neg(r, x); break;
+        case 5: ok = fp_sqrt(r, x); break;
+        default: return -1;
+    }
+    fp_out(out, r);
+    return ok;
+}
+// raw Montgomery multiplication on little-endian limb arrays (no conversions): out = a*b/R mod p
+EXPORT void hs_mont_mul_raw(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    Fp x, y, r; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fp_mul(r, x, y); memcpy(out, r.v, 48);
+}
+// op: 0 mul 1 sqr 2 inv 3 sqrt(ok) 4 sgn0
+EXPORT int hs_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fp2 x, y, r; fp2_in(x, a); fp2_in(y, b);
+    int ok = 1;
+    switch (op) {
+        case 0: fp2_mul(r, x, y); break;
+        case 1: fp2_sqr(r, x); break;
+        case 2: fp2_inv(r, x); break;
+        case 3: ok = fp2_sqrt(r, x); break;
+        case 4: ok = (int)fp2_sgn0(x); r = x; break;
+        default: return -1;
+    }
+    fp2_out(out, r);
+    return ok;
+}
+static void fp12_out(uint8_t* b, const Fp12& f) {
+    const Fp2* c[6] = {&f.c0.c0, &f.c0.c1, &f.c0.c2, &f.c1.c0, &f.c1.c1, &f.c1.c2};
+    for (int i = 0; i < 6; i++) fp2_out(b + 96 * i, *c[i]);
+}
+static void fp12_in(Fp12& f, const uint8_t* b) {
+    Fp2* c[6] = {&f.c0.c0, &f.c0.c1, &f.c0.c2, &f.c1.c0, &f.c1.c1, &f.c1.c2};
+    for (int i = 0; i < 6; i++) fp2_in(*c[i], b + 96 * i);
+}
+// op: 0 mul 1 sqr 2 inv 3 frob 4 frob2 5 cyclotomic_sqr 6 final_exp 7 mul_by_014 (b = c0|c1|c4 in first 3 fp2 slots)
+EXPORT void hs_fp12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fp12 x, y, r; fp12_in(x, a); fp12_in(y, b);
+    switch (op) {
+        case 0: fp12_mul(r, x, y); break;
+        case 1: fp12_sqr(r, x); break;
+        case 2: fp12_inv(r, x); break;
+        case 3: fp12_frob(r, x); break;
+        case 4: fp12_frob2(r, x); break;
+        case 5: fp12_cyclotomic_sqr(r, x); break;
+        case 6: final_exp(r, x); break;
+        case 7: fp12_mul_by_014(r, x, y.c0.c0, y.c0.c1, y.c0.c2); break;
+    }
+    fp12_out(out, r);
+}
+// G1: uncompressed 96 in -> [k]P uncompressed 96 out ; also compress/decompress
+EXPORT int hs_g1_mul(const uint8_t* p96, const uint32_t* k, int nbits, uint8_t* out96, uint8_t* out48) {
+    G1Affine a; if (g1_from_uncompressed(a, p96) == DEC_BAD) return -1;
+    G1Jac j; jac_mul_affine(j, a, k, nbits);
+    G1Affine r; jac_to_affine(r, j);
+    g1_to_uncompressed(out96, r); g1_compress(out48, r);
+    return 0;
+}
+EXPORT int hs_g1_decompress(const uint8_t* p48, uint8_t* out96) {
+    G1Affine a; int rc = g1_decompress(a, p48); if (rc == DEC_BAD) return rc;
+    g1_to_uncompressed(out96, a); return rc;
+}
+// sum of n uncompressed keys -> uncompressed
+EXPORT int hs_g1_sum(const uint8_t* keys, int n, uint8_t* out96) {
+    G1Jac acc; jac_set_inf(acc);
+    for (int i = 0; i < n; i++) { G1Affine a; if (g1_from_uncompressed(a, keys + 96 * i) == DEC_BAD) return -1; jac_add_affine(acc, acc, a); }
+    G1Affine r; jac_to_affine(r, acc); g1_to_uncompressed(out96, r); return 0;
+}
+EXPORT int hs_g2_roundtrip(const uint8_t* p96, uint8_t* out96) {
+    G2Affine a; int rc = g2_decompress(a, p96); if (rc == DEC_BAD) return rc;
+    g2_compress(out96, a); return rc;
+}
+EXPORT int hs_g2_subgroup(const uint8_t* p96) {
+    G2Affine a; int rc = g2_decompress(a, p96); if (rc == DEC_BAD) return -1;
+    return g2_in_subgroup(a) ? 1 : 0;
+}
+EXPORT int hs_g2_mul(const uint8_t* p96, const uint32_t* k, int nbits, uint8_t* out96) {
+    G2Affine a; if (g2_decompress(a, p96) == DEC_BAD) return -1;
+    G2Jac j; jac_mul_affine(j, a, k, nbits);
+    G2Affine r; jac_to_affine(r, j); g2_compress(out96, r); return 0;
+}
+EXPORT void hs_hash_to_g2(const uint8_t* msg32, uint8_t* out96) {
+    G2Jac j; hash_to_g2_jac(j, msg32);
+    G2Affine r; jac_to_affine(r, j); g2_compress(out96, r);
+}
+EXPORT void hs_expand(const uint8_t* msg32, uint8_t* out256) { expand_message_xmd_256(msg32, out256); }
+EXPORT void hs_sswu(const uint8_t* u96, uint8_t* xy192) {
+    Fp2 u, x, y; fp2_in(u, u96); map_to_curve_sswu(x, y, u); fp2_out(xy192, x); fp2_out(xy192 + 96, y);
+}
+// miller loop (+ optional final exp) of (P uncompressed G1, Q compressed G2); proj: feed P as a re-randomised Jacobian
+EXPORT int hs_pairing(const uint8_t* p96, const uint8_t* q96, int do_final, int proj, uint8_t* out576) {
+    G1Affine p; G2Affine q;
+    if (g1_from_uncompressed(p, p96) != DEC_OK || g2_decompress(q, q96) != DEC_OK) return -1;
+    G1Proj3 pp;
+    if (proj) {
+        G1Jac j; jac_from_affine(j, p); jac_dbl(j, j);  // 2P in Jacobian form with Z != 1
+        g1proj3_from_jac(pp, j);
+    } else g1proj3_from_affine(pp, p);
+    Fp12 f; miller_loop(f, pp, q);
+    if (do_final) final_exp(f, f);
+    fp12_out(out576, f);
+    return 0;
+}
+// full single verification e(pk, H(m)) * e(-g1, sig) == 1
+EXPORT int hs_verify(const uint8_t* pk96, const uint8_t* msg32, const uint8_t* sig96) {
+    G1Affine pk, g1; G2Affine sig, h;
+    if (g1_from_uncompressed(pk, pk96) != DEC_OK || g2_decompress(sig, sig96) != DEC_OK) return -1;
+    if (!g2_in_subgroup(sig)) return -2;
+    G2Jac hj; hash_to_g2_jac(hj, msg32); jac_to_affine(h, hj);
+    g1.x = G1_GEN_X; fp_neg(g1.y, G1_GEN_Y); g1.inf = 0;
+    G1Proj3 a, b; g1proj3_from_affine(a, pk); g1proj3_from_affine(b, g1);
+    Fp12 f1, f2; miller_loop(f1, a, h); miller_loop(f2, b, sig);
+    fp12_mul(f1, f1, f2); final_exp(f1, f1);
+    return fp12_is_one(f1) ? 1 : 0;
+}
