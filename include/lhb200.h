@@ -90,8 +90,6 @@ LHB200_API int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t*
 /* Same as lhb200_state_root but only enqueues; the root lands in device memory (returned pointer valid until
  * the next call on this handle).  Used by bench.py to time kernels with CUDA events. */
 LHB200_API int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root);
-/* Leaf-range sharding for multi-GPU: keep only validators/balances/... in [first, first+count)
- * (must be a power-of-two aligned range) and produce the 32-byte subtree roots of the big lists. */
 LHB200_API int32_t lhb200_state_release(lhb200_state* st);
 /* Algorithmic work of the last root computed on this handle: number of hash32_concat units. */
 LHB200_API uint64_t lhb200_state_hash_units(const lhb200_state* st);
@@ -104,6 +102,53 @@ LHB200_API int32_t lhb200_merkle_tree_proof(const uint8_t* leaves, uint64_t n, u
  * ok[i] = (fold(leaf_i, branch_i, depth, index_i) == root_i).  branches: n * depth * 32 bytes. */
 LHB200_API int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branches, uint32_t depth,
                                     const uint64_t* indices, const uint8_t* roots, uint64_t n, uint8_t* ok);
+
+/* ---- BLS batch verification path ---------------------------------------------------------------- */
+
+/* bls::verify_signature_sets (crypto/bls/src/impls/blst.rs:37-119) over SoA-flattened SignatureSets
+ * (crypto/bls/src/generic_signature_set.rs:61-121):
+ *   sigs        n x 96 B  compressed G2 (ZCash format; all-zero = Lighthouse's "empty" signature -> false)
+ *   msgs        n x 32 B  signing roots
+ *   pks         K x 96 B  uncompressed affine G1, x || y big-endian (the validator_pubkey_cache.rs:195-199 format;
+ *                         keys are NOT re-validated, matching pks_validate=false at blst.rs:115)
+ *   pk_offsets  n+1 u32   CSR: set i owns keys [pk_offsets[i], pk_offsets[i+1])
+ *   rands       n x u64   nonzero random scalars (blst.rs:55-67), or NULL to have the library draw them
+ * *ok = 1 iff  prod_i e(r_i apk_i, H(m_i)) == e(g1, sum_i r_i sig_i)  and every set passed its checks
+ * (non-empty, subgroup-checked signature; >= 1 key; aggregate key not at infinity).  n_sets == 0 -> *ok = 0
+ * (blst.rs:42-44).  set_status (optional, n bytes): 0 fine, 1 empty sig, 2 sig decode, 3 sig not in subgroup,
+ * 4 no keys, 5 aggregate key at infinity, 6 key decode.  fast_aggregate_verify / Signature::verify
+ * (blst.rs:196-200, :250-261) are the n_sets == 1 case. */
+LHB200_API int32_t lhb200_verify_signature_sets(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks,
+                                                const uint32_t* pk_offsets, const uint64_t* rands, uint32_t n_sets,
+                                                uint8_t* ok, uint8_t* set_status);
+
+/* Staged form of the same call (what bench.py times): create once, upload or point at device-resident inputs,
+ * enqueue on a stream, read the verdict. */
+typedef struct lhb200_bls_batch lhb200_bls_batch;
+LHB200_API int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls_batch** out);
+LHB200_API int32_t lhb200_bls_batch_destroy(lhb200_bls_batch* b);
+LHB200_API int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* sigs, const uint8_t* msgs,
+                                           const uint8_t* pks, const uint32_t* pk_offsets, const uint64_t* rands,
+                                           uint32_t n_sets);
+LHB200_API int32_t lhb200_bls_batch_set_device_inputs(lhb200_bls_batch* b, const void* d_sigs, const void* d_msgs,
+                                                      const void* d_pks, const void* d_offsets, const void* d_rands,
+                                                      uint32_t n_sets);
+LHB200_API int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream);
+LHB200_API int32_t lhb200_bls_batch_result(lhb200_bls_batch* b, void* stream, uint8_t* ok, uint8_t* set_status);
+/* Test hook: final-exponentiated product of the last verify as 12 x 48-byte big-endian Fp (tower order
+ * c0.c0.c0 .. c1.c2.c1).  NOTE: this is the cube of the canonical GT element (3 is coprime to r). */
+LHB200_API int32_t lhb200_bls_batch_gt(lhb200_bls_batch* b, uint8_t out576[576]);
+LHB200_API uint64_t lhb200_bls_batch_launches(const lhb200_bls_batch* b);
+
+/* TSecretKey::public_key / ::sign (crypto/bls/src/impls/blst.rs:282-298): n big-endian 32-byte scalars (< r). */
+LHB200_API int32_t lhb200_sk_to_pk(const uint8_t* sk32, uint32_t n, uint8_t* pk48, uint8_t* pk96);
+LHB200_API int32_t lhb200_sign(const uint8_t* sk32, const uint8_t* msg32, uint32_t n, uint8_t* sig96);
+/* PublicKey::deserialize + key_validate, batch form (blst.rs:130-140; validator_pubkey_cache.rs:116-118).
+ * status[i]: 0 ok, 1 infinity (rejected), 2 bad encoding / not on curve, 3 not in subgroup. */
+LHB200_API int32_t lhb200_g1_decompress_validate(const uint8_t* pk48, uint32_t n, uint8_t* pk96, uint8_t* status);
+/* Signature::deserialize, batch form (blst.rs:192-194): 192-byte affine out; status 0 ok, 1 infinity, 2 bad. */
+LHB200_API int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, uint8_t* status);
+
 
 #ifdef __cplusplus
 }

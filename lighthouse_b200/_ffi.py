@@ -84,3 +84,18 @@ def buf(b):
     import numpy as np
     a = np.ascontiguousarray(b)
     return C.c_void_p(a.ctypes.data), a
+
+# ---- BLS path
+_sig("lhb200_verify_signature_sets", C.c_int32, vp, vp, vp, vp, vp, C.c_uint32, vp, vp)
+_sig("lhb200_bls_batch_create", C.c_int32, C.c_uint32, C.c_uint64, C.POINTER(vp))
+_sig("lhb200_bls_batch_destroy", C.c_int32, vp)
+_sig("lhb200_bls_batch_upload", C.c_int32, vp, vp, vp, vp, vp, vp, C.c_uint32)
+_sig("lhb200_bls_batch_set_device_inputs", C.c_int32, vp, vp, vp, vp, vp, vp, C.c_uint32)
+_sig("lhb200_bls_batch_verify_enqueue", C.c_int32, vp, vp)
+_sig("lhb200_bls_batch_result", C.c_int32, vp, vp, vp, vp)
+_sig("lhb200_bls_batch_gt", C.c_int32, vp, vp)
+_sig("lhb200_bls_batch_launches", C.c_uint64, vp)
+_sig("lhb200_sk_to_pk", C.c_int32, vp, C.c_uint32, vp, vp)
+_sig("lhb200_sign", C.c_int32, vp, vp, C.c_uint32, vp)
+_sig("lhb200_g1_decompress_validate", C.c_int32, vp, C.c_uint32, vp, vp)
+_sig("lhb200_g2_decompress", C.c_int32, vp, C.c_uint32, vp, vp)

@@ -18,7 +18,7 @@
 #define LHB_INLINE inline
 #define LHB_CONST static const
 #else
-#define LHB_HD __host__ __device__
+#define LHB_HD __device__
 #define LHB_NOINLINE __noinline__
 #define LHB_INLINE __forceinline__
 #define LHB_CONST static __device__ __constant__ const

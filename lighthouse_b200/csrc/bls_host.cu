@@ -1,6 +1,424 @@
-// bls_host.cu — placeholder until the BLS path lands.
+// bls_host.cu — host driver + C ABI of the batch BLS verification path.
+//
+// Mirrors bls::verify_signature_sets (crypto/bls/src/impls/blst.rs:37-119) at the batch level: the caller (the
+// Rust shim in INTEGRATION.md, or lighthouse_b200/bls.py) flattens SignatureSets into SoA buffers
+//   sigs  n x 96 B  compressed G2            (AggregateSignature::serialize, generic_aggregate_signature.rs:153-160)
+//   msgs  n x 32 B  signing roots            (generic_signature_set.rs:70)
+//   pks   K x 96 B  uncompressed affine G1   (validator_pubkey_cache.rs:195-199 format), CSR offsets n+1
+// and gets back the batch verdict.  All arithmetic runs on the device; there is no CPU fallback.
+#include <string.h>
+#include <algorithm>
+#include <random>
+#include <vector>
+#include "bls/kernels.cuh"
 #include "ctx.h"
+
 namespace lhb200 {
+
+using namespace bls;
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
 int32_t bls_init() { return LHB200_OK; }
 void bls_shutdown() {}
+
 }  // namespace lhb200
+
+using namespace lhb200;
+
+struct lhb200_bls_batch {
+    uint32_t cap_sets = 0;
+    uint64_t cap_keys = 0;
+    uint32_t n = 0;
+    // inputs (owned copies, or caller's device buffers)
+    uint8_t *d_sigs = nullptr, *d_msgs = nullptr, *d_pks = nullptr;
+    uint32_t* d_offsets = nullptr;
+    uint64_t* d_rands = nullptr;
+    const uint8_t *in_sigs = nullptr, *in_msgs = nullptr, *in_pks = nullptr;
+    const uint32_t* in_offsets = nullptr;
+    const uint64_t* in_rands = nullptr;
+    // intermediates
+    G2Jac* d_sigr = nullptr;      // r_i * sig_i
+    G2Jac* d_sig_tmp[2] = {nullptr, nullptr};
+    G1Proj3* d_p = nullptr;       // r_i * apk_i (projective evaluation point)
+    G2Affine* d_h = nullptr;      // H(m_i)
+    Fp12* d_f = nullptr;          // Miller loop values
+    Fp12* d_f_tmp[2] = {nullptr, nullptr};
+    Fp12* d_flast = nullptr;
+    Fp12* d_gt = nullptr;
+    uint8_t* d_status = nullptr;
+    uint32_t* d_fail = nullptr;
+    uint8_t* d_ok = nullptr;
+    uint8_t* h_res = nullptr;     // pinned: ok + status
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t e_fork = nullptr, e_join = nullptr;
+    uint64_t launches_last = 0;
+};
+
+static void batch_free(lhb200_bls_batch* b) {
+    if (!b) return;
+    void* ptrs[] = {b->d_sigs, b->d_msgs, b->d_pks, b->d_offsets, b->d_rands, b->d_sigr, b->d_sig_tmp[0],
+                    b->d_sig_tmp[1], b->d_p, b->d_h, b->d_f, b->d_f_tmp[0], b->d_f_tmp[1], b->d_flast, b->d_gt,
+                    b->d_status, b->d_fail, b->d_ok};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (b->h_res) cudaFreeHost(b->h_res);
+    if (b->s2) cudaStreamDestroy(b->s2);
+    if (b->e_fork) cudaEventDestroy(b->e_fork);
+    if (b->e_join) cudaEventDestroy(b->e_join);
+    delete b;
+}
+
+constexpr uint32_t REDUCE_CHUNK = 8;
+
+extern "C" {
+
+int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls_batch** out) {
+    LHB_REQUIRE_READY();
+    if (!out || max_sets == 0) { set_error("bls_batch_create: bad arguments"); return LHB200_EINVAL; }
+    lhb200_bls_batch* b = new lhb200_bls_batch();
+    b->cap_sets = max_sets;
+    b->cap_keys = max_keys;
+    const uint64_t n = max_sets, n1 = cdiv(n, REDUCE_CHUNK) + 1, n2 = cdiv(n1, REDUCE_CHUNK) + 1;
+#define ALLOC(p, bytes)                                                         \
+    do {                                                                        \
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&(p)), (bytes));    \
+        if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaMalloc(" #p ")"); } \
+    } while (0)
+    ALLOC(b->d_sigs, n * 96 + 16);
+    ALLOC(b->d_msgs, n * 32 + 16);
+    ALLOC(b->d_pks, std::max<uint64_t>(max_keys, 1) * 96 + 16);
+    ALLOC(b->d_offsets, (n + 1) * 4);
+    ALLOC(b->d_rands, n * 8);
+    ALLOC(b->d_sigr, n * sizeof(G2Jac));
+    ALLOC(b->d_sig_tmp[0], n1 * sizeof(G2Jac));
+    ALLOC(b->d_sig_tmp[1], n2 * sizeof(G2Jac));
+    ALLOC(b->d_p, n * sizeof(G1Proj3));
+    ALLOC(b->d_h, n * sizeof(G2Affine));
+    ALLOC(b->d_f, n * sizeof(Fp12));
+    ALLOC(b->d_f_tmp[0], n1 * sizeof(Fp12));
+    ALLOC(b->d_f_tmp[1], n2 * sizeof(Fp12));
+    ALLOC(b->d_flast, sizeof(Fp12));
+    ALLOC(b->d_gt, sizeof(Fp12));
+    ALLOC(b->d_status, n);
+    ALLOC(b->d_fail, 4);
+    ALLOC(b->d_ok, 4);
+#undef ALLOC
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b->h_res), n + 64 + sizeof(Fp12), cudaHostAllocDefault);
+    if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaHostAlloc(result)"); }
+    if ((e = cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess) {
+        batch_free(b);
+        return cuda_fail(e, "stream/event create");
+    }
+    *out = b;
+    return LHB200_OK;
+}
+
+int32_t lhb200_bls_batch_destroy(lhb200_bls_batch* b) {
+    if (ctx().ready) cudaDeviceSynchronize();
+    batch_free(b);
+    return LHB200_OK;
+}
+
+static void gen_rands(uint64_t* r, uint32_t n) {
+    // blst.rs:55-67: one nonzero 64-bit scalar per set from a CSPRNG-seeded generator
+    std::random_device rd;
+    std::seed_seq seq{rd(), rd(), rd(), rd(), rd(), rd(), rd(), rd()};
+    std::mt19937_64 g(seq);
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t v;
+        do v = g(); while (v == 0);
+        r[i] = v;
+    }
+}
+
+// Copy host inputs into the batch's device buffers.  rands == NULL: drawn here.
+int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks,
+                                const uint32_t* pk_offsets, const uint64_t* rands, uint32_t n_sets) {
+    LHB_REQUIRE_READY();
+    if (!b || n_sets == 0 || n_sets > b->cap_sets || !sigs || !msgs || !pk_offsets) {
+        set_error("bls_batch_upload: bad arguments");
+        return LHB200_EINVAL;
+    }
+    const uint64_t n_keys = pk_offsets[n_sets];
+    if (n_keys > b->cap_keys || (n_keys && !pks)) { set_error("bls_batch_upload: key buffer too small"); return LHB200_EINVAL; }
+    for (uint32_t i = 0; i < n_sets; i++)
+        if (pk_offsets[i] > pk_offsets[i + 1]) { set_error("bls_batch_upload: offsets not monotone"); return LHB200_EINVAL; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    cudaStream_t s = c.stream;
+    std::vector<uint64_t> rbuf;
+    if (!rands) {
+        rbuf.resize(n_sets);
+        gen_rands(rbuf.data(), n_sets);
+        rands = rbuf.data();
+    } else {
+        for (uint32_t i = 0; i < n_sets; i++)
+            if (rands[i] == 0) { set_error("bls_batch_upload: zero random scalar"); return LHB200_EINVAL; }
+    }
+    LHB_CUDA(cudaMemcpyAsync(b->d_sigs, sigs, (size_t)n_sets * 96, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_msgs, msgs, (size_t)n_sets * 32, cudaMemcpyHostToDevice, s));
+    if (n_keys) LHB_CUDA(cudaMemcpyAsync(b->d_pks, pks, (size_t)n_keys * 96, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_offsets, pk_offsets, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_rands, rands, (size_t)n_sets * 8, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaStreamSynchronize(s));  // rbuf / caller buffers may go away
+    b->n = n_sets;
+    b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = b->d_pks;
+    b->in_offsets = b->d_offsets; b->in_rands = b->d_rands;
+    return LHB200_OK;
+}
+
+// Use caller-owned device buffers (16-byte aligned) as the inputs: nothing is copied.
+int32_t lhb200_bls_batch_set_device_inputs(lhb200_bls_batch* b, const void* d_sigs, const void* d_msgs,
+                                           const void* d_pks, const void* d_offsets, const void* d_rands,
+                                           uint32_t n_sets) {
+    LHB_REQUIRE_READY();
+    if (!b || n_sets == 0 || n_sets > b->cap_sets || !d_sigs || !d_msgs || !d_offsets || !d_rands ||
+        ((uintptr_t)d_sigs & 15) || ((uintptr_t)d_msgs & 15) || ((uintptr_t)d_pks & 15)) {
+        set_error("bls_batch_set_device_inputs: bad arguments (buffers must be 16-byte aligned)");
+        return LHB200_EINVAL;
+    }
+    b->n = n_sets;
+    b->in_sigs = static_cast<const uint8_t*>(d_sigs);
+    b->in_msgs = static_cast<const uint8_t*>(d_msgs);
+    b->in_pks = static_cast<const uint8_t*>(d_pks);
+    b->in_offsets = static_cast<const uint32_t*>(d_offsets);
+    b->in_rands = static_cast<const uint64_t*>(d_rands);
+    return LHB200_OK;
+}
+
+int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
+    LHB_REQUIRE_READY();
+    if (!b || b->n == 0 || !b->in_sigs) { set_error("bls_batch_verify_enqueue: no inputs"); return LHB200_EINVAL; }
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+    const uint32_t n = b->n;
+    const uint32_t grid = cdiv(n, BLS_BLOCK);
+    uint64_t launches = 0;
+    LHB_CUDA(cudaMemsetAsync(b->d_status, 0, n, s));
+    LHB_CUDA(cudaMemsetAsync(b->d_fail, 0, 4, s));
+    LHB_CUDA(cudaMemsetAsync(b->d_ok, 0, 4, s));
+    k_sig_prepare<<<grid, BLS_BLOCK, 0, s>>>(b->in_sigs, b->in_rands, n, b->d_sigr, b->d_status, b->d_fail);
+    launches++;
+    // side stream: sum r_i*sig_i, then the Miller loop of (-g1, sum)
+    LHB_CUDA(cudaEventRecord(b->e_fork, s));
+    LHB_CUDA(cudaStreamWaitEvent(b->s2, b->e_fork, 0));
+    {
+        const G2Jac* cur = b->d_sigr;
+        uint32_t m = n;
+        int flip = 0;
+        while (m > 1) {
+            const uint32_t mo = cdiv(m, REDUCE_CHUNK);
+            k_g2_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, b->s2>>>(cur, m, REDUCE_CHUNK, b->d_sig_tmp[flip]);
+            launches++;
+            cur = b->d_sig_tmp[flip];
+            flip ^= 1;
+            m = mo;
+        }
+        k_last_miller<<<1, 32, 0, b->s2>>>(cur, b->d_flast);
+        launches++;
+        LHB_CUDA(cudaEventRecord(b->e_join, b->s2));
+    }
+    k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
+    k_hash_to_g2<<<grid, BLS_BLOCK, 0, s>>>(b->in_msgs, n, b->d_h);
+    k_miller<<<grid, BLS_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);
+    launches += 3;
+    const Fp12* cur = b->d_f;
+    {
+        uint32_t m = n;
+        int flip = 0;
+        while (m > 1) {
+            const uint32_t mo = cdiv(m, REDUCE_CHUNK);
+            k_fp12_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, s>>>(cur, m, REDUCE_CHUNK, b->d_f_tmp[flip]);
+            launches++;
+            cur = b->d_f_tmp[flip];
+            flip ^= 1;
+            m = mo;
+        }
+    }
+    LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));
+    k_final<<<1, 32, 0, s>>>(cur, b->d_flast, b->d_fail, b->d_ok, b->d_gt);
+    launches++;
+    LHB_CUDA(cudaGetLastError());
+    count_launch(launches);
+    b->launches_last = launches;
+    return LHB200_OK;
+}
+
+int32_t lhb200_bls_batch_result(lhb200_bls_batch* b, void* stream, uint8_t* ok, uint8_t* set_status) {
+    LHB_REQUIRE_READY();
+    if (!b || !ok) return LHB200_EINVAL;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+    LHB_CUDA(cudaMemcpyAsync(b->h_res, b->d_ok, 1, cudaMemcpyDeviceToHost, s));
+    if (set_status) LHB_CUDA(cudaMemcpyAsync(b->h_res + 64, b->d_status, b->n, cudaMemcpyDeviceToHost, s));
+    LHB_CUDA(cudaStreamSynchronize(s));
+    *ok = b->h_res[0];
+    if (set_status) memcpy(set_status, b->h_res + 64, b->n);
+    return LHB200_OK;
+}
+
+// Test hook: the value final_exp(product)^... of the last verify as 12 x 48-byte big-endian canonical Fp
+// (order c0.c0.c0, c0.c0.c1, c0.c1.c0, ... c1.c2.c1).  It is the CUBE of the canonical GT element (pairing.cuh).
+int32_t lhb200_bls_batch_gt(lhb200_bls_batch* b, uint8_t out576[576]) {
+    LHB_REQUIRE_READY();
+    if (!b || !out576) return LHB200_EINVAL;
+    Fp12 f;
+    LHB_CUDA(cudaDeviceSynchronize());
+    LHB_CUDA(cudaMemcpy(&f, b->d_gt, sizeof f, cudaMemcpyDeviceToHost));
+    const Fp* c = reinterpret_cast<const Fp*>(&f);
+    // host-side conversion out of Montgomery form (plain integer arithmetic on 12 limbs, test hook only)
+    for (int k = 0; k < 12; k++) {
+        // t = c[k] * R^-1 mod p via 12 rounds of word-wise Montgomery reduction
+        uint64_t t[13] = {0};
+        for (int i = 0; i < 12; i++) t[i] = c[k].v[i];
+        static const uint32_t P32[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                         0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        for (int i = 0; i < 12; i++) {
+            const uint32_t m = (uint32_t)t[0] * 0xfffcfffdu;
+            uint64_t carry = 0;
+            for (int j = 0; j < 12; j++) {
+                uint64_t v = t[j] + (uint64_t)m * P32[j] + carry;
+                t[j] = v & 0xffffffffu;
+                carry = v >> 32;
+            }
+            uint64_t top = t[12] + carry;
+            for (int j = 0; j < 12; j++) t[j] = t[j + 1];
+            t[11] = top & 0xffffffffu;
+            t[12] = top >> 32;
+        }
+        // conditional subtract
+        bool ge = t[12] != 0;
+        if (!ge) {
+            ge = true;
+            for (int j = 11; j >= 0; j--) {
+                if (t[j] != P32[j]) { ge = t[j] > P32[j]; break; }
+            }
+        }
+        if (ge) {
+            int64_t brw = 0;
+            for (int j = 0; j < 12; j++) {
+                int64_t v = (int64_t)t[j] - P32[j] - brw;
+                brw = v < 0;
+                t[j] = (uint64_t)(v & 0xffffffff);
+            }
+        }
+        for (int j = 0; j < 12; j++) {
+            uint8_t* q = out576 + 48 * k + 4 * (11 - j);
+            q[0] = t[j] >> 24; q[1] = t[j] >> 16; q[2] = t[j] >> 8; q[3] = t[j];
+        }
+    }
+    return LHB200_OK;
+}
+
+uint64_t lhb200_bls_batch_launches(const lhb200_bls_batch* b) { return b ? b->launches_last : 0; }
+
+// bls::verify_signature_sets (crypto/bls/src/impls/blst.rs:37-119).  *ok = 1 iff every set verifies.
+// n_sets == 0 -> *ok = 0 (blst.rs:42-44).  rands may be NULL (drawn internally, 64 nonzero bits each).
+// set_status (optional, n bytes): per-set preparation status (0 = fine; see SetStatus in kernels.cuh).
+int32_t lhb200_verify_signature_sets(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks,
+                                     const uint32_t* pk_offsets, const uint64_t* rands, uint32_t n_sets, uint8_t* ok,
+                                     uint8_t* set_status) {
+    LHB_REQUIRE_READY();
+    if (!ok) return LHB200_EINVAL;
+    *ok = 0;
+    if (n_sets == 0) return LHB200_OK;
+    if (!pk_offsets) { set_error("verify_signature_sets: null offsets"); return LHB200_EINVAL; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    lhb200_bls_batch* b = nullptr;
+    int32_t rc = lhb200_bls_batch_create(n_sets, pk_offsets[n_sets], &b);
+    if (rc) return rc;
+    rc = lhb200_bls_batch_upload(b, sigs, msgs, pks, pk_offsets, rands, n_sets);
+    if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, c.stream);
+    if (!rc) rc = lhb200_bls_batch_result(b, c.stream, ok, set_status);
+    cudaStreamSynchronize(b->s2);
+    batch_free(b);
+    return rc;
+}
+
+// TSecretKey::public_key (blst.rs:282-298): n big-endian 32-byte scalars -> compressed (48 B) and/or
+// uncompressed (96 B) public keys.  Either output may be NULL.
+int32_t lhb200_sk_to_pk(const uint8_t* sk32, uint32_t n, uint8_t* pk48, uint8_t* pk96) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!sk32 || (!pk48 && !pk96)) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch((size_t)n * (32 + 48 + 96) + 1024));
+    if (!d) return LHB200_ENOMEM;
+    uint8_t *d48 = d + (size_t)n * 32, *d96 = d48 + (size_t)n * 48;
+    LHB_CUDA(cudaMemcpyAsync(d, sk32, (size_t)n * 32, cudaMemcpyHostToDevice, c.stream));
+    k_sk_to_pk<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, n, pk48 ? d48 : nullptr, pk96 ? d96 : nullptr);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    if (pk48) LHB_CUDA(cudaMemcpyAsync(pk48, d48, (size_t)n * 48, cudaMemcpyDeviceToHost, c.stream));
+    if (pk96) LHB_CUDA(cudaMemcpyAsync(pk96, d96, (size_t)n * 96, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    return LHB200_OK;
+}
+
+// TSecretKey::sign (blst.rs:282-298 / generic_secret_key.rs): sig_i = sk_i * H(msg_i), compressed 96 B.
+int32_t lhb200_sign(const uint8_t* sk32, const uint8_t* msg32, uint32_t n, uint8_t* sig96) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!sk32 || !msg32 || !sig96) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch((size_t)n * (32 + 32 + 96) + 1024));
+    if (!d) return LHB200_ENOMEM;
+    uint8_t *dm = d + (size_t)n * 32, *ds = dm + (size_t)n * 32;
+    LHB_CUDA(cudaMemcpyAsync(d, sk32, (size_t)n * 32, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(dm, msg32, (size_t)n * 32, cudaMemcpyHostToDevice, c.stream));
+    k_sign<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, dm, n, ds);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(sig96, ds, (size_t)n * 96, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    return LHB200_OK;
+}
+
+// PublicKey::deserialize + key_validate for n compressed keys (blst.rs:130-140; the batch form of
+// validator_pubkey_cache.rs:116-118).  status[i]: 0 ok, 1 infinity (rejected, generic_public_key.rs:87-88),
+// 2 bad encoding / not on curve, 3 not in the r-order subgroup.  pk96[i] is zeroed unless status is 0.
+int32_t lhb200_g1_decompress_validate(const uint8_t* pk48, uint32_t n, uint8_t* pk96, uint8_t* status) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!pk48 || !pk96 || !status) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch((size_t)n * (48 + 96 + 1) + 1024));
+    if (!d) return LHB200_ENOMEM;
+    uint8_t *d96 = d + (size_t)n * 48, *dst = d96 + (size_t)n * 96;
+    LHB_CUDA(cudaMemcpyAsync(d, pk48, (size_t)n * 48, cudaMemcpyHostToDevice, c.stream));
+    k_g1_decompress_validate<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, n, d96, dst);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(pk96, d96, (size_t)n * 96, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    return LHB200_OK;
+}
+
+// Signature::deserialize for n compressed signatures (blst.rs:192-194): 192-byte affine out
+// (x.c1 | x.c0 | y.c1 | y.c0), status[i]: 0 ok, 1 infinity, 2 bad encoding / not on curve.  No subgroup check.
+int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, uint8_t* status) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!sig96 || !out192 || !status) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch((size_t)n * (96 + 192 + 1) + 1024));
+    if (!d) return LHB200_ENOMEM;
+    uint8_t *do_ = d + (size_t)n * 96, *dst = do_ + (size_t)n * 192;
+    LHB_CUDA(cudaMemcpyAsync(d, sig96, (size_t)n * 96, cudaMemcpyHostToDevice, c.stream));
+    k_g2_decompress<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, n, do_, dst);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(out192, do_, (size_t)n * 192, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    return LHB200_OK;
+}
+
+}  // extern "C"

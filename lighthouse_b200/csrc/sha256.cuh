@@ -18,7 +18,7 @@
 #else
 #define LHB_SHA_CONSTEXPR __host__ __device__ constexpr
 #define LHB_SHA_FN __device__ __forceinline__
-#define LHB_SHA_NOINLINE __device__ __noinline__
+#define LHB_SHA_NOINLINE static __device__ __noinline__
 #endif
 
 namespace lhb200 {

@@ -85,3 +85,90 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
     ])
     assert len(fixed) == DENEB_FIXED, len(fixed)
     return b"".join([fixed, hist, votes, vals, bal, pp, cp, inact, leph, summ])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Synthetic attestation SignatureSets.  Secret keys are the interop keys
+# (common/eth2_interop_keypairs/src/lib.rs:40-56); public keys and signatures are produced by the CUDA
+# library's own sk_to_pk / sign kernels (the SecretKey surface), so this module has no curve arithmetic.
+CURVE_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+MAINNET_GVR = bytes.fromhex("4b363db94e286120d76eb905340fdd4e54bfe9f06bf33ff6cf5ad27f511bfe95")
+
+
+def interop_secret_keys(n):
+    import hashlib
+    out = []
+    for i in range(n):
+        out.append(int.from_bytes(hashlib.sha256(i.to_bytes(32, "little")).digest(), "little") % CURVE_ORDER)
+    return out
+
+
+def _sha(b):
+    import hashlib
+    return hashlib.sha256(b).digest()
+
+
+def attester_domain(fork_version=bytes.fromhex("04000000"), gvr=MAINNET_GVR):
+    """compute_domain(DOMAIN_BEACON_ATTESTER = 1, fork_version, genesis_validators_root) (chain_spec.rs:548-566)"""
+    fork_data_root = _sha(fork_version + bytes(28) + gvr)
+    return (1).to_bytes(4, "little") + fork_data_root[:28]
+
+
+def attestation_signing_root(j, epoch, domain):
+    """signing_root(AttestationData{slot, index, beacon_block_root, source, target}, domain)
+    (attestation_data.rs:28-39, signing_data.rs:27-35).  Synthetic field values per SURVEY §8d."""
+    u64 = lambda v: v.to_bytes(8, "little") + bytes(24)
+    slot = (j // 64) % 32 + 32 * epoch
+    bbr = _sha(b"bbr" + j.to_bytes(8, "little"))
+    src = _sha(u64(epoch - 1) + _sha(b"src"))
+    tgt = _sha(u64(epoch) + _sha(b"tgt"))
+    z = bytes(32)
+    l1 = [_sha(u64(slot) + u64(j % 64)), _sha(bbr + src), _sha(tgt + z), _sha(z + z)]
+    root = _sha(_sha(l1[0] + l1[1]) + _sha(l1[2] + l1[3]))
+    return _sha(root + domain)
+
+
+class AttestationBatch:
+    """SoA buffers for lhb200_verify_signature_sets."""
+
+    def __init__(self, sigs, msgs, pks, offsets, committees, pk_table):
+        self.sigs, self.msgs, self.pks, self.offsets = sigs, msgs, pks, offsets
+        self.committees, self.pk_table = committees, pk_table
+        self.n_sets = len(offsets) - 1
+
+    @property
+    def input_bytes(self):
+        return len(self.sigs) + len(self.msgs) + len(self.pks) + 8 * self.n_sets
+
+
+def attestation_batch(n_sets, keys_per_set=128, n_validators=16384, seed=0x11570000, epoch=100):
+    """n_sets aggregate attestations, each signed by `keys_per_set` distinct validators.  Needs lhb200.init()."""
+    from . import bls
+    assert n_validators & (n_validators - 1) == 0 and keys_per_set <= n_validators
+    rng = np.random.default_rng(seed)
+    sks = interop_secret_keys(n_validators)
+    sk_bytes = b"".join(s.to_bytes(32, "big") for s in sks)
+    _, pk96 = bls.sk_to_pk(sk_bytes)
+    pk_tab = np.frombuffer(pk96, dtype=np.uint8).reshape(n_validators, 96)
+    # committee j = perm[(a_j + t*b_j) mod V], b_j odd  (distinct because V is a power of two)
+    perm = rng.permutation(n_validators)
+    a = rng.integers(0, n_validators, size=n_sets)
+    b = rng.integers(0, n_validators // 2, size=n_sets) * 2 + 1
+    t = np.arange(keys_per_set)
+    committees = perm[(a[:, None] + t[None, :] * b[:, None]) % n_validators]
+    # aggregate secret keys: limb-wise sums (8 x 32-bit words held in uint64), recombined with Python ints
+    words = np.array([[(s >> (32 * w)) & 0xFFFFFFFF for w in range(8)] for s in sks], dtype=np.uint64)
+    agg = []
+    for lo in range(0, n_sets, 8192):
+        ws = words[committees[lo:lo + 8192]].sum(axis=1)  # [chunk, 8]
+        for row in ws:
+            v = 0
+            for w in range(8):
+                v += int(row[w]) << (32 * w)
+            agg.append(v % CURVE_ORDER)
+    domain = attester_domain()
+    msgs = b"".join(attestation_signing_root(j, epoch, domain) for j in range(n_sets))
+    sigs = bls.sign(b"".join(v.to_bytes(32, "big") for v in agg), msgs)
+    pks = pk_tab[committees.reshape(-1)].tobytes()
+    offsets = (np.arange(n_sets + 1, dtype=np.uint64) * keys_per_set).astype(np.uint32)
+    return AttestationBatch(sigs, msgs, pks, offsets, committees, pk_tab)

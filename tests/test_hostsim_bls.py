@@ -1,0 +1,180 @@
+"""CPU-only: the device BLS math headers (lighthouse_b200/csrc/bls/*.cuh) compiled for the host with the PTX
+carry chains emulated (tests/hostsim), checked limb-exactly against the big-integer oracle.  This validates the
+exact algorithms that run on the GPU; the `-m gpu` tests then validate the GPU execution itself."""
+import ctypes as C
+import hashlib
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bls_ref as B
+from tests import oracle_lib as O
+
+HS = os.path.join(O.ROOT, "tests", "hostsim")
+P = B.P
+
+
+@pytest.fixture(scope="module")
+def L():
+    subprocess.check_call(["make", "-C", HS, "-s"])
+    return C.CDLL(os.path.join(HS, "libhostsim.so"))
+
+
+def be(x): return x.to_bytes(48, "big")
+def b2(a): return be(a[0]) + be(a[1])
+def f2_from(r): return (int.from_bytes(r[:48], "big"), int.from_bytes(r[48:96], "big"))
+
+
+def test_fp_ops(L):
+    rnd = random.Random(1)
+    def op(o, a, b=0):
+        out = C.create_string_buffer(48)
+        ok = L.hs_fp_op(o, be(a), be(b), out)
+        return ok, int.from_bytes(out.raw, "big")
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (1 << 380) % P, 2 ** 32 - 1, 2 ** 64 - 1, 2 ** 352]
+    vals = edge + [rnd.randrange(P) for _ in range(120)]
+    for a in vals:
+        for b in vals[:12] + [rnd.randrange(P)]:
+            assert op(0, a, b)[1] == a * b % P
+            assert op(1, a, b)[1] == (a + b) % P
+            assert op(2, a, b)[1] == (a - b) % P
+        assert op(4, a)[1] == -a % P
+    for a in vals[:40]:
+        if a:
+            assert op(3, a)[1] == pow(a, -1, P)
+        ok, s = op(5, a)
+        assert bool(ok) == (B.fp_sqrt(a) is not None)
+        if ok:
+            assert s * s % P == a
+
+
+def test_fp2_ops(L):
+    rnd = random.Random(2)
+    def op(o, a, b=(0, 0)):
+        out = C.create_string_buffer(96)
+        ok = L.hs_fp2_op(o, b2(a), b2(b), out)
+        return ok, f2_from(out.raw)
+    vals = [(0, 0), (1, 0), (0, 1), (P - 1, P - 1), (5, 0), (0, 7)] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(40)]
+    for a in vals:
+        for b in vals[:8]:
+            assert op(0, a, b)[1] == B.f2_mul(a, b)
+        assert op(1, a)[1] == B.f2_sqr(a)
+        if a != (0, 0):
+            assert op(2, a)[1] == B.f2_inv(a)
+        ok, s = op(3, a)
+        assert bool(ok) == (B.f2_sqrt(a) is not None)
+        if ok:
+            assert B.f2_sqr(s) == a
+        sq = B.f2_sqr(a)
+        ok, s = op(3, sq)
+        assert ok and B.f2_sqr(s) == sq
+        assert op(4, a)[0] == B.f2_sgn0(a)
+
+
+def f12_bytes(f):
+    (a, b, c), (d, e, g) = f
+    return b"".join(b2(x) for x in (a, b, c, d, e, g))
+
+
+def f12_from(bs):
+    v = [f2_from(bs[96 * i:96 * i + 96]) for i in range(6)]
+    return ((v[0], v[1], v[2]), (v[3], v[4], v[5]))
+
+
+def test_fp12_and_final_exp(L):
+    rnd = random.Random(3)
+    rf2 = lambda: (rnd.randrange(P), rnd.randrange(P))
+    rf12 = lambda: ((rf2(), rf2(), rf2()), (rf2(), rf2(), rf2()))
+    def op(o, a, b=None):
+        out = C.create_string_buffer(576)
+        L.hs_fp12_op(o, f12_bytes(a), f12_bytes(b or a), out)
+        return f12_from(out.raw)
+    a, b = rf12(), rf12()
+    assert op(0, a, b) == B.f12_mul(a, b)
+    assert op(1, a) == B.f12_sqr(a)
+    assert op(2, a) == B.f12_inv(a)
+    assert op(3, a) == B.f12_frob(a)
+    assert op(4, a) == B.f12_frob(B.f12_frob(a))
+    sp = ((b[0][0], b[0][1], (0, 0)), ((0, 0), b[0][2], (0, 0)))
+    assert op(7, a, b) == B.f12_mul(a, sp)
+    e = B.f12_mul(B.f12_conj(a), B.f12_inv(a))
+    e = B.f12_mul(B.f12_frob(B.f12_frob(e)), e)
+    assert op(5, e) == B.f12_sqr(e)                        # Granger-Scott cyclotomic squaring
+    ref = B.final_exp(a)
+    assert op(6, a) == B.f12_mul(B.f12_sqr(ref), ref)      # device final_exp returns the cube
+
+
+def words(k, n): return (C.c_uint32 * n)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def test_g1(L):
+    rnd = random.Random(4)
+    g96 = B.g1_uncompressed(B.G1_GEN)
+    for k in O.golden_json("interop_keypairs.json")[:4]:
+        sk = int(k["privkey"], 16)
+        o96, o48 = C.create_string_buffer(96), C.create_string_buffer(48)
+        assert L.hs_g1_mul(g96, words(sk, 8), 255, o96, o48) == 0
+        assert o48.raw.hex() == k["pubkey"][2:]
+        d96 = C.create_string_buffer(96)
+        assert L.hs_g1_decompress(o48.raw, d96) == 0 and d96.raw == o96.raw
+    pts = [B.g1_mul(B.G1_GEN, rnd.randrange(B.R)) for _ in range(9)]
+    pts += [pts[0], pts[3]]
+    s = None
+    for p in pts:
+        s = B.g1_add(s, p)
+    o = C.create_string_buffer(96)
+    assert L.hs_g1_sum(b"".join(B.g1_uncompressed(p) for p in pts), len(pts), o) == 0 and o.raw == B.g1_uncompressed(s)
+    assert L.hs_g1_sum(B.g1_uncompressed(pts[0]) + B.g1_uncompressed(B.g1_neg(pts[0])), 2, o) == 0 and o.raw[0] == 0x40
+
+
+def test_g2_and_hash_to_curve(L):
+    rnd = random.Random(5)
+    Q = B.g2_mul(B.G2_GEN, rnd.randrange(B.R))
+    qb = B.g2_compress(Q)
+    o = C.create_string_buffer(96)
+    assert L.hs_g2_roundtrip(qb, o) == 0 and o.raw == qb
+    assert L.hs_g2_roundtrip(B.g2_compress(None), o) == 1
+    assert L.hs_g2_subgroup(qb) == 1
+    x = (3, 1)
+    while True:
+        y = B.f2_sqrt(B.f2_add(B.f2_mul(B.f2_sqr(x), x), B.B2))
+        if y:
+            break
+        x = (x[0] + 1, 1)
+    assert not B.g2_in_subgroup((x, y)) and L.hs_g2_subgroup(B.g2_compress((x, y))) == 0
+    k = rnd.randrange(1 << 64)
+    assert L.hs_g2_mul(qb, words(k, 2), 64, o) == 0 and o.raw == B.g2_compress(B.g2_mul(Q, k))
+    for msg in (bytes(range(32)), bytes(32), hashlib.sha256(b"x").digest()):
+        o256 = C.create_string_buffer(256)
+        L.hs_expand(msg, o256)
+        assert o256.raw == B.expand_message_xmd(msg, B.DST, 256)
+        for u in B.hash_to_field_fp2(msg):
+            o192 = C.create_string_buffer(192)
+            L.hs_sswu(b2(u), o192)
+            assert (f2_from(o192.raw[:96]), f2_from(o192.raw[96:])) == B.map_to_curve_sswu(u)
+        L.hs_hash_to_g2(msg, o)
+        assert o.raw == B.g2_compress(B.hash_to_g2(msg))
+    for u in [(0, 0), (1, 0), (0, 1)]:  # includes the exceptional branch inputs
+        o192 = C.create_string_buffer(192)
+        L.hs_sswu(b2(u), o192)
+        assert (f2_from(o192.raw[:96]), f2_from(o192.raw[96:])) == B.map_to_curve_sswu(u)
+
+
+def test_pairing_and_verify(L):
+    Q = B.g2_mul(B.G2_GEN, 777)
+    Pt = B.g1_mul(B.G1_GEN, 12345)
+    for proj in (0, 1):
+        out = C.create_string_buffer(576)
+        assert L.hs_pairing(B.g1_uncompressed(Pt), B.g2_compress(Q), 1, proj, out) == 0
+        ref = B.pairing(B.g1_add(Pt, Pt) if proj else Pt, Q)
+        assert f12_from(out.raw) == B.f12_mul(B.f12_sqr(ref), ref)
+    d = O.golden_json("deposit_data.json")[0]
+    fv = bytes.fromhex(d["fork_version"])
+    fdr = hashlib.sha256(fv + bytes(28) + bytes(32)).digest()
+    m = hashlib.sha256(bytes.fromhex(d["deposit_message_root"]) + bytes([3, 0, 0, 0]) + fdr[:28]).digest()
+    pk = B.g1_uncompressed(B.g1_decompress(bytes.fromhex(d["pubkey"])))
+    sig = bytes.fromhex(d["signature"])
+    assert L.hs_verify(pk, m, sig) == 1
+    assert L.hs_verify(pk, bytes(32), sig) == 0
