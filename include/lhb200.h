@@ -150,6 +150,13 @@ LHB200_API int32_t lhb200_g1_decompress_validate(const uint8_t* pk48, uint32_t n
 LHB200_API int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, uint8_t* status);
 
 
+/* Test hook: run one stage of the BLS pipeline on a single device thread so `pytest -m gpu` can compare every
+ * stage with the oracle.  op: 0 expand_message_xmd(32->256), 1 hash_to_g2(32->96), 2 SSWU(u 96 -> x|y 192),
+ * 3 g2_decompress(96 -> [in_subgroup, 96 recompressed], rc=DecodeStatus), 4 g2_mul(96|u64le -> 96),
+ * 5 fp2 op([opcode|a|b] -> 96), 6 pairing+final_exp(g1 96|g2 96 -> 576), 7 g1 sum([n|n*96] -> 96). */
+LHB200_API int32_t lhb200_debug_bls(int32_t op, const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len,
+                                    int32_t* rc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,3 +318,12 @@ class Batch:
             self.destroy()
         except Exception:
             pass
+
+
+def debug_stage(op, data: bytes, out_len: int):
+    """lhb200_debug_bls test hook -> (rc, out bytes)"""
+    out = C.create_string_buffer(out_len)
+    rc = C.c_int32(0)
+    p, k = buf(data)
+    check(lib.lhb200_debug_bls(op, p, len(data), out, out_len, C.byref(rc)), "lhb200_debug_bls")
+    return rc.value, out.raw

@@ -19,7 +19,9 @@
 #define LHB_CONST static const
 #else
 #define LHB_HD __device__
+#ifndef LHB_NOINLINE
 #define LHB_NOINLINE __noinline__
+#endif
 #define LHB_INLINE __forceinline__
 #define LHB_CONST static __device__ __constant__ const
 #endif
@@ -134,6 +136,9 @@ LHB_HD LHB_INLINE void fp_final_sub(Fp& r, const uint32_t t[NL], uint32_t top) {
     for (int i = 0; i < NL; i++) r.v[i] = keep ? t[i] : s[i];
 }
 
+#ifdef LHB_FP_DECL_ONLY
+LHB_HD void fp_add(Fp& r, const Fp& a, const Fp& b);
+#else
 LHB_HD LHB_NOINLINE void fp_add(Fp& r, const Fp& a, const Fp& b) {
     uint32_t t[NL], top;
     add_cc(t[0], a.v[0], b.v[0]);
@@ -142,7 +147,11 @@ LHB_HD LHB_NOINLINE void fp_add(Fp& r, const Fp& a, const Fp& b) {
     addc(top, 0, 0);
     fp_final_sub(r, t, top);
 }
+#endif
 
+#ifdef LHB_FP_DECL_ONLY
+LHB_HD void fp_sub(Fp& r, const Fp& a, const Fp& b);
+#else
 LHB_HD LHB_NOINLINE void fp_sub(Fp& r, const Fp& a, const Fp& b) {
     uint32_t t[NL], m;
     sub_cc(t[0], a.v[0], b.v[0]);
@@ -157,6 +166,7 @@ LHB_HD LHB_NOINLINE void fp_sub(Fp& r, const Fp& a, const Fp& b) {
     for (int i = 1; i < NL - 1; i++) addc_cc(r.v[i], t[i], q[i]);
     addc(r.v[NL - 1], t[NL - 1], q[NL - 1]);
 }
+#endif
 
 LHB_HD LHB_INLINE void fp_neg(Fp& r, const Fp& a) {
     const bool z = fp_is_zero(a);
@@ -215,7 +225,11 @@ LHB_HD LHB_INLINE void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
     fp_final_sub(r, even, 0);
 }
 
+#ifdef LHB_FP_DECL_ONLY
+LHB_HD void fp_mul(Fp& r, const Fp& a, const Fp& b);
+#else
 LHB_HD LHB_NOINLINE void fp_mul(Fp& r, const Fp& a, const Fp& b) { fp_mul_inl(r, a, b); }
+#endif
 LHB_HD LHB_INLINE void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
 
 LHB_HD LHB_INLINE void fp_to_mont(Fp& r, const Fp& a) { fp_mul(r, a, FP_R2); }
@@ -228,6 +242,9 @@ LHB_HD LHB_INLINE void fp_from_mont(Fp& r, const Fp& a) {
 
 // r = a^((p-3)/4): 4-bit fixed window (15-entry table, 380 squarings + ~95 multiplications).
 // Serves sqrt (a * r), inverse (r^4 * a) and the quadratic-residue test (a * r^2 = a^((p-1)/2)).
+#ifdef LHB_FP_DECL_ONLY
+LHB_HD void fp_pow_pm3d4(Fp& r, const Fp& a);
+#else
 LHB_HD LHB_NOINLINE void fp_pow_pm3d4(Fp& r, const Fp& a) {
     Fp tab[16];
     tab[1] = a;
@@ -250,6 +267,7 @@ LHB_HD LHB_NOINLINE void fp_pow_pm3d4(Fp& r, const Fp& a) {
     }
     r = acc;
 }
+#endif
 
 // r = 1/a (a != 0); 0 -> 0
 LHB_HD LHB_INLINE void fp_inv(Fp& r, const Fp& a) {

@@ -74,7 +74,7 @@ LHB_HD LHB_INLINE void fp2_norm(Fp& n, const Fp2& a) {
 }
 
 // Simplified SWU onto E2': y^2 = x^3 + A'x + B'.  Output affine (x, y).
-LHB_HD LHB_NOINLINE void map_to_curve_sswu(Fp2& x, Fp2& y, const Fp2& u) {
+LHB_HD LHB_NOINLINE void map_to_curve_sswu(Fp2& x, Fp2& y, const Fp2& u, Fp2* trace = nullptr) {
     Fp2 tv1, tv2, x1n, x1d, xd2, D, N, t, a;
     fp2_sqr(tv1, u);
     fp2_mul(tv1, tv1, SSWU_Z);           // Z u^2
@@ -133,6 +133,11 @@ LHB_HD LHB_NOINLINE void map_to_curve_sswu(Fp2& x, Fp2& y, const Fp2& u) {
         fp2_mul(x, tv1, x1);             // x2 = Z u^2 x1
         fp2_mul(y, tv1, u);
         fp2_mul(y, y, y1);               // y2 = Z u^3 sqrt(Z g(x1))
+    }
+    if (trace) {  // stage probe for the parity tests
+        trace[0] = tv1; trace[1] = tv2; trace[2] = x1n; trace[3] = x1d; trace[4] = N; trace[5] = D; trace[6] = a;
+        trace[7].c0 = na; trace[7].c1 = t1; trace[8].c0 = s; trace[8].c1 = inv_na; trace[9] = target; trace[10] = y0;
+        trace[11] = invD; trace[12] = y1; trace[13] = x1; trace[14] = x; trace[15] = y;
     }
     if (fp2_sgn0(u) != fp2_sgn0(y)) fp2_neg(y, y);
 }

@@ -10,7 +10,7 @@
 #include <algorithm>
 #include <random>
 #include <vector>
-#include "bls/kernels.cuh"
+#include "bls/debug.cuh"
 #include "ctx.h"
 
 namespace lhb200 {
@@ -417,6 +417,27 @@ int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, 
     LHB_CUDA(cudaGetLastError());
     LHB_CUDA(cudaMemcpyAsync(out192, do_, (size_t)n * 192, cudaMemcpyDeviceToHost, c.stream));
     LHB_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    return LHB200_OK;
+}
+
+// Test hook: run one pipeline stage on a single device thread (op codes in bls/debug.cuh).
+int32_t lhb200_debug_bls(int32_t op, const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, int32_t* rc) {
+    LHB_REQUIRE_READY();
+    if (!in || !out || !rc) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch((size_t)in_len + out_len + 1024));
+    if (!d) return LHB200_ENOMEM;
+    uint8_t* d_out = d + ((in_len + 255) / 256) * 256;
+    int32_t* d_rc = reinterpret_cast<int32_t*>(d_out + ((out_len + 255) / 256) * 256);
+    LHB_CUDA(cudaMemcpyAsync(d, in, in_len, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemsetAsync(d_out, 0, out_len, c.stream));
+    k_debug_bls<<<1, 32, 0, c.stream>>>(op, d, d_out, d_rc);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(out, d_out, out_len, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(rc, d_rc, 4, cudaMemcpyDeviceToHost, c.stream));
     LHB_CUDA(cudaStreamSynchronize(c.stream));
     return LHB200_OK;
 }

@@ -140,3 +140,7 @@ EXPORT int hs_verify(const uint8_t* pk96, const uint8_t* msg32, const uint8_t* s
     fp12_mul(f1, f1, f2); final_exp(f1, f1);
     return fp12_is_one(f1) ? 1 : 0;
 }
+EXPORT void hs_sswu_trace(const uint8_t* u96, uint8_t* out) {
+    Fp2 u, x, y, tr[16]; fp2_in(u, u96); map_to_curve_sswu(x, y, u, tr);
+    for (int k = 0; k < 16; k++) fp2_out(out + 96 * k, tr[k]);
+}
