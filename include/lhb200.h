@@ -93,6 +93,9 @@ LHB200_API int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, con
 LHB200_API int32_t lhb200_state_release(lhb200_state* st);
 /* Algorithmic work of the last root computed on this handle: number of hash32_concat units. */
 LHB200_API uint64_t lhb200_state_hash_units(const lhb200_state* st);
+/* Device time (ms) of the dominant kernel (k_validator_roots) in the last completed root, from CUDA events on the
+ * launching stream; < 0 if unavailable. */
+LHB200_API float lhb200_state_dominant_kernel_ms(const lhb200_state* st);
 
 /* MerkleTree::create(leaves, depth) + generate_proof(index, depth) (consensus/merkle_proof/src/lib.rs:68-99,
  * :290-324): root and the bottom-up branch (depth * 32 bytes).  n <= 2^depth, depth <= 32. */
@@ -139,6 +142,9 @@ LHB200_API int32_t lhb200_bls_batch_result(lhb200_bls_batch* b, void* stream, ui
  * c0.c0.c0 .. c1.c2.c1).  NOTE: this is the cube of the canonical GT element (3 is coprime to r). */
 LHB200_API int32_t lhb200_bls_batch_gt(lhb200_bls_batch* b, uint8_t out576[576]);
 LHB200_API uint64_t lhb200_bls_batch_launches(const lhb200_bls_batch* b);
+/* Device time (ms) of the dominant kernel (k_miller) in the last completed enqueue, from CUDA events recorded on
+ * the launching stream; < 0 if unavailable. */
+LHB200_API float lhb200_bls_batch_dominant_kernel_ms(const lhb200_bls_batch* b);
 
 /* TSecretKey::public_key / ::sign (crypto/bls/src/impls/blst.rs:282-298): n big-endian 32-byte scalars (< r). */
 LHB200_API int32_t lhb200_sk_to_pk(const uint8_t* sk32, uint32_t n, uint8_t* pk48, uint8_t* pk96);

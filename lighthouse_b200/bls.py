@@ -308,6 +308,10 @@ class Batch:
     def launches(self):
         return lib.lhb200_bls_batch_launches(self._h)
 
+    @property
+    def dominant_kernel_ms(self):
+        return float(lib.lhb200_bls_batch_dominant_kernel_ms(self._h))
+
     def destroy(self):
         if self._h:
             lib.lhb200_bls_batch_destroy(self._h)

@@ -52,6 +52,7 @@ struct lhb200_bls_batch {
     uint8_t* h_res = nullptr;     // pinned: ok + status
     cudaStream_t s2 = nullptr;
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
+    cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller), for the roofline
     uint64_t launches_last = 0;
 };
 
@@ -66,6 +67,8 @@ static void batch_free(lhb200_bls_batch* b) {
     if (b->s2) cudaStreamDestroy(b->s2);
     if (b->e_fork) cudaEventDestroy(b->e_fork);
     if (b->e_join) cudaEventDestroy(b->e_join);
+    if (b->e_k0) cudaEventDestroy(b->e_k0);
+    if (b->e_k1) cudaEventDestroy(b->e_k1);
     delete b;
 }
 
@@ -108,7 +111,8 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaHostAlloc(result)"); }
     if ((e = cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_fork, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess) {
+        (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreate(&b->e_k0)) != cudaSuccess || (e = cudaEventCreate(&b->e_k1)) != cudaSuccess) {
         batch_free(b);
         return cuda_fail(e, "stream/event create");
     }
@@ -222,7 +226,9 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     }
     k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     k_hash_to_g2<<<grid, BLS_BLOCK, 0, s>>>(b->in_msgs, n, b->d_h);
+    LHB_CUDA(cudaEventRecord(b->e_k0, s));
     k_miller<<<grid, BLS_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);
+    LHB_CUDA(cudaEventRecord(b->e_k1, s));
     launches += 3;
     const Fp12* cur = b->d_f;
     {
@@ -312,6 +318,14 @@ int32_t lhb200_bls_batch_gt(lhb200_bls_batch* b, uint8_t out576[576]) {
 }
 
 uint64_t lhb200_bls_batch_launches(const lhb200_bls_batch* b) { return b ? b->launches_last : 0; }
+
+// Device time (ms, CUDA events on the launching stream) of the dominant kernel k_miller in the last completed
+// enqueue; negative if unavailable.  Call after the stream has been synchronised.
+float lhb200_bls_batch_dominant_kernel_ms(const lhb200_bls_batch* b) {
+    float ms = -1.f;
+    if (!b || cudaEventElapsedTime(&ms, b->e_k0, b->e_k1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
 
 // bls::verify_signature_sets (crypto/bls/src/impls/blst.rs:37-119).  *ok = 1 iff every set verifies.
 // n_sets == 0 -> *ok = 0 (blst.rs:42-44).  rands may be NULL (drawn internally, 64 nonzero bits each).

@@ -162,11 +162,13 @@ struct Plan {
 };
 
 // Enqueue a finished plan on `s`.  Literals must already be in the arena.
-static int32_t plan_enqueue(Plan& pl, cudaStream_t s) {
+static int32_t plan_enqueue(Plan& pl, cudaStream_t s, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
     for (const LeafLaunch& L : pl.leaves) {
         switch (L.kind) {
             case 0:
+                if (e0) cudaEventRecord(e0, s);
                 k_validator_roots<<<(unsigned)ceil_div(L.n, VAL_PER_CTA), VAL_PER_CTA, 0, s>>>(L.in, L.n, L.out);
+                if (e1) cudaEventRecord(e1, s);
                 break;
             case 1:
                 k_record_roots<<<(unsigned)ceil_div(L.n, 128), 128, 0, s>>>(L.in, L.n, 0, L.out);
@@ -346,6 +348,7 @@ struct lhb200_state {
     uint64_t field_ops[28];
     uint64_t root_op = 0;
     uint8_t* d_result = nullptr;  // 29 * 32 bytes: root + field roots gathered
+    cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around k_validator_roots
 };
 
 namespace lhb200 {
@@ -644,7 +647,8 @@ int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d
     LHB_REQUIRE_READY();
     if (!st) return LHB200_EINVAL;
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
-    int32_t rc = plan_enqueue(st->plan, s);
+    if (!st->e_k0) { cudaEventCreate(&st->e_k0); cudaEventCreate(&st->e_k1); }
+    int32_t rc = plan_enqueue(st->plan, s, st->e_k0, st->e_k1);
     if (rc) return rc;
     k_gather_nodes<<<1, 32, 0, s>>>(reinterpret_cast<const HashOp*>(st->plan.root_addr), 29, st->d_result);
     count_launch();
@@ -673,11 +677,19 @@ int32_t lhb200_state_release(lhb200_state* st) {
     if (!st) return LHB200_OK;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     if (st->arena) cudaFree(st->arena);
+    if (st->e_k0) cudaEventDestroy(st->e_k0);
+    if (st->e_k1) cudaEventDestroy(st->e_k1);
     delete st;
     return LHB200_OK;
 }
 
 uint64_t lhb200_state_hash_units(const lhb200_state* st) { return st ? st->plan.hash_units : 0; }
+
+float lhb200_state_dominant_kernel_ms(const lhb200_state* st) {
+    float ms = -1.f;
+    if (!st || !st->e_k0 || cudaEventElapsedTime(&ms, st->e_k0, st->e_k1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
 
 int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* field_roots) {
     LHB_REQUIRE_READY();

@@ -115,6 +115,10 @@ class ResidentState:
     def hash_units(self):
         return lib.lhb200_state_hash_units(self._h)
 
+    @property
+    def dominant_kernel_ms(self):
+        return float(lib.lhb200_state_dominant_kernel_ms(self._h))
+
     def release(self):
         if self._h:
             lib.lhb200_state_release(self._h)

@@ -90,3 +90,39 @@ def golden_json(name):
 
 def golden_validators(net):
     return lzma.open(os.path.join(GOLDEN, f"genesis_validators_{net}.bin.xz")).read()
+
+
+# ---- BLS C oracle (oracle/bls12_381.c)
+import numpy as _np
+
+
+def bls_verify_signature_sets(sigs, msgs, pks, offsets, rands, want_gt=False, want_muls=False, want_status=False):
+    n = len(offsets) - 1
+    offs = _np.ascontiguousarray(offsets, dtype=_np.uint32)
+    r = _np.ascontiguousarray(rands, dtype=_np.uint64)
+    st = _np.zeros(max(n, 1), dtype=_np.uint8)
+    gt = C.create_string_buffer(576)
+    muls = C.c_uint64(0)
+    L.orc_verify_signature_sets.restype = C.c_int
+    ok = L.orc_verify_signature_sets(sigs, msgs, pks, C.c_void_p(offs.ctypes.data), C.c_void_p(r.ctypes.data),
+                                     C.c_uint32(n), C.c_void_p(st.ctypes.data), gt, C.byref(muls))
+    out = [bool(ok)]
+    if want_gt:
+        out.append(gt.raw)
+    if want_muls:
+        out.append(muls.value)
+    if want_status:
+        out.append(st[:n])
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def bls_hash_to_g2(msg):
+    o = C.create_string_buffer(96); L.orc_hash_to_g2(msg, o); return o.raw
+
+
+def bls_sk_to_pk(sk_be32):
+    o = C.create_string_buffer(96); L.orc_sk_to_pk(sk_be32, o); return o.raw
+
+
+def bls_sign(sk_be32, msg):
+    o = C.create_string_buffer(96); L.orc_sign(sk_be32, msg, o); return o.raw
