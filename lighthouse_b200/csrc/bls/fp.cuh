@@ -31,7 +31,7 @@ namespace bls {
 
 constexpr int NL = 12;  // limbs
 
-struct Fp {
+struct alignas(16) Fp {
     uint32_t v[NL];
 };
 struct Fp2 {
@@ -136,10 +136,7 @@ LHB_HD LHB_INLINE void fp_final_sub(Fp& r, const uint32_t t[NL], uint32_t top) {
     for (int i = 0; i < NL; i++) r.v[i] = keep ? t[i] : s[i];
 }
 
-#ifdef LHB_FP_DECL_ONLY
-LHB_HD void fp_add(Fp& r, const Fp& a, const Fp& b);
-#else
-LHB_HD LHB_NOINLINE void fp_add(Fp& r, const Fp& a, const Fp& b) {
+LHB_HD LHB_INLINE void fp_add_inl(Fp& r, const Fp& a, const Fp& b) {
     uint32_t t[NL], top;
     add_cc(t[0], a.v[0], b.v[0]);
 #pragma unroll
@@ -147,12 +144,8 @@ LHB_HD LHB_NOINLINE void fp_add(Fp& r, const Fp& a, const Fp& b) {
     addc(top, 0, 0);
     fp_final_sub(r, t, top);
 }
-#endif
 
-#ifdef LHB_FP_DECL_ONLY
-LHB_HD void fp_sub(Fp& r, const Fp& a, const Fp& b);
-#else
-LHB_HD LHB_NOINLINE void fp_sub(Fp& r, const Fp& a, const Fp& b) {
+LHB_HD LHB_INLINE void fp_sub_inl(Fp& r, const Fp& a, const Fp& b) {
     uint32_t t[NL], m;
     sub_cc(t[0], a.v[0], b.v[0]);
 #pragma unroll
@@ -166,6 +159,12 @@ LHB_HD LHB_NOINLINE void fp_sub(Fp& r, const Fp& a, const Fp& b) {
     for (int i = 1; i < NL - 1; i++) addc_cc(r.v[i], t[i], q[i]);
     addc(r.v[NL - 1], t[NL - 1], q[NL - 1]);
 }
+#ifdef LHB_FP_DECL_ONLY
+LHB_HD void fp_add(Fp& r, const Fp& a, const Fp& b);
+LHB_HD void fp_sub(Fp& r, const Fp& a, const Fp& b);
+#else
+LHB_HD LHB_NOINLINE void fp_add(Fp& r, const Fp& a, const Fp& b) { Fp x = a, y = b, o; fp_add_inl(o, x, y); r = o; }
+LHB_HD LHB_NOINLINE void fp_sub(Fp& r, const Fp& a, const Fp& b) { Fp x = a, y = b, o; fp_sub_inl(o, x, y); r = o; }
 #endif
 
 LHB_HD LHB_INLINE void fp_neg(Fp& r, const Fp& a) {
@@ -228,7 +227,7 @@ LHB_HD LHB_INLINE void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
 #ifdef LHB_FP_DECL_ONLY
 LHB_HD void fp_mul(Fp& r, const Fp& a, const Fp& b);
 #else
-LHB_HD LHB_NOINLINE void fp_mul(Fp& r, const Fp& a, const Fp& b) { fp_mul_inl(r, a, b); }
+LHB_HD LHB_NOINLINE void fp_mul(Fp& r, const Fp& a, const Fp& b) { Fp x = a, y = b, o; fp_mul_inl(o, x, y); r = o; }
 #endif
 LHB_HD LHB_INLINE void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
 

@@ -13,46 +13,99 @@ struct Fp12 {
 };
 
 // ------------------------------------------------------------------------------------------------ Fp2
-LHB_HD LHB_INLINE void fp2_add(Fp2& r, const Fp2& a, const Fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
-LHB_HD LHB_INLINE void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
-LHB_HD LHB_INLINE void fp2_dbl(Fp2& r, const Fp2& a) { fp_add(r.c0, a.c0, a.c0); fp_add(r.c1, a.c1, a.c1); }
-LHB_HD LHB_INLINE void fp2_neg(Fp2& r, const Fp2& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
-LHB_HD LHB_INLINE void fp2_conj(Fp2& r, const Fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+// The Fp2 leaf operations are out-of-line and REGISTER-FUSED: operands are loaded once (LD.128), the whole Fp2
+// operation (three Montgomery products for a multiplication) runs in registers with its independent carry
+// chains interleaved by ptxas, and only the result is stored.  Versus composing fp_mul/fp_add calls this cuts
+// local-memory traffic ~3x and call overhead ~5x (profiles/r1_ncu_k_miller_100k_baseline.txt: the baseline was
+// stalled on local-memory latency).  Like the Fp leafs they live in the opaque TU (bls/fp_core.cu, §7 DESIGN.md).
 LHB_HD LHB_INLINE bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
 LHB_HD LHB_INLINE bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
 LHB_HD LHB_INLINE void fp2_set_zero(Fp2& a) { fp_set_zero(a.c0); fp_set_zero(a.c1); }
 LHB_HD LHB_INLINE void fp2_set_one(Fp2& a) { a.c0 = FP_ONE; fp_set_zero(a.c1); }
 LHB_HD LHB_INLINE void fp2_cmov(Fp2& r, const Fp2& a, bool c) { fp_cmov(r.c0, a.c0, c); fp_cmov(r.c1, a.c1, c); }
 
-// Karatsuba: 3 Fp multiplications
+#ifdef LHB_FP_DECL_ONLY
+LHB_HD void fp2_add(Fp2& r, const Fp2& a, const Fp2& b);
+LHB_HD void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b);
+LHB_HD void fp2_dbl(Fp2& r, const Fp2& a);
+LHB_HD void fp2_neg(Fp2& r, const Fp2& a);
+LHB_HD void fp2_conj(Fp2& r, const Fp2& a);
+LHB_HD void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b);
+LHB_HD void fp2_sqr(Fp2& r, const Fp2& a);
+LHB_HD void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& s);
+LHB_HD void fp2_mul_xi(Fp2& r, const Fp2& a);
+#else
+LHB_HD LHB_NOINLINE void fp2_add(Fp2& r, const Fp2& a, const Fp2& b) {
+    Fp2 x = a, y = b, o;
+    fp_add_inl(o.c0, x.c0, y.c0);
+    fp_add_inl(o.c1, x.c1, y.c1);
+    r = o;
+}
+LHB_HD LHB_NOINLINE void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) {
+    Fp2 x = a, y = b, o;
+    fp_sub_inl(o.c0, x.c0, y.c0);
+    fp_sub_inl(o.c1, x.c1, y.c1);
+    r = o;
+}
+LHB_HD LHB_NOINLINE void fp2_dbl(Fp2& r, const Fp2& a) {
+    Fp2 x = a, o;
+    fp_add_inl(o.c0, x.c0, x.c0);
+    fp_add_inl(o.c1, x.c1, x.c1);
+    r = o;
+}
+LHB_HD LHB_NOINLINE void fp2_neg(Fp2& r, const Fp2& a) {
+    Fp2 x = a, o;
+    fp_neg(o.c0, x.c0);
+    fp_neg(o.c1, x.c1);
+    r = o;
+}
+LHB_HD LHB_NOINLINE void fp2_conj(Fp2& r, const Fp2& a) {
+    Fp2 x = a, o;
+    o.c0 = x.c0;
+    fp_neg(o.c1, x.c1);
+    r = o;
+}
+// Karatsuba: 3 Montgomery products
 LHB_HD LHB_NOINLINE void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+    Fp2 x = a, y = b, o;
     Fp t0, t1, s0, s1;
-    fp_mul(t0, a.c0, b.c0);
-    fp_mul(t1, a.c1, b.c1);
-    fp_add(s0, a.c0, a.c1);
-    fp_add(s1, b.c0, b.c1);
-    fp_mul(s0, s0, s1);
-    fp_sub(r.c0, t0, t1);
-    fp_sub(s0, s0, t0);
-    fp_sub(r.c1, s0, t1);
+    fp_mul_inl(t0, x.c0, y.c0);
+    fp_mul_inl(t1, x.c1, y.c1);
+    fp_add_inl(s0, x.c0, x.c1);
+    fp_add_inl(s1, y.c0, y.c1);
+    fp_mul_inl(s0, s0, s1);
+    fp_sub_inl(o.c0, t0, t1);
+    fp_sub_inl(s0, s0, t0);
+    fp_sub_inl(o.c1, s0, t1);
+    r = o;
 }
-// (a0+a1)(a0-a1), 2 a0 a1 : 2 Fp multiplications
+// (a0+a1)(a0-a1), 2 a0 a1 : 2 Montgomery products
 LHB_HD LHB_NOINLINE void fp2_sqr(Fp2& r, const Fp2& a) {
+    Fp2 x = a, o;
     Fp s, d, m;
-    fp_add(s, a.c0, a.c1);
-    fp_sub(d, a.c0, a.c1);
-    fp_mul(m, a.c0, a.c1);
-    fp_mul(r.c0, s, d);
-    fp_add(r.c1, m, m);
+    fp_add_inl(s, x.c0, x.c1);
+    fp_sub_inl(d, x.c0, x.c1);
+    fp_mul_inl(m, x.c0, x.c1);
+    fp_mul_inl(o.c0, s, d);
+    fp_add_inl(o.c1, m, m);
+    r = o;
 }
-LHB_HD LHB_INLINE void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
+LHB_HD LHB_NOINLINE void fp2_mul_fp(Fp2& r, const Fp2& a, const Fp& s) {
+    Fp2 x = a, o;
+    Fp k = s;
+    fp_mul_inl(o.c0, x.c0, k);
+    fp_mul_inl(o.c1, x.c1, k);
+    r = o;
+}
 // multiply by xi = 1 + i
-LHB_HD LHB_INLINE void fp2_mul_xi(Fp2& r, const Fp2& a) {
-    Fp t;
-    fp_sub(t, a.c0, a.c1);
-    fp_add(r.c1, a.c0, a.c1);
-    r.c0 = t;
+LHB_HD LHB_NOINLINE void fp2_mul_xi(Fp2& r, const Fp2& a) {
+    Fp2 x = a, o;
+    fp_sub_inl(o.c0, x.c0, x.c1);
+    fp_add_inl(o.c1, x.c0, x.c1);
+    r = o;
 }
+#endif
+#ifndef LHB_FP_CORE_ONLY  // everything below is compiled only in the callers' TU
 LHB_HD LHB_INLINE void fp2_inv(Fp2& r, const Fp2& a) {
     Fp n, t;
     fp_sqr(n, a.c0);
@@ -334,6 +387,8 @@ LHB_HD LHB_NOINLINE void fp12_cyclotomic_sqr(Fp12& r, const Fp12& a) {
     fp2_add(u, t3, z5); fp2_dbl(u, u); fp2_add(o.c1.c2, u, t3);
     r = o;
 }
+
+#endif  // !LHB_FP_CORE_ONLY
 
 }  // namespace bls
 }  // namespace lhb200

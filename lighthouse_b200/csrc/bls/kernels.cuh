@@ -41,33 +41,34 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_sig_prepare(const uint8_t* __rest
                                                             const uint64_t* __restrict__ rands, uint32_t n,
                                                             G2Jac* __restrict__ sig_r, uint8_t* __restrict__ status,
                                                             uint32_t* __restrict__ fail) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    __align__(16) uint8_t b[96];
-    load_bytes16(b, sigs + 96ull * i, 96);
-    uint32_t nz = 0;
-    for (int k = 0; k < 96; k++) nz |= b[k];
-    G2Jac out;
-    jac_set_inf(out);
-    uint8_t st = SET_OK;
-    if (nz == 0) {
-        st = SET_EMPTY_SIG;
-    } else {
-        G2Affine a;
-        const int32_t rc = g2_decompress(a, b);
-        if (rc == DEC_BAD) st = SET_SIG_DECODE;
-        else if (rc == DEC_OK) {
-            if (!g2_in_subgroup(a)) st = SET_SIG_SUBGROUP;
-            else {
-                const uint64_t r = rands[i];
-                const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
-                jac_mul_affine(out, a, k, 64);
+    // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        __align__(16) uint8_t b[96];
+        load_bytes16(b, sigs + 96ull * i, 96);
+        uint32_t nz = 0;
+        for (int k = 0; k < 96; k++) nz |= b[k];
+        G2Jac out;
+        jac_set_inf(out);
+        uint8_t st = SET_OK;
+        if (nz == 0) {
+            st = SET_EMPTY_SIG;
+        } else {
+            G2Affine a;
+            const int32_t rc = g2_decompress(a, b);
+            if (rc == DEC_BAD) st = SET_SIG_DECODE;
+            else if (rc == DEC_OK) {
+                if (!g2_in_subgroup(a)) st = SET_SIG_SUBGROUP;
+                else {
+                    const uint64_t r = rands[i];
+                    const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
+                    jac_mul_affine(out, a, k, 64);
+                }
             }
+            // DEC_INFINITY: the infinity signature passes the subgroup check and contributes nothing to the sum
         }
-        // DEC_INFINITY: the infinity signature passes the subgroup check and contributes nothing to the sum
+        sig_r[i] = out;
+        if (st != SET_OK) { status[i] = st; atomicOr(fail, 1u); }
     }
-    sig_r[i] = out;
-    if (st != SET_OK) { status[i] = st; atomicOr(fail, 1u); }
 }
 
 __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate(const uint8_t* __restrict__ pks,
@@ -75,62 +76,65 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate(const uint8_t* __res
                                                              const uint64_t* __restrict__ rands, uint32_t n,
                                                              G1Proj3* __restrict__ out_p, uint8_t* __restrict__ status,
                                                              uint32_t* __restrict__ fail) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t lo = offsets[i], hi = offsets[i + 1];
-    uint8_t st = SET_OK;
-    G1Jac acc;
-    jac_set_inf(acc);
-    if (hi <= lo) st = SET_NO_KEYS;
-    for (uint32_t j = lo; j < hi && st == SET_OK; j++) {
-        __align__(16) uint8_t b[96];
-        load_bytes16(b, pks + 96ull * j, 96);
-        G1Affine a;
-        if (g1_from_uncompressed(a, b) == DEC_BAD) { st = SET_PK_DECODE; break; }
-        jac_add_affine(acc, acc, a);
+    // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t lo = offsets[i], hi = offsets[i + 1];
+        uint8_t st = SET_OK;
+        G1Jac acc;
+        jac_set_inf(acc);
+        if (hi <= lo) st = SET_NO_KEYS;
+        for (uint32_t j = lo; j < hi && st == SET_OK; j++) {
+            __align__(16) uint8_t b[96];
+            load_bytes16(b, pks + 96ull * j, 96);
+            G1Affine a;
+            if (g1_from_uncompressed(a, b) == DEC_BAD) { st = SET_PK_DECODE; break; }
+            jac_add_affine(acc, acc, a);
+        }
+        if (st == SET_OK && jac_is_inf(acc)) st = SET_APK_INFINITY;
+        G1Proj3 P;
+        if (st == SET_OK) {
+            const uint64_t r = rands[i];
+            const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
+            G1Jac ra;
+            jac_mul(ra, acc, k, 64);
+            g1proj3_from_jac(P, ra);
+        } else {
+            P.px = FP_ONE; P.py = FP_ONE; P.pz = FP_ONE;
+        }
+        out_p[i] = P;
+        if (st != SET_OK) { status[i] = st; atomicOr(fail, 1u); }
     }
-    if (st == SET_OK && jac_is_inf(acc)) st = SET_APK_INFINITY;
-    G1Proj3 P;
-    if (st == SET_OK) {
-        const uint64_t r = rands[i];
-        const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
-        G1Jac ra;
-        jac_mul(ra, acc, k, 64);
-        g1proj3_from_jac(P, ra);
-    } else {
-        P.px = FP_ONE; P.py = FP_ONE; P.pz = FP_ONE;
-    }
-    out_p[i] = P;
-    if (st != SET_OK) { status[i] = st; atomicOr(fail, 1u); }
 }
 
 __global__ void __launch_bounds__(BLS_BLOCK) k_hash_to_g2(const uint8_t* __restrict__ msgs, uint32_t n,
                                                            G2Affine* __restrict__ out_h) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    __align__(16) uint8_t m[32];
-    load_bytes16(m, msgs + 32ull * i, 32);
-    G2Jac j;
-    hash_to_g2_jac(j, m);
-    G2Affine a;
-    jac_to_affine(a, j);
-    out_h[i] = a;
+    // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        __align__(16) uint8_t m[32];
+        load_bytes16(m, msgs + 32ull * i, 32);
+        G2Jac j;
+        hash_to_g2_jac(j, m);
+        G2Affine a;
+        jac_to_affine(a, j);
+        out_h[i] = a;
+    }
 }
 
 __global__ void __launch_bounds__(BLS_BLOCK) k_miller(const G1Proj3* __restrict__ P, const G2Affine* __restrict__ H,
                                                        const uint8_t* __restrict__ status, uint32_t n,
                                                        Fp12* __restrict__ out_f) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fp12 f;
-    if (status[i] != SET_OK || H[i].inf) {
-        fp12_set_one(f);
-    } else {
-        G1Proj3 p = P[i];
-        G2Affine q = H[i];
-        miller_loop(f, p, q);
+    // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Fp12 f;
+        if (status[i] != SET_OK || H[i].inf) {
+            fp12_set_one(f);
+        } else {
+            G1Proj3 p = P[i];
+            G2Affine q = H[i];
+            miller_loop(f, p, q);
+        }
+        out_f[i] = f;
     }
-    out_f[i] = f;
 }
 
 // out[t] = prod in[t*chunk .. min(n,(t+1)*chunk))

@@ -6,6 +6,7 @@
 //   msgs  n x 32 B  signing roots            (generic_signature_set.rs:70)
 //   pks   K x 96 B  uncompressed affine G1   (validator_pubkey_cache.rs:195-199 format), CSR offsets n+1
 // and gets back the batch verdict.  All arithmetic runs on the device; there is no CPU fallback.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <random>
@@ -198,7 +199,16 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     if (!b || b->n == 0 || !b->in_sigs) { set_error("bls_batch_verify_enqueue: no inputs"); return LHB200_EINVAL; }
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
     const uint32_t n = b->n;
-    const uint32_t grid = cdiv(n, BLS_BLOCK);
+    // Resident CTAs per SM are capped (grid-stride kernels): fewer threads keep their 1-4 KB stacks in L1/L2.
+    // LHB_BLS_CTAS_PER_SM overrides (tuning knob; 0 = one CTA per BLS_BLOCK sets, i.e. no cap).
+    static const int ctas_per_sm = [] { const char* e = getenv("LHB_BLS_CTAS_PER_SM"); return e ? atoi(e) : 6; }();
+    static const int n_sm = [] { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx().device); return v; }();
+    uint32_t grid = cdiv(n, BLS_BLOCK);
+    if (ctas_per_sm > 0 && grid > (uint32_t)(n_sm * ctas_per_sm)) {
+        const uint32_t max_thr = (uint32_t)(n_sm * ctas_per_sm) * BLS_BLOCK;
+        const uint32_t per_thread = cdiv(n, max_thr);            // sets per thread, balanced across the grid
+        grid = cdiv(n, (uint64_t)per_thread * BLS_BLOCK);
+    }
     uint64_t launches = 0;
     LHB_CUDA(cudaMemsetAsync(b->d_status, 0, n, s));
     LHB_CUDA(cudaMemsetAsync(b->d_fail, 0, 4, s));
