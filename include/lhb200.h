@@ -138,6 +138,19 @@ LHB200_API int32_t lhb200_bls_batch_set_device_inputs(lhb200_bls_batch* b, const
                                                       uint32_t n_sets);
 LHB200_API int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream);
 LHB200_API int32_t lhb200_bls_batch_result(lhb200_bls_batch* b, void* stream, uint8_t* ok, uint8_t* set_status);
+/* Device-resident validator pubkey table — the mirror of ValidatorPubkeyCache
+ * (beacon_node/beacon_chain/src/validator_pubkey_cache.rs:20-25,138-140; same 96-byte key format it persists, :195-199).
+ * Keys are decoded to Montgomery form once at import; SignatureSets then carry u32 validator indices
+ * (what consensus/state_processing/src/per_block_processing/signature_sets.rs:315-320 gathers) instead of 96-byte keys:
+ * 512 B instead of 12 288 B per 128-key set on the host link. */
+typedef struct lhb200_pubkey_table lhb200_pubkey_table;
+LHB200_API int32_t lhb200_pubkey_table_create(uint64_t capacity, lhb200_pubkey_table** out);
+LHB200_API int32_t lhb200_pubkey_table_destroy(lhb200_pubkey_table* t);
+LHB200_API int32_t lhb200_pubkey_table_append(lhb200_pubkey_table* t, const uint8_t* pks96, uint64_t n);
+LHB200_API uint64_t lhb200_pubkey_table_len(const lhb200_pubkey_table* t);
+LHB200_API int32_t lhb200_bls_batch_upload_indexed(lhb200_bls_batch* b, const lhb200_pubkey_table* table,
+                                                   const uint8_t* sigs, const uint8_t* msgs, const uint32_t* key_indices,
+                                                   const uint32_t* pk_offsets, const uint64_t* rands, uint32_t n_sets);
 /* Test hook: final-exponentiated product of the last verify as 12 x 48-byte big-endian Fp (tower order
  * c0.c0.c0 .. c1.c2.c1).  NOTE: this is the cube of the canonical GT element (3 is coprime to r). */
 LHB200_API int32_t lhb200_bls_batch_gt(lhb200_bls_batch* b, uint8_t out576[576]);

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblhb200.so")
+LIB_PATH = os.environ.get("LHB200_LIB_PATH", os.path.join(_HERE, "liblhb200.so"))  # override: tuning experiments only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -102,3 +102,8 @@ _sig("lhb200_g2_decompress", C.c_int32, vp, C.c_uint32, vp, vp)
 _sig("lhb200_debug_bls", C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_int32))
 _sig("lhb200_bls_batch_dominant_kernel_ms", C.c_float, vp)
 _sig("lhb200_state_dominant_kernel_ms", C.c_float, vp)
+_sig("lhb200_pubkey_table_create", C.c_int32, C.c_uint64, C.POINTER(vp))
+_sig("lhb200_pubkey_table_destroy", C.c_int32, vp)
+_sig("lhb200_pubkey_table_append", C.c_int32, vp, vp, C.c_uint64)
+_sig("lhb200_pubkey_table_len", C.c_uint64, vp)
+_sig("lhb200_bls_batch_upload_indexed", C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_uint32)

@@ -268,6 +268,33 @@ def verify_signature_sets(sets, rands=None) -> bool:
     return verify_signature_sets_raw(sigs, msgs, pks, offs, rands)
 
 
+class PubkeyTable:
+    """Device-resident validator pubkey table (mirror of ValidatorPubkeyCache, validator_pubkey_cache.rs)."""
+
+    def __init__(self, capacity):
+        self._h = C.c_void_p()
+        check(lib.lhb200_pubkey_table_create(capacity, C.byref(self._h)), "lhb200_pubkey_table_create")
+
+    def append(self, pks96: bytes):
+        p, k = buf(pks96)
+        n = (len(pks96) if isinstance(pks96, (bytes, bytearray)) else k.nbytes) // 96
+        check(lib.lhb200_pubkey_table_append(self._h, p, n), "lhb200_pubkey_table_append")
+
+    def __len__(self):
+        return int(lib.lhb200_pubkey_table_len(self._h))
+
+    def destroy(self):
+        if self._h:
+            lib.lhb200_pubkey_table_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class Batch:
     """Staged verify (lhb200_bls_batch_*): device-resident inputs, enqueue on a stream, read the verdict."""
 
@@ -283,6 +310,16 @@ class Batch:
         ps, k1 = buf(sigs); pm, k2 = buf(msgs); pp, k3 = buf(pks)
         check(lib.lhb200_bls_batch_upload(self._h, ps, pm, pp, offs.ctypes.data, None if r is None else r.ctypes.data,
                                           self.n), "lhb200_bls_batch_upload")
+
+    def upload_indexed(self, table, sigs, msgs, indices, offsets, rands=None):
+        offs = np.ascontiguousarray(offsets, dtype=np.uint32)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        self.n = len(offs) - 1
+        r = None if rands is None else np.ascontiguousarray(rands, dtype=np.uint64)
+        ps, k1 = buf(sigs); pm, k2 = buf(msgs)
+        check(lib.lhb200_bls_batch_upload_indexed(self._h, table._h, ps, pm, idx.ctypes.data, offs.ctypes.data,
+                                                  None if r is None else r.ctypes.data, self.n),
+              "lhb200_bls_batch_upload_indexed")
 
     def set_device_inputs(self, d_sigs, d_msgs, d_pks, d_offsets, d_rands, n):
         self.n = n

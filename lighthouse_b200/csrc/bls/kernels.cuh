@@ -106,6 +106,65 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate(const uint8_t* __res
     }
 }
 
+// Device-resident pubkey table (mirror of ValidatorPubkeyCache, beacon_chain/src/validator_pubkey_cache.rs:20-25):
+// entries are affine G1 in Montgomery form, converted once at import, so per-set aggregation needs no decoding.
+struct G1Mont {
+    Fp x, y;
+};
+__global__ void __launch_bounds__(BLS_BLOCK) k_table_import(const uint8_t* __restrict__ pks96, uint32_t n,
+                                                             G1Mont* __restrict__ out, uint32_t* __restrict__ n_bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __align__(16) uint8_t b[96];
+    load_bytes16(b, pks96 + 96ull * i, 96);
+    G1Affine a;
+    const int32_t rc = g1_from_uncompressed(a, b);
+    G1Mont m;
+    m.x = a.x; m.y = a.y;
+    if (rc != DEC_OK || !g1_on_curve(a)) {  // infinity is rejected at import like generic_public_key.rs:87-88
+        atomicAdd(n_bad, 1u);
+        fp_set_zero(m.x); fp_set_zero(m.y);
+    }
+    out[i] = m;
+}
+
+__global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate_indexed(const G1Mont* __restrict__ table, uint32_t table_len,
+                                                                     const uint32_t* __restrict__ indices,
+                                                                     const uint32_t* __restrict__ offsets,
+                                                                     const uint64_t* __restrict__ rands, uint32_t n,
+                                                                     G1Proj3* __restrict__ out_p,
+                                                                     uint8_t* __restrict__ status,
+                                                                     uint32_t* __restrict__ fail) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t lo = offsets[i], hi = offsets[i + 1];
+        uint8_t st = SET_OK;
+        G1Jac acc;
+        jac_set_inf(acc);
+        if (hi <= lo) st = SET_NO_KEYS;
+        for (uint32_t j = lo; j < hi && st == SET_OK; j++) {
+            const uint32_t idx = __ldg(indices + j);
+            if (idx >= table_len) { st = SET_PK_DECODE; break; }
+            G1Affine a;
+            const G1Mont& m = table[idx];
+            a.x = m.x; a.y = m.y; a.inf = 0;
+            jac_add_affine(acc, acc, a);
+        }
+        if (st == SET_OK && jac_is_inf(acc)) st = SET_APK_INFINITY;
+        G1Proj3 P;
+        if (st == SET_OK) {
+            const uint64_t r = rands[i];
+            const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
+            G1Jac ra;
+            jac_mul(ra, acc, k, 64);
+            g1proj3_from_jac(P, ra);
+        } else {
+            P.px = FP_ONE; P.py = FP_ONE; P.pz = FP_ONE;
+        }
+        out_p[i] = P;
+        if (st != SET_OK) { status[i] = st; atomicOr(fail, 1u); }
+    }
+}
+
 __global__ void __launch_bounds__(BLS_BLOCK) k_hash_to_g2(const uint8_t* __restrict__ msgs, uint32_t n,
                                                            G2Affine* __restrict__ out_h) {
     // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident

@@ -27,7 +27,17 @@ void bls_shutdown() {}
 
 using namespace lhb200;
 
+struct lhb200_pubkey_table {
+    G1Mont* d_keys = nullptr;
+    uint64_t capacity = 0, len = 0;
+};
+
 struct lhb200_bls_batch {
+    // indexed mode: keys come from a device-resident table
+    const lhb200_pubkey_table* table = nullptr;
+    uint32_t* d_indices = nullptr;
+    uint64_t cap_indices = 0;
+    const uint32_t* in_indices = nullptr;
     uint32_t cap_sets = 0;
     uint64_t cap_keys = 0;
     uint32_t n = 0;
@@ -59,6 +69,7 @@ struct lhb200_bls_batch {
 
 static void batch_free(lhb200_bls_batch* b) {
     if (!b) return;
+    if (b->d_indices) cudaFree(b->d_indices);
     void* ptrs[] = {b->d_sigs, b->d_msgs, b->d_pks, b->d_offsets, b->d_rands, b->d_sigr, b->d_sig_tmp[0],
                     b->d_sig_tmp[1], b->d_p, b->d_h, b->d_f, b->d_f_tmp[0], b->d_f_tmp[1], b->d_flast, b->d_gt,
                     b->d_status, b->d_fail, b->d_ok};
@@ -172,6 +183,90 @@ int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* sigs, const 
     b->n = n_sets;
     b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = b->d_pks;
     b->in_offsets = b->d_offsets; b->in_rands = b->d_rands;
+    b->table = nullptr;
+    return LHB200_OK;
+}
+
+// ---- device-resident pubkey table (mirror of ValidatorPubkeyCache) ---------------------------
+int32_t lhb200_pubkey_table_create(uint64_t capacity, lhb200_pubkey_table** out) {
+    LHB_REQUIRE_READY();
+    if (!out || capacity == 0) return LHB200_EINVAL;
+    lhb200_pubkey_table* t = new lhb200_pubkey_table();
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->d_keys), capacity * sizeof(G1Mont));
+    if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(pubkey table)"); }
+    t->capacity = capacity;
+    *out = t;
+    return LHB200_OK;
+}
+int32_t lhb200_pubkey_table_destroy(lhb200_pubkey_table* t) {
+    if (!t) return LHB200_OK;
+    if (ctx().ready) cudaDeviceSynchronize();
+    if (t->d_keys) cudaFree(t->d_keys);
+    delete t;
+    return LHB200_OK;
+}
+uint64_t lhb200_pubkey_table_len(const lhb200_pubkey_table* t) { return t ? t->len : 0; }
+
+// Append n validated keys (96-byte uncompressed, the validator_pubkey_cache.rs:195-199 format) at indices
+// [len, len+n).  Malformed / off-curve / infinity entries make the call fail with LHB200_EDECODE (nothing appended).
+int32_t lhb200_pubkey_table_append(lhb200_pubkey_table* t, const uint8_t* pks96, uint64_t n) {
+    LHB_REQUIRE_READY();
+    if (!t || (n && !pks96)) return LHB200_EINVAL;
+    if (t->len + n > t->capacity) { set_error("pubkey table full"); return LHB200_EINVAL; }
+    if (n == 0) return LHB200_OK;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(n * 96 + 256));
+    if (!d) return LHB200_ENOMEM;
+    uint32_t* d_bad = reinterpret_cast<uint32_t*>(d + ((n * 96 + 15) / 16) * 16);
+    LHB_CUDA(cudaMemcpyAsync(d, pks96, n * 96, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    k_table_import<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, (uint32_t)n, t->d_keys + t->len, d_bad);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    uint32_t bad = 0;
+    LHB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    if (bad) { set_error("%u of %llu keys are malformed, off-curve or at infinity", bad, (unsigned long long)n); return LHB200_EDECODE; }
+    t->len += n;
+    return LHB200_OK;
+}
+
+// Like lhb200_bls_batch_upload, but the signing keys are given as indices into a resident table
+// (what signature_sets.rs:315-320 gathers from the pubkey cache): key_indices[K], CSR offsets as before.
+int32_t lhb200_bls_batch_upload_indexed(lhb200_bls_batch* b, const lhb200_pubkey_table* table, const uint8_t* sigs,
+                                        const uint8_t* msgs, const uint32_t* key_indices, const uint32_t* pk_offsets,
+                                        const uint64_t* rands, uint32_t n_sets) {
+    LHB_REQUIRE_READY();
+    if (!b || !table || n_sets == 0 || n_sets > b->cap_sets || !sigs || !msgs || !pk_offsets) {
+        set_error("bls_batch_upload_indexed: bad arguments");
+        return LHB200_EINVAL;
+    }
+    const uint64_t n_keys = pk_offsets[n_sets];
+    if (n_keys && !key_indices) return LHB200_EINVAL;
+    for (uint32_t i = 0; i < n_sets; i++)
+        if (pk_offsets[i] > pk_offsets[i + 1]) { set_error("bls_batch_upload_indexed: offsets not monotone"); return LHB200_EINVAL; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    cudaStream_t s = c.stream;
+    if (n_keys > b->cap_indices) {
+        if (b->d_indices) { cudaStreamSynchronize(s); cudaFree(b->d_indices); b->d_indices = nullptr; }
+        LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_indices), std::max<uint64_t>(n_keys, 1) * 4));
+        b->cap_indices = n_keys;
+    }
+    std::vector<uint64_t> rbuf;
+    if (!rands) { rbuf.resize(n_sets); gen_rands(rbuf.data(), n_sets); rands = rbuf.data(); }
+    else for (uint32_t i = 0; i < n_sets; i++) if (rands[i] == 0) { set_error("zero random scalar"); return LHB200_EINVAL; }
+    LHB_CUDA(cudaMemcpyAsync(b->d_sigs, sigs, (size_t)n_sets * 96, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_msgs, msgs, (size_t)n_sets * 32, cudaMemcpyHostToDevice, s));
+    if (n_keys) LHB_CUDA(cudaMemcpyAsync(b->d_indices, key_indices, (size_t)n_keys * 4, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_offsets, pk_offsets, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_rands, rands, (size_t)n_sets * 8, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaStreamSynchronize(s));
+    b->n = n_sets;
+    b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = nullptr;
+    b->in_offsets = b->d_offsets; b->in_rands = b->d_rands; b->in_indices = b->d_indices;
+    b->table = table;
     return LHB200_OK;
 }
 
@@ -191,6 +286,7 @@ int32_t lhb200_bls_batch_set_device_inputs(lhb200_bls_batch* b, const void* d_si
     b->in_pks = static_cast<const uint8_t*>(d_pks);
     b->in_offsets = static_cast<const uint32_t*>(d_offsets);
     b->in_rands = static_cast<const uint64_t*>(d_rands);
+    b->table = nullptr;
     return LHB200_OK;
 }
 
@@ -201,7 +297,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     const uint32_t n = b->n;
     // Resident CTAs per SM are capped (grid-stride kernels): fewer threads keep their 1-4 KB stacks in L1/L2.
     // LHB_BLS_CTAS_PER_SM overrides (tuning knob; 0 = one CTA per BLS_BLOCK sets, i.e. no cap).
-    static const int ctas_per_sm = [] { const char* e = getenv("LHB_BLS_CTAS_PER_SM"); return e ? atoi(e) : 6; }();
+    static const int ctas_per_sm = [] { const char* e = getenv("LHB_BLS_CTAS_PER_SM"); return e ? atoi(e) : 12; }();
     static const int n_sm = [] { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx().device); return v; }();
     uint32_t grid = cdiv(n, BLS_BLOCK);
     if (ctas_per_sm > 0 && grid > (uint32_t)(n_sm * ctas_per_sm)) {
@@ -234,7 +330,11 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         launches++;
         LHB_CUDA(cudaEventRecord(b->e_join, b->s2));
     }
-    k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
+    if (b->table)
+        k_pk_aggregate_indexed<<<grid, BLS_BLOCK, 0, s>>>(b->table->d_keys, (uint32_t)b->table->len, b->in_indices,
+                                                         b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
+    else
+        k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     k_hash_to_g2<<<grid, BLS_BLOCK, 0, s>>>(b->in_msgs, n, b->d_h);
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
     k_miller<<<grid, BLS_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);

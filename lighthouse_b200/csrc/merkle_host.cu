@@ -341,6 +341,9 @@ static inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uin
 
 }  // namespace lhb200
 
+static uint8_t* g_spare_arena = nullptr;  // guarded by ctx().mu
+static size_t g_spare_bytes = 0;
+
 struct lhb200_state {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
@@ -595,10 +598,17 @@ int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state*
     size_t prog = align_up(dry.ops.size() * sizeof(HashOp), 256) + align_up((dry.ops.size() + 2) * 4, 256) + 512;
     size_t need = align_up(dry.bump, 256) + prog + 29 * 32 + 29 * sizeof(HashOp) + 1024;
     std::unique_ptr<lhb200_state> st(new lhb200_state());
-    LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->arena), need));
-    st->arena_bytes = need;
+    if (g_spare_arena && g_spare_bytes >= need) {       // recycled from the last released handle (no cudaMalloc)
+        st->arena = g_spare_arena;
+        st->arena_bytes = g_spare_bytes;
+        g_spare_arena = nullptr;
+        g_spare_bytes = 0;
+    } else {
+        LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->arena), need + (need >> 3)));
+        st->arena_bytes = need + (need >> 3);
+    }
     std::vector<StageCopy> copies;
-    rc = build_plan(st->plan, st->arena, need, lit_cap, [&](Plan& p) {
+    rc = build_plan(st->plan, st->arena, st->arena_bytes, lit_cap, [&](Plan& p) {
         rc = describe_deneb(p, ssz, len, &copies, st->field_ops, &st->root_op);
     });
     if (rc) { cudaFree(st->arena); return rc; }
@@ -675,8 +685,13 @@ int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t* field_root
 
 int32_t lhb200_state_release(lhb200_state* st) {
     if (!st) return LHB200_OK;
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
-    if (st->arena) cudaFree(st->arena);
+    if (st->arena) {  // keep one arena around for the next stage call (host-buffer entry point re-stages every call)
+        if (g_spare_arena) cudaFree(g_spare_arena);
+        g_spare_arena = st->arena;
+        g_spare_bytes = st->arena_bytes;
+    }
     if (st->e_k0) cudaEventDestroy(st->e_k0);
     if (st->e_k1) cudaEventDestroy(st->e_k1);
     delete st;

@@ -265,3 +265,39 @@ def test_ragged_sets_and_linearity(bls):
     assert not bls.verify_signature_sets(sets + [bad])
     assert bls.verify_signature_sets(sets[:4]) and bls.verify_signature_sets(sets[4:])
     assert not bls.verify_signature_sets(sets[:4] + [bad] + sets[4:])
+
+
+def test_pubkey_table_indexed_matches_explicit(bls):
+    """device-resident pubkey table (ValidatorPubkeyCache mirror) + u32 indices gives the same
+    verdicts as shipping the 96-byte keys, including the failure statuses."""
+    from lighthouse_b200.synthetic import attestation_batch
+    ab = attestation_batch(64, keys_per_set=32, n_validators=512, seed=5)
+    table = bls.PubkeyTable(600)
+    table.append(ab.pk_table.tobytes())
+    assert len(table) == 512
+    idx = ab.committees.reshape(-1).astype(np.uint32)
+    b = bls.Batch(64, 64 * 32)
+    b.upload_indexed(table, ab.sigs, ab.msgs, idx, ab.offsets)
+    b.enqueue()
+    assert b.result() is True
+    gt_indexed = b.gt_bytes()
+    rands = np.arange(1, 65, dtype=np.uint64) * 0x9E3779B97F4A7C15
+    b.upload_indexed(table, ab.sigs, ab.msgs, idx, ab.offsets, rands); b.enqueue(); assert b.result(); g1 = b.gt_bytes()
+    b.upload(ab.sigs, ab.msgs, ab.pks, ab.offsets, rands); b.enqueue(); assert b.result(); g2 = b.gt_bytes()
+    assert g1 == g2 and gt_indexed == g1                       # GT == 1 in all three
+    bad = idx.copy(); bad[40] = (bad[40] + 1) % 512            # wrong validator in one committee
+    b.upload_indexed(table, ab.sigs, ab.msgs, bad, ab.offsets, rands); b.enqueue()
+    ok, st = b.result(want_status=True)
+    assert not ok and not st.any()
+    bad[40] = 512                                              # index past the table
+    b.upload_indexed(table, ab.sigs, ab.msgs, bad, ab.offsets, rands); b.enqueue()
+    ok, st = b.result(want_status=True)
+    assert not ok and st[40 // 32] == 6
+    # import validation: infinity and off-curve keys are refused, nothing is appended
+    with pytest.raises(bls.Lhb200Error if hasattr(bls, "Lhb200Error") else Exception):
+        table.append(bytes([0x40]) + bytes(95))
+    off_curve = bytearray(ab.pk_table[0].tobytes()); off_curve[95] ^= 1
+    with pytest.raises(Exception):
+        table.append(bytes(off_curve))
+    assert len(table) == 512
+    b.destroy(); table.destroy()
