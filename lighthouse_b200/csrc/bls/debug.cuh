@@ -2,6 +2,7 @@
 // lets `pytest -m gpu` compare every stage of the BLS pipeline with the oracle, not just the final boolean.
 #pragma once
 #include "kernels.cuh"
+#include "coop.cuh"
 
 namespace lhb200 {
 namespace bls {

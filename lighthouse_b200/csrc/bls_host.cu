@@ -354,7 +354,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         }
     }
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));
-    k_final<<<1, 32, 0, s>>>(cur, b->d_flast, b->d_fail, b->d_ok, b->d_gt);
+    k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, b->d_flast, b->d_fail, b->d_ok, b->d_gt);
     launches++;
     LHB_CUDA(cudaGetLastError());
     count_launch(launches);
