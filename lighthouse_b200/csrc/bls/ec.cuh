@@ -272,6 +272,63 @@ LHB_HD LHB_INLINE bool jac_eq(const Jac<F>& a, const Jac<F>& b) {
     return f_eq(l, r);
 }
 
+// [r]P for a 64-bit r, SIMT-friendly: right-to-left over signed base-4 digits d_j in {-2,-1,0,1} with two
+// buckets (B1 collects +-4^j P for |d_j| = 1, B2 for |d_j| = 2), result B1 + 2 B2.  Every lane performs the same
+// 33 additions at the same program points (only the target bucket / sign differ), so a warp does 33 + 2 additions
+// instead of the ~64 a divergent double-and-add costs it.  `on_bit(i, D)` is called with D = 2^i P for i = 0..63
+// (k_sig_prepare uses it to collect [|x|]P from the same doublings).
+template <class F, class OnBit>
+LHB_HD LHB_INLINE void jac_mul_u64_buckets(Jac<F>& out, const Jac<F>& p, uint64_t r, OnBit on_bit) {
+    Jac<F> D = p, T, B1, B2;
+    jac_set_inf(B1);
+    jac_set_inf(B2);
+    uint32_t carry = 0;
+    for (int j = 0; j <= 32; j++) {
+        const uint32_t v = (j < 32 ? (uint32_t)((r >> (2 * j)) & 3u) : 0u) + carry;
+        const int d = v >= 2 ? (int)v - 4 : (int)v;
+        carry = v >= 2 ? 1u : 0u;
+        if (d != 0) {
+            T = D;
+            if (d < 0) f_neg(T.Y, D.Y);
+            Jac<F>* tgt = (d == 2 || d == -2) ? &B2 : &B1;
+            jac_add(*tgt, *tgt, T);
+        }
+        if (j < 32) {
+            on_bit(2 * j, D);
+            jac_dbl(D, D);
+            on_bit(2 * j + 1, D);
+            jac_dbl(D, D);
+        }
+    }
+    jac_dbl(B2, B2);
+    jac_add(out, B1, B2);
+}
+struct NoOnBit {
+    template <class J>
+    LHB_HD void operator()(int, const J&) const {}
+};
+template <class F>
+LHB_HD LHB_NOINLINE void jac_mul_u64(Jac<F>& out, const Jac<F>& p, uint64_t r) {
+    jac_mul_u64_buckets(out, p, r, NoOnBit());
+}
+
+// One pass computing BOTH [r]P and [|x|]P from the same 64 doublings of P (k_sig_prepare: r*sig for the batch sum,
+// [x]sig for the subgroup check).
+struct CollectX {
+    G2Jac* acc;
+    LHB_HD void operator()(int i, const G2Jac& D) const {
+        if ((BLS_X_ABS >> i) & 1) jac_add(*acc, *acc, D);
+    }
+};
+LHB_HD LHB_NOINLINE void g2_mul_r_and_x(G2Jac& out_r, G2Jac& out_x, const G2Affine& p, uint64_t r) {
+    G2Jac pj;
+    jac_from_affine(pj, p);
+    jac_set_inf(out_x);
+    CollectX cx;
+    cx.acc = &out_x;
+    jac_mul_u64_buckets(out_r, pj, r, cx);
+}
+
 // P in G2  <=>  psi(P) == [x]P = -[|x|]P   (blst.rs:75 subgroup_check).
 // The point at infinity passes (Appendix C item 3).
 LHB_HD LHB_NOINLINE bool g2_in_subgroup(const G2Affine& p) {

@@ -300,14 +300,14 @@ LHB_HD LHB_NOINLINE void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
     fp6_mul_v(t1, t1);
     fp6_add(r.c0, t0, t1);
 }
-// complex squaring: 2 Fp6 multiplications
+// complex squaring: 2 Fp6 multiplications, three Fp6 temporaries (stack footprint matters: DESIGN.md §2.3)
 LHB_HD LHB_NOINLINE void fp12_sqr(Fp12& r, const Fp12& a) {
-    Fp6 s, t, m, av;
-    fp6_add(s, a.c0, a.c1);          // a0 + a1
-    fp6_mul_v(av, a.c1);
-    fp6_add(t, a.c0, av);            // a0 + v a1
+    Fp6 m, s, t;
     fp6_mul(m, a.c0, a.c1);          // a0 a1
-    fp6_mul(s, s, t);                // (a0+a1)(a0+v a1) = a0^2 + v a1^2 + (1+v) a0 a1
+    fp6_mul_v(t, a.c1);
+    fp6_add(t, t, a.c0);             // a0 + v a1
+    fp6_add(s, a.c0, a.c1);          // a0 + a1
+    fp6_mul(s, s, t);                // a0^2 + v a1^2 + (1+v) a0 a1
     fp6_sub(s, s, m);
     fp6_mul_v(t, m);
     fp6_sub(r.c0, s, t);

@@ -57,12 +57,13 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_sig_prepare(const uint8_t* __rest
             const int32_t rc = g2_decompress(a, b);
             if (rc == DEC_BAD) st = SET_SIG_DECODE;
             else if (rc == DEC_OK) {
-                if (!g2_in_subgroup(a)) st = SET_SIG_SUBGROUP;
-                else {
-                    const uint64_t r = rands[i];
-                    const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
-                    jac_mul_affine(out, a, k, 64);
-                }
+                // [r]sig and [|x|]sig in one pass; in G2  <=>  psi(sig) == -[|x|]sig   (blst.rs:75)
+                G2Jac xs, ps, aj;
+                g2_mul_r_and_x(out, xs, a, rands[i]);
+                jac_neg(xs, xs);
+                jac_from_affine(aj, a);
+                g2_psi(ps, aj);
+                if (!jac_eq(ps, xs)) { st = SET_SIG_SUBGROUP; jac_set_inf(out); }
             }
             // DEC_INFINITY: the infinity signature passes the subgroup check and contributes nothing to the sum
         }
@@ -93,10 +94,8 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate(const uint8_t* __res
         if (st == SET_OK && jac_is_inf(acc)) st = SET_APK_INFINITY;
         G1Proj3 P;
         if (st == SET_OK) {
-            const uint64_t r = rands[i];
-            const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
             G1Jac ra;
-            jac_mul(ra, acc, k, 64);
+            jac_mul_u64(ra, acc, rands[i]);
             g1proj3_from_jac(P, ra);
         } else {
             P.px = FP_ONE; P.py = FP_ONE; P.pz = FP_ONE;
@@ -152,10 +151,8 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate_indexed(const G1Mont
         if (st == SET_OK && jac_is_inf(acc)) st = SET_APK_INFINITY;
         G1Proj3 P;
         if (st == SET_OK) {
-            const uint64_t r = rands[i];
-            const uint32_t k[2] = {(uint32_t)r, (uint32_t)(r >> 32)};
             G1Jac ra;
-            jac_mul(ra, acc, k, 64);
+            jac_mul_u64(ra, acc, rands[i]);
             g1proj3_from_jac(P, ra);
         } else {
             P.px = FP_ONE; P.py = FP_ONE; P.pz = FP_ONE;
@@ -188,9 +185,7 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_miller(const G1Proj3* __restrict_
         if (status[i] != SET_OK || H[i].inf) {
             fp12_set_one(f);
         } else {
-            G1Proj3 p = P[i];
-            G2Affine q = H[i];
-            miller_loop(f, p, q);
+            miller_loop(f, P[i], H[i]);   // operands are read in place (no 352-byte private copies)
         }
         out_f[i] = f;
     }

@@ -144,3 +144,15 @@ EXPORT void hs_sswu_trace(const uint8_t* u96, uint8_t* out) {
     Fp2 u, x, y, tr[16]; fp2_in(u, u96); map_to_curve_sswu(x, y, u, tr);
     for (int k = 0; k < 16; k++) fp2_out(out + 96 * k, tr[k]);
 }
+EXPORT int hs_g2_mul_r_and_x(const uint8_t* p96, uint64_t r, uint8_t* out_r96, uint8_t* out_x96) {
+    G2Affine a; if (g2_decompress(a, p96) == DEC_BAD) return -1;
+    G2Jac jr, jx; g2_mul_r_and_x(jr, jx, a, r);
+    G2Affine ar, ax; jac_to_affine(ar, jr); jac_to_affine(ax, jx);
+    g2_compress(out_r96, ar); g2_compress(out_x96, ax); return 0;
+}
+EXPORT int hs_g1_mul_u64(const uint8_t* p96, uint64_t r, uint8_t* out96) {
+    G1Affine a; if (g1_from_uncompressed(a, p96) == DEC_BAD) return -1;
+    G1Jac j, o; jac_from_affine(j, a); jac_dbl(j, j);   // Jacobian base with Z != 1 (2P)
+    jac_mul_u64(o, j, r);
+    G1Affine ar; jac_to_affine(ar, o); g1_to_uncompressed(out96, ar); return 0;
+}

@@ -119,6 +119,13 @@ def test_g1(L):
         assert o48.raw.hex() == k["pubkey"][2:]
         d96 = C.create_string_buffer(96)
         assert L.hs_g1_decompress(o48.raw, d96) == 0 and d96.raw == o96.raw
+    L.hs_g1_mul_u64.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
+    Pt = B.g1_mul(B.G1_GEN, 99)
+    for r in (1, 2, 3, 4, 0xFFFFFFFFFFFFFFFF, 0x8000000000000000, 0xAAAAAAAAAAAAAAAA, 0x5555555555555555,
+              rnd.randrange(1, 1 << 64)):
+        o = C.create_string_buffer(96)
+        assert L.hs_g1_mul_u64(B.g1_uncompressed(Pt), r, o) == 0
+        assert o.raw == B.g1_uncompressed(B.g1_mul(Pt, 2 * r)), hex(r)
     pts = [B.g1_mul(B.G1_GEN, rnd.randrange(B.R)) for _ in range(9)]
     pts += [pts[0], pts[3]]
     s = None
@@ -146,6 +153,12 @@ def test_g2_and_hash_to_curve(L):
     assert not B.g2_in_subgroup((x, y)) and L.hs_g2_subgroup(B.g2_compress((x, y))) == 0
     k = rnd.randrange(1 << 64)
     assert L.hs_g2_mul(qb, words(k, 2), 64, o) == 0 and o.raw == B.g2_compress(B.g2_mul(Q, k))
+    L.hs_g2_mul_r_and_x.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    for r in (1, 2, 3, 0xFFFFFFFFFFFFFFFF, 0x8000000000000000, 0xAAAAAAAAAAAAAAAA, rnd.randrange(1, 1 << 64)):
+        o2 = C.create_string_buffer(96)
+        assert L.hs_g2_mul_r_and_x(qb, r, o, o2) == 0
+        assert o.raw == B.g2_compress(B.g2_mul(Q, r)), hex(r)
+        assert o2.raw == B.g2_compress(B.g2_mul(Q, B.X_ABS))
     for msg in (bytes(range(32)), bytes(32), hashlib.sha256(b"x").digest()):
         o256 = C.create_string_buffer(256)
         L.hs_expand(msg, o256)
