@@ -90,6 +90,16 @@ LHB200_API int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t*
 /* Same as lhb200_state_root but only enqueues; the root lands in device memory (returned pointer valid until
  * the next call on this handle).  Used by bench.py to time kernels with CUDA events. */
 LHB200_API int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root);
+/* One state sharded over `world` GPUs (a power of two): rank r stages and hashes only its leaf range
+ * of the big lists (validators, balances, randao_mixes, participation x2, inactivity_scores) plus the small fields.
+ *   1. lhb200_state_stage_deneb_shard(ssz, len, rank, world, &h)       every rank, its own slice
+ *   2. lhb200_state_shard_roots(h, roots, &n)                          n x 32-byte subtree roots of this rank
+ *   3. all-gather the n*32 bytes over NCCL (rank-major)                 the path's single collective
+ *   4. lhb200_state_combine(h, gathered, out)                          every rank: log2(world) levels + ladders + top tree */
+LHB200_API int32_t lhb200_state_stage_deneb_shard(const uint8_t* ssz, uint64_t len, uint32_t rank, uint32_t world,
+                                                  lhb200_state** out);
+LHB200_API int32_t lhb200_state_shard_roots(lhb200_state* st, uint8_t* out, uint32_t* n_lists);
+LHB200_API int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t out[32]);
 LHB200_API int32_t lhb200_state_release(lhb200_state* st);
 /* Algorithmic work of the last root computed on this handle: number of hash32_concat units. */
 LHB200_API uint64_t lhb200_state_hash_units(const lhb200_state* st);

@@ -107,3 +107,6 @@ _sig("lhb200_pubkey_table_destroy", C.c_int32, vp)
 _sig("lhb200_pubkey_table_append", C.c_int32, vp, vp, C.c_uint64)
 _sig("lhb200_pubkey_table_len", C.c_uint64, vp)
 _sig("lhb200_bls_batch_upload_indexed", C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_uint32)
+_sig("lhb200_state_stage_deneb_shard", C.c_int32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp))
+_sig("lhb200_state_shard_roots", C.c_int32, vp, vp, C.POINTER(C.c_uint32))
+_sig("lhb200_state_combine", C.c_int32, vp, vp, vp)

@@ -341,6 +341,24 @@ static inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uin
 
 }  // namespace lhb200
 
+namespace lhb200 {
+// Multi-GPU sharding of one state: rank r of `world` (a power of two) owns the leaf range
+// [r * 2^s, (r+1) * 2^s) of every big list (s = ceil_log2(#chunks) - log2(world)) and produces the 32-byte root of
+// that height-s subtree; small fields are computed by every rank.  After one all-gather of the subtree roots each
+// rank folds them (log2(world) levels + zero ladder + length mix-in + the 32-leaf container) in lhb200_state_combine.
+struct ShardCfg {
+    uint32_t rank = 0, world = 1;
+};
+struct ShardedList {
+    int field;            // index in the 28-field container
+    uint32_t s;           // height of the per-rank subtree
+    uint32_t limit_depth; // chunk-tree depth of the list limit
+    uint64_t mix_len;     // length to mix in (lists); UINT64_MAX = vector (no mix-in)
+    uint64_t local_op;    // operand holding this rank's subtree root
+};
+
+}  // namespace lhb200
+
 static uint8_t* g_spare_arena = nullptr;  // guarded by ctx().mu
 static size_t g_spare_bytes = 0;
 
@@ -352,6 +370,8 @@ struct lhb200_state {
     uint64_t root_op = 0;
     uint8_t* d_result = nullptr;  // 29 * 32 bytes: root + field roots gathered
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around k_validator_roots
+    lhb200::ShardCfg shard;
+    std::vector<lhb200::ShardedList> sharded;
 };
 
 namespace lhb200 {
@@ -365,7 +385,8 @@ struct StageCopy {
 // Describe the whole Deneb state.  `s` = host SSZ (read for offsets and small literal fields only).
 // Big fields are placed in the arena by `place(src_off, nbytes)` which records an H2D copy.
 static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vector<StageCopy>* copies,
-                              uint64_t field_ops[28], uint64_t* root_op) {
+                              uint64_t field_ops[28], uint64_t* root_op, ShardCfg sh = ShardCfg(),
+                              std::vector<ShardedList>* sharded = nullptr) {
     using namespace deneb;
     if (len < FIXED) { set_error("BeaconStateDeneb SSZ shorter than its fixed part"); return LHB200_EINVAL; }
     const uint32_t o_hist = rd32(s + O_HIST_OFF), o_votes = rd32(s + O_VOTES_OFF), o_val = rd32(s + O_VAL_OFF),
@@ -393,6 +414,36 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
     };
     auto chunk = [&](uint32_t off) { return p.literal(s + off); };
     uint64_t* f = field_ops;
+    const uint32_t lg_world = ceil_log2(sh.world);
+    // Big list with `n_chunks` leaf chunks produced from `n_items` source items of `item_bytes` at `src_off`
+    // (leaf_kind < 0: the bytes already are the chunks).  Unsharded: the full field root.  Sharded: this rank's subtree.
+    auto big_list = [&](int field, size_t src_off, uint64_t n_items, uint32_t item_bytes, int leaf_kind,
+                        uint64_t n_chunks, uint32_t limit_depth, uint64_t mix_len) -> uint64_t {
+        const uint32_t d0 = ceil_log2(std::max<uint64_t>(n_chunks, 1));
+        const bool shard = sh.world > 1 && sharded && d0 >= lg_world + 6;
+        if (!shard) {
+            const uint8_t* src = place(src_off, n_items * item_bytes);
+            const uint8_t* chunks = leaf_kind >= 0 ? p.leaf_kernel(leaf_kind, src, n_items) : src;
+            uint64_t r = p.merkle_list(chunks, n_chunks, limit_depth);
+            return mix_len == UINT64_MAX ? r : p.mix_in_length(r, mix_len);
+        }
+        const uint32_t sub = d0 - lg_world;
+        const uint64_t c_lo = std::min<uint64_t>(n_chunks, (uint64_t)sh.rank << sub);
+        const uint64_t c_hi = std::min<uint64_t>(n_chunks, ((uint64_t)sh.rank + 1) << sub);
+        const uint64_t cnt = c_hi - c_lo;
+        uint64_t op;
+        if (leaf_kind >= 0) {          // one chunk per source item
+            const uint8_t* src = place(src_off + c_lo * item_bytes, cnt * item_bytes);
+            op = p.merkle_list(p.leaf_kernel(leaf_kind, src, cnt), cnt, sub);
+        } else {                       // packed bytes: chunk c covers bytes [32c, 32c+32) of the field
+            const uint64_t total_bytes = n_items * item_bytes;
+            const uint64_t b_lo = c_lo * 32, b_hi = std::min<uint64_t>(total_bytes, c_hi * 32);
+            const uint8_t* src = place(src_off + b_lo, b_hi > b_lo ? b_hi - b_lo : 0);
+            op = p.merkle_list(src, cnt, sub);
+        }
+        sharded->push_back({field, sub, limit_depth, mix_len, op});
+        return Plan::zero_op(0);       // placeholder; the field root is formed in lhb200_state_combine
+    };
     f[0] = p.literal_u64(rd64(s + O_GENESIS_TIME));
     f[1] = chunk(O_GVR);
     f[2] = p.literal_u64(rd64(s + O_SLOT));
@@ -406,17 +457,17 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
     f[8] = p.container({chunk(O_ETH1_DATA), p.literal_u64(rd64(s + O_ETH1_DATA + 32)), chunk(O_ETH1_DATA + 40)});
     f[9] = p.mix_in_length(p.merkle_list(p.leaf_kernel(2, place(o_votes, n_votes * 72), n_votes), n_votes, 11), n_votes);
     f[10] = p.literal_u64(rd64(s + O_DEPOSIT_INDEX));
-    f[11] = p.mix_in_length(p.merkle_list(p.leaf_kernel(0, place(o_val, n_val * 121), n_val), n_val, 40), n_val);
-    f[12] = p.mix_in_length(p.merkle_list(place(o_bal, n_bal * 8), ceil_div(n_bal * 8, 32), 38), n_bal);
-    f[13] = p.merkle_list(place(O_RANDAO, 65536 * 32), 65536, 16);
+    f[11] = big_list(11, o_val, n_val, 121, 0, n_val, 40, n_val);
+    f[12] = big_list(12, o_bal, n_bal, 8, -1, ceil_div(n_bal * 8, 32), 38, n_bal);
+    f[13] = big_list(13, O_RANDAO, 65536, 32, -1, 65536, 16, UINT64_MAX);
     f[14] = p.merkle_list(place(O_SLASHINGS, 8192 * 8), 2048, 11);
-    f[15] = p.mix_in_length(p.merkle_list(place(o_pp, n_pp), ceil_div(n_pp, 32), 35), n_pp);
-    f[16] = p.mix_in_length(p.merkle_list(place(o_cp, n_cp), ceil_div(n_cp, 32), 35), n_cp);
+    f[15] = big_list(15, o_pp, n_pp, 1, -1, ceil_div(n_pp, 32), 35, n_pp);
+    f[16] = big_list(16, o_cp, n_cp, 1, -1, ceil_div(n_cp, 32), 35, n_cp);
     f[17] = p.literal_bytes(s + O_JUST, 1);
     f[18] = p.container({p.literal_u64(rd64(s + O_PJC)), chunk(O_PJC + 8)});
     f[19] = p.container({p.literal_u64(rd64(s + O_CJC)), chunk(O_CJC + 8)});
     f[20] = p.container({p.literal_u64(rd64(s + O_FC)), chunk(O_FC + 8)});
-    f[21] = p.mix_in_length(p.merkle_list(place(o_inact, n_inact * 8), ceil_div(n_inact * 8, 32), 38), n_inact);
+    f[21] = big_list(21, o_inact, n_inact, 8, -1, ceil_div(n_inact * 8, 32), 38, n_inact);
     for (int k = 0; k < 2; k++) {
         uint8_t* roots = p.leaf_kernel(1, place(k ? O_NSC : O_CSC, SYNC_COMMITTEE_BYTES), 513);
         f[22 + k] = p.container({p.merkle_list(roots, 512, 9), reinterpret_cast<uint64_t>(roots + 512 * 32)});
@@ -584,16 +635,21 @@ int32_t lhb200_validator_roots(const uint8_t* ssz, uint64_t n, uint8_t* out_root
     return LHB200_OK;
 }
 
-int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state** out) {
+static int32_t stage_deneb(const uint8_t* ssz, uint64_t len, ShardCfg sh, lhb200_state** out) {
     LHB_REQUIRE_READY();
     if (!ssz || !out) return LHB200_EINVAL;
+    if (sh.world == 0 || (sh.world & (sh.world - 1)) || sh.rank >= sh.world) {
+        set_error("state shard: world must be a power of two and rank < world");
+        return LHB200_EINVAL;
+    }
     Ctx& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
     const size_t lit_cap = 16384;
     Plan dry;
     uint64_t fops[28], rop;
     int32_t rc = LHB200_OK;
-    build_plan(dry, nullptr, 0, lit_cap, [&](Plan& p) { rc = describe_deneb(p, ssz, len, nullptr, fops, &rop); });
+    std::vector<ShardedList> dry_sh;
+    build_plan(dry, nullptr, 0, lit_cap, [&](Plan& p) { rc = describe_deneb(p, ssz, len, nullptr, fops, &rop, sh, &dry_sh); });
     if (rc) return rc;
     size_t prog = align_up(dry.ops.size() * sizeof(HashOp), 256) + align_up((dry.ops.size() + 2) * 4, 256) + 512;
     size_t need = align_up(dry.bump, 256) + prog + 29 * 32 + 29 * sizeof(HashOp) + 1024;
@@ -609,8 +665,10 @@ int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state*
     }
     std::vector<StageCopy> copies;
     rc = build_plan(st->plan, st->arena, st->arena_bytes, lit_cap, [&](Plan& p) {
-        rc = describe_deneb(p, ssz, len, &copies, st->field_ops, &st->root_op);
+        st->sharded.clear();
+        rc = describe_deneb(p, ssz, len, &copies, st->field_ops, &st->root_op, sh, &st->sharded);
     });
+    st->shard = sh;
     if (rc) { cudaFree(st->arena); return rc; }
     // H2D: per-field copies into the aligned layout.  Pinned caller memory goes straight to the copy engine;
     // pageable memory is bounced through the pinned staging slab.
@@ -651,6 +709,70 @@ int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state*
     LHB_CUDA(cudaStreamSynchronize(c.stream));
     *out = st.release();
     return LHB200_OK;
+}
+
+int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state** out) {
+    return stage_deneb(ssz, len, ShardCfg(), out);
+}
+
+int32_t lhb200_state_stage_deneb_shard(const uint8_t* ssz, uint64_t len, uint32_t rank, uint32_t world,
+                                       lhb200_state** out) {
+    ShardCfg sh;
+    sh.rank = rank;
+    sh.world = world;
+    return stage_deneb(ssz, len, sh, out);
+}
+
+// Run this rank's part and return the subtree roots of the sharded lists (n_lists x 32 bytes, fixed list order).
+int32_t lhb200_state_shard_roots(lhb200_state* st, uint8_t* out, uint32_t* n_lists) {
+    LHB_REQUIRE_READY();
+    if (!st || !out || !n_lists) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    int32_t rc = lhb200_state_root_enqueue(st, c.stream, nullptr);
+    if (rc) return rc;
+    const uint32_t n = (uint32_t)st->sharded.size();
+    *n_lists = n;
+    if (n == 0) { LHB_CUDA(cudaStreamSynchronize(c.stream)); return LHB200_OK; }
+    std::vector<HashOp> gath(n);
+    for (uint32_t i = 0; i < n; i++) gath[i] = {0, st->sharded[i].local_op, 0};
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(n * sizeof(HashOp) + n * 32 + 512));
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(n * sizeof(HashOp) + n * 32 + 512));
+    if (!h || !d) return LHB200_ENOMEM;
+    memcpy(h, gath.data(), n * sizeof(HashOp));
+    uint8_t* d_res = d + ((n * sizeof(HashOp) + 255) / 256) * 256;
+    LHB_CUDA(cudaMemcpyAsync(d, h, n * sizeof(HashOp), cudaMemcpyHostToDevice, c.stream));
+    k_gather_nodes<<<1, 32, 0, c.stream>>>(reinterpret_cast<const HashOp*>(d), (int)n, d_res);
+    count_launch();
+    uint8_t* h_res = h + ((n * sizeof(HashOp) + 255) / 256) * 256;
+    LHB_CUDA(cudaMemcpyAsync(h_res, d_res, n * 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(out, h_res, n * 32);
+    return LHB200_OK;
+}
+
+// Fold the all-gathered subtree roots (rank-major: gathered[(g * n_lists + l) * 32]) into the state root.
+// Must be called after lhb200_state_shard_roots on the same handle (the unsharded field roots live in its arena).
+int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    if (!st || !gathered || !out) return LHB200_EINVAL;
+    const uint32_t n = (uint32_t)st->sharded.size(), world = st->shard.world;
+    uint32_t lg = 0;
+    while ((1u << lg) < world) lg++;
+    return run_simple(gathered, (size_t)world * n * 32, out, [&](Plan& p, uint8_t* d_in) {
+        std::vector<uint64_t> f(st->field_ops, st->field_ops + 28);
+        for (uint32_t l = 0; l < n; l++) {
+            const ShardedList& L = st->sharded[l];
+            std::vector<uint64_t> nodes;
+            for (uint32_t gidx = 0; gidx < world; gidx++)
+                nodes.push_back(reinterpret_cast<uint64_t>(d_in + ((size_t)gidx * n + l) * 32));
+            uint64_t r = p.small_tree(nodes, lg);
+            for (uint32_t d = L.s + lg; d < L.limit_depth; d++) r = p.op_hash(r, Plan::zero_op(d));
+            if (L.mix_len != UINT64_MAX) r = p.mix_in_length(r, L.mix_len);
+            f[L.field] = r;
+        }
+        return p.container(f);
+    });
 }
 
 int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root) {

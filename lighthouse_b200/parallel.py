@@ -64,3 +64,26 @@ def verify_signature_sets_sharded(sigs, msgs, pks, offsets, verify_fn, device=No
     lo, hi = shard_ranges_by_keys(offsets, world)[rank]
     ok = True if hi == lo else verify_fn(*shard_of(sigs, msgs, pks, offsets, lo, hi))
     return allreduce_verdict(ok, device)
+
+
+def beacon_state_root_sharded(ssz, device=None):
+    """hash_tree_root(BeaconStateDeneb) with the big lists sharded over the ranks of the default process group:
+    per-rank subtree roots -> one all-gather (32 bytes x lists x ranks) -> every rank folds the top.  world must be
+    a power of two.  Every SHA-256 runs on the GPUs (lighthouse_b200.tree_hash.ShardedState)."""
+    import torch
+    import torch.distributed as dist
+    from . import tree_hash as T
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    st = T.ShardedState(ssz, rank, world)
+    mine = st.shard_roots()
+    if world > 1:
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        out = torch.empty(world * len(mine), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(out, t)
+        gathered = bytes(out.cpu().tolist())
+    else:
+        gathered = mine
+    root = st.combine(gathered)
+    st.release()
+    return root

@@ -89,6 +89,40 @@ def beacon_state_root_deneb(ssz, want_field_roots=False):
     return out.raw
 
 
+class ShardedState:
+    """One rank's shard of a BeaconStateDeneb hashed over `world` GPUs."""
+
+    def __init__(self, ssz, rank, world):
+        self._h = C.c_void_p()
+        p, keep = buf(ssz)
+        n = len(ssz) if isinstance(ssz, (bytes, bytearray)) else keep.nbytes
+        check(lib.lhb200_state_stage_deneb_shard(p, n, rank, world, C.byref(self._h)), "lhb200_state_stage_deneb_shard")
+        self.world = world
+
+    def shard_roots(self) -> bytes:
+        out = C.create_string_buffer(32 * 16)
+        n = C.c_uint32(0)
+        check(lib.lhb200_state_shard_roots(self._h, out, C.byref(n)), "lhb200_state_shard_roots")
+        return out.raw[: 32 * n.value]
+
+    def combine(self, gathered: bytes) -> bytes:
+        out = C.create_string_buffer(32)
+        p, keep = buf(gathered)
+        check(lib.lhb200_state_combine(self._h, p, out), "lhb200_state_combine")
+        return out.raw
+
+    def release(self):
+        if self._h:
+            lib.lhb200_state_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class ResidentState:
     """A BeaconStateDeneb staged once into HBM and hashed from there."""
 

@@ -156,3 +156,21 @@ def test_merkle_tree_create_and_proofs(gpu):
     assert all(oks)
     oks = verify_merkle_proofs([leaves[i] for i in idxs], proofs, 10, [i + 1 for i in idxs], [root] * len(idxs))
     assert not any(oks)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("nv", [70_001, 300])
+def test_sharded_state_root_equals_full(gpu, world, nv):
+    """one state split into `world` leaf ranges (simulated in one process): per-rank subtree roots,
+    one all-gather, combine -> the same 32-byte root as the single-GPU path and the oracle."""
+    from lighthouse_b200 import tree_hash as T
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    ssz = beacon_state_deneb_ssz(nv, seed=nv)
+    want, _ = O.beacon_state_root_deneb(ssz)
+    shards = [T.ShardedState(ssz, r, world) for r in range(world)]
+    parts = [s.shard_roots() for s in shards]
+    assert len({len(p) for p in parts}) == 1
+    gathered = b"".join(parts)                      # what the all-gather delivers (rank-major)
+    for s in shards:
+        assert s.combine(gathered) == want
+        s.release()
