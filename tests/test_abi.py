@@ -42,5 +42,19 @@ def test_product_does_not_touch_oracle():
         for f in fs:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="replace").read()
-                assert "liboracle" not in txt and "oracle_lib" not in txt and "oracle/" not in txt.replace(
-                    "routing through oracle/", ""), f"{f} references the oracle"
+                assert "liboracle" not in txt and "oracle_lib" not in txt and "from oracle" not in txt and \
+                    "import oracle" not in txt and "oracle/" not in txt.replace("routing through oracle/", ""), \
+                    f"{f} references the oracle"
+
+
+def test_cpp_host_layer_builds_and_fails_loudly_without_gpu():
+    """include/lhb200.hpp compiles and links against the C ABI; without a device the program reports ENODEV
+    (exit code 2) instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"])
+    exe = os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
+    assert os.path.exists(exe)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "/dev/null"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no device" in r.stderr

@@ -301,3 +301,71 @@ def test_pubkey_table_indexed_matches_explicit(bls):
         table.append(bytes(off_curve))
     assert len(table) == 512
     b.destroy(); table.destroy()
+
+
+def test_full_size_batch_properties(bls):
+    """BASELINE configs[2] at full size (100 000 sets x 128 keys): size-independent properties — a valid batch
+    verifies, any single corrupted unit (signature / message / key index) flips the verdict, and the verdict does
+    not depend on the random scalars."""
+    from lighthouse_b200.synthetic import attestation_batch
+    n, k = 100_000, 128
+    ab = attestation_batch(n, keys_per_set=k, n_validators=16384, seed=0xBEEF)
+    table = bls.PubkeyTable(16384)
+    table.append(ab.pk_table.tobytes())
+    idx = ab.committees.reshape(-1).astype(np.uint32)
+    b = bls.Batch(n, n * k)
+    for seed in (1, 2):
+        rands = np.random.default_rng(seed).integers(1, 2 ** 63, size=n, dtype=np.uint64) * 2 + 1
+        b.upload_indexed(table, ab.sigs, ab.msgs, idx, ab.offsets, rands)
+        b.enqueue()
+        assert b.result() is True
+    sigs = bytearray(ab.sigs); sigs[96 * 77_777:96 * 77_778] = ab.sigs[96 * 5:96 * 6]      # someone else's signature
+    b.upload_indexed(table, bytes(sigs), ab.msgs, idx, ab.offsets); b.enqueue(); assert b.result() is False
+    msgs = bytearray(ab.msgs); msgs[32 * 99_999 + 31] ^= 0x80
+    b.upload_indexed(table, ab.sigs, bytes(msgs), idx, ab.offsets); b.enqueue(); assert b.result() is False
+    bad = idx.copy(); bad[12_345 * k + 7] = (bad[12_345 * k + 7] + 1) % 16384
+    b.upload_indexed(table, ab.sigs, ab.msgs, bad, ab.offsets); b.enqueue(); assert b.result() is False
+    b.destroy(); table.destroy()
+
+
+def test_block_signature_batch_shape(bls):
+    """BASELINE configs[3] shape at reduced scale: the sets BlockSignatureVerifier::include_all_signatures collects
+    for consecutive blocks (block_signature_verifier.rs:141-393) — 1-key sets (proposal, randao, exits,
+    BLS-to-execution changes), committee-sized attestation sets and one 512-key sync aggregate per block — in ONE
+    verify_signature_sets call (ParallelSignatureSets::verify, :416-418)."""
+    rng = np.random.default_rng(33)
+    n_validators = 600
+    sks = [int.from_bytes(secret_from_u64(i), "big") for i in range(n_validators)]
+    pk48, pk96 = bls.sk_to_pk(b"".join(secret_from_u64(i) for i in range(n_validators)))
+    keys = [pk96[96 * i:96 * i + 96] for i in range(n_validators)]
+    sets_ids = []
+    for blk in range(3):
+        sets_ids += [[int(rng.integers(n_validators))] for _ in range(2)]                  # proposal, randao
+        sets_ids += [sorted(rng.choice(n_validators, size=61, replace=False).tolist()) for _ in range(8)]  # attestations
+        sets_ids += [sorted(rng.choice(n_validators, size=512, replace=True).tolist())]    # sync aggregate (repeats allowed)
+        sets_ids += [[int(rng.integers(n_validators))] for _ in range(4)]                  # exits, bls changes
+    msgs = [hashlib.sha256(b"blk%d" % i).digest() for i in range(len(sets_ids))]
+    agg = [sum(sks[i] for i in ids) % B.R for ids in sets_ids]
+    sigs = bls.sign(b"".join(a.to_bytes(32, "big") for a in agg), b"".join(msgs))
+    pks = b"".join(keys[i] for ids in sets_ids for i in ids)
+    offs = np.concatenate([[0], np.cumsum([len(ids) for ids in sets_ids])]).astype(np.uint32)
+    assert bls.verify_signature_sets_raw(sigs, b"".join(msgs), pks, offs)
+    for victim in (0, 10, len(sets_ids) - 1):                                              # invalid_signature_* cases
+        bad = bytearray(sigs); bad[96 * victim:96 * victim + 96] = sigs[96 * ((victim + 1) % len(sets_ids)):][:96]
+        assert not bls.verify_signature_sets_raw(bytes(bad), b"".join(msgs), pks, offs)
+
+
+def test_cpp_host_layer_on_golden_vectors(gpu, tmp_path):
+    """The C++ host mirror (include/lhb200.hpp: bls::SignatureSet, verify_signature_sets, MerkleTree ...) on the
+    reference's 22 deposit vectors."""
+    import os
+    import subprocess
+    deps = O.golden_json("deposit_data.json")
+    p = tmp_path / "vectors.bin"
+    with open(p, "wb") as f:
+        for d in deps:
+            f.write(bytes.fromhex(d["pubkey"]) + deposit_signing_root(d) + bytes.fromhex(d["signature"]))
+    subprocess.check_call(["make", "-C", os.path.join(O.ROOT, "tests", "cpp"), "-s"])
+    r = subprocess.run([os.path.join(O.ROOT, "tests", "cpp", "host_mirror_test"), str(p)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "OK 22 sets" in r.stdout
