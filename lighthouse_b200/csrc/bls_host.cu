@@ -61,7 +61,8 @@ struct lhb200_bls_batch {
     uint32_t* d_fail = nullptr;
     uint8_t* d_ok = nullptr;
     uint8_t* h_res = nullptr;     // pinned: ok + status
-    cudaStream_t s2 = nullptr;
+    cudaStream_t s2 = nullptr, s3 = nullptr;
+    cudaEvent_t e_h2c = nullptr, e_sig = nullptr;
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller), for the roofline
     uint64_t launches_last = 0;
@@ -77,6 +78,9 @@ static void batch_free(lhb200_bls_batch* b) {
         if (p) cudaFree(p);
     if (b->h_res) cudaFreeHost(b->h_res);
     if (b->s2) cudaStreamDestroy(b->s2);
+    if (b->s3) cudaStreamDestroy(b->s3);
+    if (b->e_h2c) cudaEventDestroy(b->e_h2c);
+    if (b->e_sig) cudaEventDestroy(b->e_sig);
     if (b->e_fork) cudaEventDestroy(b->e_fork);
     if (b->e_join) cudaEventDestroy(b->e_join);
     if (b->e_k0) cudaEventDestroy(b->e_k0);
@@ -122,6 +126,9 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b->h_res), n + 64 + sizeof(Fp12), cudaHostAllocDefault);
     if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaHostAlloc(result)"); }
     if ((e = cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->s3, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_h2c, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_sig, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&b->e_k0)) != cudaSuccess || (e = cudaEventCreate(&b->e_k1)) != cudaSuccess) {
@@ -309,11 +316,15 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaMemsetAsync(b->d_status, 0, n, s));
     LHB_CUDA(cudaMemsetAsync(b->d_fail, 0, 4, s));
     LHB_CUDA(cudaMemsetAsync(b->d_ok, 0, 4, s));
-    k_sig_prepare<<<grid, BLS_BLOCK, 0, s>>>(b->in_sigs, b->in_rands, n, b->d_sigr, b->d_status, b->d_fail);
-    launches++;
-    // side stream: sum r_i*sig_i, then the Miller loop of (-g1, sum)
+    // Three independent per-set stages run concurrently (they matter for small batches, where each kernel is a
+    // latency-bound handful of warps): s2 = signatures (+ their sum tree + the last Miller loop), s3 = hash_to_g2,
+    // s = key aggregation; the Miller kernel joins s and s3, k_final joins s2.
     LHB_CUDA(cudaEventRecord(b->e_fork, s));
     LHB_CUDA(cudaStreamWaitEvent(b->s2, b->e_fork, 0));
+    LHB_CUDA(cudaStreamWaitEvent(b->s3, b->e_fork, 0));
+    k_sig_prepare<<<grid, BLS_BLOCK, 0, b->s2>>>(b->in_sigs, b->in_rands, n, b->d_sigr, b->d_status, b->d_fail);
+    launches++;
+    LHB_CUDA(cudaEventRecord(b->e_sig, b->s2));
     {
         const G2Jac* cur = b->d_sigr;
         uint32_t m = n;
@@ -330,12 +341,15 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         launches++;
         LHB_CUDA(cudaEventRecord(b->e_join, b->s2));
     }
+    k_hash_to_g2<<<grid, BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);
+    LHB_CUDA(cudaEventRecord(b->e_h2c, b->s3));
     if (b->table)
         k_pk_aggregate_indexed<<<grid, BLS_BLOCK, 0, s>>>(b->table->d_keys, (uint32_t)b->table->len, b->in_indices,
                                                          b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     else
         k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
-    k_hash_to_g2<<<grid, BLS_BLOCK, 0, s>>>(b->in_msgs, n, b->d_h);
+    LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
+    LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller reads the status bytes k_sig_prepare may set
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
     k_miller<<<grid, BLS_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);
     LHB_CUDA(cudaEventRecord(b->e_k1, s));
