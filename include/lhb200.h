@@ -87,6 +87,10 @@ LHB200_API int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t l
 typedef struct lhb200_state lhb200_state;
 LHB200_API int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state** out);
 LHB200_API int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t* field_roots);
+/* Same-length in-place mutation of a staged state — the resident analogue of apply_pending_mutations
+ * (beacon_state.rs:2459-2481): bytes [ssz_offset, ssz_offset+len) of the SSZ encoding are replaced; the next
+ * lhb200_state_root re-hashes everything on the device (warm path = patch + full re-hash). */
+LHB200_API int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t* data, uint64_t len);
 /* Same as lhb200_state_root but only enqueues; the root lands in device memory (returned pointer valid until
  * the next call on this handle).  Used by bench.py to time kernels with CUDA events. */
 LHB200_API int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root);

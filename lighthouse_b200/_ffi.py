@@ -110,3 +110,4 @@ _sig("lhb200_bls_batch_upload_indexed", C.c_int32, vp, vp, vp, vp, vp, vp, vp, C
 _sig("lhb200_state_stage_deneb_shard", C.c_int32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp))
 _sig("lhb200_state_shard_roots", C.c_int32, vp, vp, C.POINTER(C.c_uint32))
 _sig("lhb200_state_combine", C.c_int32, vp, vp, vp)
+_sig("lhb200_state_patch", C.c_int32, vp, C.c_uint64, vp, C.c_uint64)

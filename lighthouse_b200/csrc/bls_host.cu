@@ -464,14 +464,27 @@ int32_t lhb200_verify_signature_sets(const uint8_t* sigs, const uint8_t* msgs, c
     if (!pk_offsets) { set_error("verify_signature_sets: null offsets"); return LHB200_EINVAL; }
     Ctx& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
-    lhb200_bls_batch* b = nullptr;
-    int32_t rc = lhb200_bls_batch_create(n_sets, pk_offsets[n_sets], &b);
-    if (rc) return rc;
-    rc = lhb200_bls_batch_upload(b, sigs, msgs, pks, pk_offsets, rands, n_sets);
+    // One cached batch (device buffers, streams, events) is reused across calls and grown on demand: a 64-set gossip
+    // batch must not pay 18 cudaMalloc/cudaFree per call.
+    static lhb200_bls_batch* cached = nullptr;
+    const uint64_t n_keys = pk_offsets[n_sets];
+    if (cached && (cached->cap_sets < n_sets || cached->cap_keys < n_keys)) {
+        cudaDeviceSynchronize();
+        batch_free(cached);
+        cached = nullptr;
+    }
+    if (!cached) {
+        const uint32_t cap_sets = std::max<uint32_t>(n_sets + n_sets / 4, 256);
+        const uint64_t cap_keys = std::max<uint64_t>(n_keys + n_keys / 4, 4096);
+        int32_t rc0 = lhb200_bls_batch_create(cap_sets, cap_keys, &cached);
+        if (rc0) { cached = nullptr; return rc0; }
+    }
+    lhb200_bls_batch* b = cached;
+    int32_t rc = lhb200_bls_batch_upload(b, sigs, msgs, pks, pk_offsets, rands, n_sets);
     if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, c.stream);
     if (!rc) rc = lhb200_bls_batch_result(b, c.stream, ok, set_status);
     cudaStreamSynchronize(b->s2);
-    batch_free(b);
+    cudaStreamSynchronize(b->s3);
     return rc;
 }
 

@@ -60,6 +60,11 @@ struct Plan {
     std::vector<int> op_wave;
     std::vector<std::pair<uint64_t, int>> ready_wave;  // dst addr -> wave producing it (small; linear scan)
     uint64_t hash_units = 0;
+    // SSZ provenance of literal chunks (for lhb200_state_patch): chunk index <- n bytes at SSZ offset src_off
+    struct LitSrc { uint32_t lit_index; uint32_t n; uint64_t src_off; };
+    std::vector<LitSrc> lit_src;
+    const uint8_t* ssz_base = nullptr;
+    uint64_t ssz_len = 0;
     // tail program (device copies)
     HashOp* d_ops = nullptr;
     int32_t* d_waves = nullptr;
@@ -72,7 +77,7 @@ struct Plan {
         return arena ? arena + off : reinterpret_cast<uint8_t*>(off);
     }
     static uint64_t zero_op(uint32_t level) { return OP_ZERO_FLAG | level; }
-    uint64_t literal(const uint8_t chunk[32]) {
+    uint64_t literal_raw(const uint8_t chunk[32]) {
         size_t i = lit.size();
         lit.resize(i + 32);
         memcpy(&lit[i], chunk, 32);
@@ -81,12 +86,15 @@ struct Plan {
     uint64_t literal_bytes(const uint8_t* p, size_t n) {  // zero-padded chunk from <=32 bytes
         uint8_t c[32] = {0};
         memcpy(c, p, n);
-        return literal(c);
+        if (ssz_base && p >= ssz_base && p + n <= ssz_base + ssz_len)
+            lit_src.push_back({(uint32_t)(lit.size() / 32), (uint32_t)n, (uint64_t)(p - ssz_base)});
+        return literal_raw(c);
     }
+    uint64_t literal(const uint8_t chunk[32]) { return literal_bytes(chunk, 32); }
     uint64_t literal_u64(uint64_t v) {
         uint8_t c[32] = {0};
         for (int k = 0; k < 8; k++) c[k] = (uint8_t)(v >> (8 * k));
-        return literal(c);
+        return literal_raw(c);
     }
     int wave_of(uint64_t operand) const {
         if (operand & OP_ZERO_FLAG) return -1;
@@ -346,6 +354,12 @@ namespace lhb200 {
 // [r * 2^s, (r+1) * 2^s) of every big list (s = ceil_log2(#chunks) - log2(world)) and produces the 32-byte root of
 // that height-s subtree; small fields are computed by every rank.  After one all-gather of the subtree roots each
 // rank folds them (log2(world) levels + zero ladder + length mix-in + the 32-leaf container) in lhb200_state_combine.
+struct StageCopy {
+    size_t src_off, nbytes;
+    uint8_t* dst;
+    size_t pad_to;  // zero-fill up to this many bytes at dst
+};
+
 struct ShardCfg {
     uint32_t rank = 0, world = 1;
 };
@@ -372,15 +386,10 @@ struct lhb200_state {
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around k_validator_roots
     lhb200::ShardCfg shard;
     std::vector<lhb200::ShardedList> sharded;
+    std::vector<lhb200::StageCopy> copies;  // SSZ ranges resident in the arena (for lhb200_state_patch)
 };
 
 namespace lhb200 {
-
-struct StageCopy {
-    size_t src_off, nbytes;
-    uint8_t* dst;
-    size_t pad_to;  // zero-fill up to this many bytes at dst
-};
 
 // Describe the whole Deneb state.  `s` = host SSZ (read for offsets and small literal fields only).
 // Big fields are placed in the arena by `place(src_off, nbytes)` which records an H2D copy.
@@ -406,6 +415,8 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
         set_error("BeaconStateDeneb SSZ: malformed variable part");
         return LHB200_EINVAL;
     }
+    p.ssz_base = s;
+    p.ssz_len = len;
     auto place = [&](size_t src_off, size_t nbytes) -> uint8_t* {
         size_t padded = align_up(nbytes + 32, 256);
         uint8_t* d = p.alloc(padded);
@@ -444,19 +455,19 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
         sharded->push_back({field, sub, limit_depth, mix_len, op});
         return Plan::zero_op(0);       // placeholder; the field root is formed in lhb200_state_combine
     };
-    f[0] = p.literal_u64(rd64(s + O_GENESIS_TIME));
+    f[0] = p.literal_bytes(s + O_GENESIS_TIME, 8);
     f[1] = chunk(O_GVR);
-    f[2] = p.literal_u64(rd64(s + O_SLOT));
+    f[2] = p.literal_bytes(s + O_SLOT, 8);
     f[3] = p.container({p.literal_bytes(s + O_FORK, 4), p.literal_bytes(s + O_FORK + 4, 4),
-                        p.literal_u64(rd64(s + O_FORK + 8))});
-    f[4] = p.container({p.literal_u64(rd64(s + O_LBH)), p.literal_u64(rd64(s + O_LBH + 8)), chunk(O_LBH + 16),
+                        p.literal_bytes(s + O_FORK + 8, 8)});
+    f[4] = p.container({p.literal_bytes(s + O_LBH, 8), p.literal_bytes(s + O_LBH + 8, 8), chunk(O_LBH + 16),
                         chunk(O_LBH + 48), chunk(O_LBH + 80)});
     f[5] = p.merkle_list(place(O_BLOCK_ROOTS, 8192 * 32), 8192, 13);
     f[6] = p.merkle_list(place(O_STATE_ROOTS, 8192 * 32), 8192, 13);
     f[7] = p.mix_in_length(p.merkle_list(place(o_hist, n_hist * 32), n_hist, 24), n_hist);
-    f[8] = p.container({chunk(O_ETH1_DATA), p.literal_u64(rd64(s + O_ETH1_DATA + 32)), chunk(O_ETH1_DATA + 40)});
+    f[8] = p.container({chunk(O_ETH1_DATA), p.literal_bytes(s + O_ETH1_DATA + 32, 8), chunk(O_ETH1_DATA + 40)});
     f[9] = p.mix_in_length(p.merkle_list(p.leaf_kernel(2, place(o_votes, n_votes * 72), n_votes), n_votes, 11), n_votes);
-    f[10] = p.literal_u64(rd64(s + O_DEPOSIT_INDEX));
+    f[10] = p.literal_bytes(s + O_DEPOSIT_INDEX, 8);
     f[11] = big_list(11, o_val, n_val, 121, 0, n_val, 40, n_val);
     f[12] = big_list(12, o_bal, n_bal, 8, -1, ceil_div(n_bal * 8, 32), 38, n_bal);
     f[13] = big_list(13, O_RANDAO, 65536, 32, -1, 65536, 16, UINT64_MAX);
@@ -464,9 +475,9 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
     f[15] = big_list(15, o_pp, n_pp, 1, -1, ceil_div(n_pp, 32), 35, n_pp);
     f[16] = big_list(16, o_cp, n_cp, 1, -1, ceil_div(n_cp, 32), 35, n_cp);
     f[17] = p.literal_bytes(s + O_JUST, 1);
-    f[18] = p.container({p.literal_u64(rd64(s + O_PJC)), chunk(O_PJC + 8)});
-    f[19] = p.container({p.literal_u64(rd64(s + O_CJC)), chunk(O_CJC + 8)});
-    f[20] = p.container({p.literal_u64(rd64(s + O_FC)), chunk(O_FC + 8)});
+    f[18] = p.container({p.literal_bytes(s + O_PJC, 8), chunk(O_PJC + 8)});
+    f[19] = p.container({p.literal_bytes(s + O_CJC, 8), chunk(O_CJC + 8)});
+    f[20] = p.container({p.literal_bytes(s + O_FC, 8), chunk(O_FC + 8)});
     f[21] = big_list(21, o_inact, n_inact, 8, -1, ceil_div(n_inact * 8, 32), 38, n_inact);
     for (int k = 0; k < 2; k++) {
         uint8_t* roots = p.leaf_kernel(1, place(k ? O_NSC : O_CSC, SYNC_COMMITTEE_BYTES), 513);
@@ -478,14 +489,14 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
         for (int i = 0; i < 8; i++) bloom.push_back(p.literal(h + 116 + 32 * i));
         const uint64_t extra_len = leph_len - 584;
         f[24] = p.container({p.literal(h), p.literal_bytes(h + 32, 20), p.literal(h + 52), p.literal(h + 84),
-                             p.small_tree(bloom, 3), p.literal(h + 372), p.literal_u64(rd64(h + 404)),
-                             p.literal_u64(rd64(h + 412)), p.literal_u64(rd64(h + 420)), p.literal_u64(rd64(h + 428)),
+                             p.small_tree(bloom, 3), p.literal(h + 372), p.literal_bytes(h + 404, 8),
+                             p.literal_bytes(h + 412, 8), p.literal_bytes(h + 420, 8), p.literal_bytes(h + 428, 8),
                              p.mix_in_length(p.literal_bytes(h + 584, extra_len), extra_len), p.literal(h + 440),
                              p.literal(h + 472), p.literal(h + 504), p.literal(h + 536),
-                             p.literal_u64(rd64(h + 568)), p.literal_u64(rd64(h + 576))});
+                             p.literal_bytes(h + 568, 8), p.literal_bytes(h + 576, 8)});
     }
-    f[25] = p.literal_u64(rd64(s + O_NWI));
-    f[26] = p.literal_u64(rd64(s + O_NWVI));
+    f[25] = p.literal_bytes(s + O_NWI, 8);
+    f[26] = p.literal_bytes(s + O_NWVI, 8);
     f[27] = p.mix_in_length(p.merkle_list(p.leaf_kernel(3, place(o_hs, n_hs * 64), n_hs), n_hs, 24), n_hs);
     *root_op = p.container(std::vector<uint64_t>(f, f + 28));
     return LHB200_OK;
@@ -670,6 +681,8 @@ static int32_t stage_deneb(const uint8_t* ssz, uint64_t len, ShardCfg sh, lhb200
     });
     st->shard = sh;
     if (rc) { cudaFree(st->arena); return rc; }
+    st->copies = copies;
+    st->plan.ssz_base = nullptr;  // the caller's buffer is not retained
     // H2D: per-field copies into the aligned layout.  Pinned caller memory goes straight to the copy engine;
     // pageable memory is bounced through the pinned staging slab.
     cudaPointerAttributes at;
@@ -773,6 +786,45 @@ int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t 
         }
         return p.container(f);
     });
+}
+
+// Apply same-length mutations to a staged state (the resident analogue of BeaconState::apply_pending_mutations,
+// consensus/types/src/beacon_state.rs:2459-2481): `data` replaces SSZ bytes [ssz_offset, ssz_offset + len) of the
+// encoding the handle was staged from.  Big-field bytes are patched in place in HBM, small-field bytes re-pack their
+// literal chunks.  List lengths / variable-part offsets must not change (re-stage for that).  The next
+// lhb200_state_root re-hashes the whole state (0.85 ms at 500 k validators - cheaper than tracking dirty paths).
+int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t* data, uint64_t len) {
+    LHB_REQUIRE_READY();
+    if (!st || (len && !data)) return LHB200_EINVAL;
+    if (len == 0) return LHB200_OK;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(len + 64));
+    if (!h) return LHB200_ENOMEM;
+    memcpy(h, data, len);
+    const uint64_t lo = ssz_offset, hi = ssz_offset + len;
+    bool touched = false;
+    for (const StageCopy& cp : st->copies) {
+        const uint64_t a = std::max<uint64_t>(lo, cp.src_off), b = std::min<uint64_t>(hi, cp.src_off + cp.nbytes);
+        if (a < b) {
+            LHB_CUDA(cudaMemcpyAsync(cp.dst + (a - cp.src_off), h + (a - lo), b - a, cudaMemcpyHostToDevice, c.stream));
+            touched = true;
+        }
+    }
+    Plan& pl = st->plan;
+    for (const Plan::LitSrc& ls : pl.lit_src) {
+        const uint64_t a = std::max<uint64_t>(lo, ls.src_off), b = std::min<uint64_t>(hi, ls.src_off + ls.n);
+        if (a < b) {
+            uint8_t* chunk = &pl.lit[(size_t)ls.lit_index * 32];
+            memcpy(chunk + (a - ls.src_off), data + (a - lo), b - a);
+            LHB_CUDA(cudaMemcpyAsync(pl.arena + pl.lit_off + (size_t)ls.lit_index * 32, chunk, 32, cudaMemcpyHostToDevice,
+                                     c.stream));
+            touched = true;
+        }
+    }
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    if (!touched) { set_error("state_patch: range is not resident on this handle (offset table or another rank's shard)"); return LHB200_EINVAL; }
+    return LHB200_OK;
 }
 
 int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root) {

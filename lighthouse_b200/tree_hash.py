@@ -140,6 +140,11 @@ class ResidentState:
             return out.raw, [fr.raw[32 * i: 32 * i + 32] for i in range(28)]
         return out.raw
 
+    def patch(self, ssz_offset: int, data: bytes):
+        """Same-length mutation of SSZ bytes [ssz_offset, ssz_offset + len(data)) (apply_pending_mutations)."""
+        p, keep = buf(data)
+        check(lib.lhb200_state_patch(self._h, ssz_offset, p, len(data)), "lhb200_state_patch")
+
     def enqueue(self, stream=None):
         d = C.c_void_p()
         check(lib.lhb200_state_root_enqueue(self._h, stream, C.byref(d)), "lhb200_state_root_enqueue")
@@ -163,3 +168,29 @@ class ResidentState:
             self.release()
         except Exception:
             pass
+
+
+# ---- SignedRoot / domain helpers (consensus/types/src/signing_data.rs:27-35, chain_spec.rs:518-566) ----------
+def container_root(field_roots) -> bytes:
+    """merkleize(field roots, next_pow2(#fields)) — what #[derive(TreeHash)] emits for a container."""
+    k = len(field_roots)
+    depth = (max(k, 1) - 1).bit_length()
+    return merkleize_chunks(b"".join(field_roots), depth)
+
+
+def compute_fork_data_root(current_version: bytes, genesis_validators_root: bytes) -> bytes:
+    assert len(current_version) == 4 and len(genesis_validators_root) == 32
+    return hash32_concat(current_version + bytes(28), genesis_validators_root)
+
+
+def compute_domain(domain_type: int, fork_version: bytes, genesis_validators_root: bytes) -> bytes:
+    """ChainSpec::compute_domain: le32(domain_type) || fork_data_root[:28]"""
+    return domain_type.to_bytes(4, "little") + compute_fork_data_root(fork_version, genesis_validators_root)[:28]
+
+
+def signing_roots(object_roots: bytes, domain: bytes) -> bytes:
+    """Batch SignedRoot::signing_root: n x 32-byte object roots -> n x 32-byte signing roots, one launch."""
+    assert len(object_roots) % 32 == 0 and len(domain) == 32
+    n = len(object_roots) // 32
+    pairs = b"".join(object_roots[32 * i:32 * i + 32] + domain for i in range(n))
+    return hash_pairs(pairs)

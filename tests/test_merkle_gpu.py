@@ -174,3 +174,54 @@ def test_sharded_state_root_equals_full(gpu, world, nv):
     for s in shards:
         assert s.combine(gathered) == want
         s.release()
+
+
+def test_resident_state_patch_matches_oracle(gpu):
+    """SURVEY §8f-3 (warm path): mutate a staged state in place — validator records, balances, participation,
+    randao mix, slot, latest_block_header, a checkpoint — and re-hash; must equal the oracle on the mutated SSZ."""
+    from lighthouse_b200 import tree_hash as T, Lhb200Error
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    rng = np.random.default_rng(8)
+    ssz = bytearray(beacon_state_deneb_ssz(20_000, seed=77))
+    st = T.ResidentState(bytes(ssz))
+    assert st.root() == O.beacon_state_root_deneb(bytes(ssz))[0]
+    o_val, o_bal = struct.unpack_from("<II", ssz, 524552)
+    o_pp, o_cp = struct.unpack_from("<II", ssz, 2687248)
+    edits = []
+    for vi in (0, 123, 19_999):                                   # effective_balance + exit_epoch of 3 validators
+        edits.append((o_val + 121 * vi + 80, struct.pack("<Q", 31_000_000_000 + vi)))
+        edits.append((o_val + 121 * vi + 105, struct.pack("<Q", 4242 + vi)))
+    edits.append((o_bal + 8 * 777, struct.pack("<Q", 123456789)))                       # one balance
+    edits.append((o_bal + 8 * 1000, rb(rng, 8 * 64)))                                   # 64 consecutive balances
+    edits.append((o_pp + 5000, bytes([7] * 100)))                                       # participation flags
+    edits.append((524560 + 32 * 4097, rb(rng, 32)))                                     # one randao mix
+    edits.append((40, struct.pack("<Q", 9_999_999)))                                    # slot
+    edits.append((64, rb(rng, 112)))                                                    # latest_block_header
+    edits.append((2687297, rb(rng, 40)))                                                # current_justified_checkpoint
+    edits.append((2687256, bytes([0x05])))                                              # justification_bits
+    for off, data in edits:
+        ssz[off:off + len(data)] = data
+        st.patch(off, data)
+    want, want_fields = O.beacon_state_root_deneb(bytes(ssz))
+    got, got_fields = st.root(want_field_roots=True)
+    for i, (g, w) in enumerate(zip(got_fields, want_fields)):
+        assert g == w, f"field {i}"
+    assert got == want
+    with pytest.raises(Lhb200Error):
+        st.patch(524552, b"\\0\\0\\0\\0")                                                  # offset table: refused
+    st.release()
+
+
+def test_signing_root_and_domain_helpers(gpu):
+    """signing_root / compute_domain (signing_data.rs:27-35, chain_spec.rs:548-566) against hashlib and the
+    synthetic generator's own CPU restatement."""
+    from lighthouse_b200 import tree_hash as T
+    from lighthouse_b200.synthetic import attester_domain, MAINNET_GVR
+    dom = T.compute_domain(1, bytes.fromhex("04000000"), MAINNET_GVR)
+    assert dom == attester_domain()
+    roots = b"".join(hashlib.sha256(bytes([i])).digest() for i in range(50))
+    got = T.signing_roots(roots, dom)
+    for i in range(50):
+        assert got[32 * i:32 * i + 32] == hashlib.sha256(roots[32 * i:32 * i + 32] + dom).digest()
+    leaves = [hashlib.sha256(bytes([i])).digest() for i in range(5)]
+    assert T.container_root(leaves) == O.merkleize(b"".join(leaves), 3)
