@@ -28,6 +28,10 @@ enum SetStatus : uint8_t {
 };
 
 constexpr int BLS_BLOCK = 64;
+#ifndef LHB_MILLER_BLOCK
+#define LHB_MILLER_BLOCK 64
+#endif
+constexpr int MILLER_BLOCK = LHB_MILLER_BLOCK;  // k_miller's residency knob (its 3.5 KB/thread stack vs the 126 MB L2)
 
 __device__ __forceinline__ void load_bytes16(uint8_t* dst, const uint8_t* src, int nbytes) {
     // src is 16-byte aligned; nbytes multiple of 16
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_hash_to_g2(const uint8_t* __restr
     }
 }
 
-__global__ void __launch_bounds__(BLS_BLOCK) k_miller(const G1Proj3* __restrict__ P, const G2Affine* __restrict__ H,
+__global__ void __launch_bounds__(MILLER_BLOCK) k_miller(const G1Proj3* __restrict__ P, const G2Affine* __restrict__ H,
                                                        const uint8_t* __restrict__ status, uint32_t n,
                                                        Fp12* __restrict__ out_f) {
     // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident

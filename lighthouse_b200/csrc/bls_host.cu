@@ -351,7 +351,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller reads the status bytes k_sig_prepare may set
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
-    k_miller<<<grid, BLS_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);
+    k_miller<<<cdiv((uint64_t)grid * BLS_BLOCK, MILLER_BLOCK), MILLER_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);
     LHB_CUDA(cudaEventRecord(b->e_k1, s));
     launches += 3;
     const Fp12* cur = b->d_f;
