@@ -120,6 +120,12 @@ LHB200_API int32_t lhb200_merkle_tree_proof(const uint8_t* leaves, uint64_t n, u
 LHB200_API int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branches, uint32_t depth,
                                     const uint64_t* indices, const uint8_t* roots, uint64_t n, uint8_t* ok);
 
+/* swap_or_not_shuffle::shuffle_list (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79-160):
+ * out = shuffle (forwards != 0) or un-shuffle (forwards == 0, the direction the spec uses for committees) of the n
+ * 64-bit values of `input`.  n == 0, n > 2^24 or rounds == 0 -> LHB200_EINVAL (the reference returns None). */
+LHB200_API int32_t lhb200_shuffle_list(const uint64_t* input, uint64_t n, uint8_t rounds, const uint8_t seed[32],
+                                       int32_t forwards, uint64_t* out);
+
 /* ---- BLS batch verification path ---------------------------------------------------------------- */
 
 /* bls::verify_signature_sets (crypto/bls/src/impls/blst.rs:37-119) over SoA-flattened SignatureSets

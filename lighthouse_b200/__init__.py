@@ -7,4 +7,4 @@ to CPU arithmetic.
 from . import _ffi  # noqa: F401  (raises ImportError if the CUDA library is missing)
 from ._ffi import init, Lhb200Error  # noqa: F401
 
-__all__ = ["init", "Lhb200Error", "tree_hash", "merkle_proof", "bls"]
+__all__ = ["init", "Lhb200Error", "tree_hash", "merkle_proof", "bls", "shuffle"]

@@ -111,3 +111,4 @@ _sig("lhb200_state_stage_deneb_shard", C.c_int32, vp, C.c_uint64, C.c_uint32, C.
 _sig("lhb200_state_shard_roots", C.c_int32, vp, vp, C.POINTER(C.c_uint32))
 _sig("lhb200_state_combine", C.c_int32, vp, vp, vp)
 _sig("lhb200_state_patch", C.c_int32, vp, C.c_uint64, vp, C.c_uint64)
+_sig("lhb200_shuffle_list", C.c_int32, vp, C.c_uint64, C.c_uint8, vp, C.c_int32, vp)

@@ -313,4 +313,56 @@ __global__ void __launch_bounds__(128) k_verify_branches(const uint8_t* __restri
     ok[i] = eq ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// swap-or-not shuffle (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79-160).
+// The reference sweeps the list in place round by round, hashing as it goes.  On the device the 90 rounds are
+// flattened: every hash the sweep can need depends only on (seed, round, position >> 8), so ONE launch computes all
+// pivots and ONE all `rounds x ceil(n/256)` source blocks; then each output index walks its 90 rounds through that
+// bit table independently (compute_shuffled_index with lookups instead of hashes) and gathers / scatters its element.
+__device__ __forceinline__ void shuffle_seed_hash(const uint8_t* seed, uint32_t round, bool with_pos, uint32_t pos,
+                                                  uint8_t out[32]) {
+    uint8_t buf[37];
+    for (int i = 0; i < 32; i++) buf[i] = seed[i];
+    buf[32] = (uint8_t)round;
+    buf[33] = (uint8_t)pos; buf[34] = (uint8_t)(pos >> 8); buf[35] = (uint8_t)(pos >> 16); buf[36] = (uint8_t)(pos >> 24);
+    sha256_short(buf, with_pos ? 37 : 33, out);
+}
+// pivots[r] = le64(H(seed || r)[0:8]) % n ; sources[r][b] = H(seed || r || le32(b))
+__global__ void __launch_bounds__(128) k_shuffle_hashes(const uint8_t* __restrict__ seed, uint32_t rounds, uint64_t n,
+                                                        uint32_t n_blocks, uint64_t* __restrict__ pivots,
+                                                        uint8_t* __restrict__ sources) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)rounds * n_blocks;
+    uint8_t d[32];
+    if (t < rounds) {
+        shuffle_seed_hash(seed, (uint32_t)t, false, 0, d);
+        uint64_t v = 0;
+        for (int k = 7; k >= 0; k--) v = (v << 8) | d[k];
+        pivots[t] = v % n;
+    }
+    if (t < total) {
+        const uint32_t r = (uint32_t)(t / n_blocks), b = (uint32_t)(t % n_blocks);
+        shuffle_seed_hash(seed, r, true, b, d);
+        for (int i = 0; i < 32; i++) sources[32 * t + i] = d[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_shuffle_permute(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                         uint64_t n, uint32_t rounds, uint32_t n_blocks,
+                                                         const uint64_t* __restrict__ pivots,
+                                                         const uint8_t* __restrict__ sources, int forwards) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t index = i;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint64_t pivot = pivots[r];
+        const uint64_t flip = (pivot + (n - index)) % n;
+        const uint64_t pos = index > flip ? index : flip;
+        const uint8_t byte = sources[32ull * ((uint64_t)r * n_blocks + (pos >> 8)) + ((pos & 0xff) >> 3)];
+        if ((byte >> (pos & 7)) & 1) index = flip;
+    }
+    // backwards (the spec's usual direction): out[i] = in[csi(i)];  forwards: out[csi(i)] = in[i]
+    if (forwards) out[index] = in[i];
+    else out[i] = in[index];
+}
+
 }  // namespace lhb200

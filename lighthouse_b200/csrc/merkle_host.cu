@@ -986,4 +986,41 @@ int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branch
     return LHB200_OK;
 }
 
+// swap_or_not_shuffle::shuffle_list(input, rounds, seed, forwards) (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79).
+// The reference returns None for an empty list, more than 2^24 elements or zero rounds: LHB200_EINVAL here.
+int32_t lhb200_shuffle_list(const uint64_t* input, uint64_t n, uint8_t rounds, const uint8_t seed[32], int32_t forwards,
+                            uint64_t* out) {
+    LHB_REQUIRE_READY();
+    if (!input || !out || !seed || n == 0 || n > (1ull << 24) || rounds == 0) {
+        set_error("shuffle_list: empty list, more than 2^24 elements or zero rounds (reference returns None)");
+        return LHB200_EINVAL;
+    }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const uint32_t n_blocks = (uint32_t)ceil_div(n, 256);
+    const size_t b_in = align_up(n * 8, 256), b_src = align_up((size_t)rounds * n_blocks * 32, 256), b_piv = 1024;
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(2 * b_in + b_src + b_piv + 256));
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(2 * b_in + 64));
+    if (!d || !h) return LHB200_ENOMEM;
+    uint64_t* d_in = reinterpret_cast<uint64_t*>(d);
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(d + b_in);
+    uint8_t* d_src = d + 2 * b_in;
+    uint64_t* d_piv = reinterpret_cast<uint64_t*>(d_src + b_src);
+    uint8_t* d_seed = reinterpret_cast<uint8_t*>(d_piv) + 768;
+    memcpy(h, input, n * 8);
+    memcpy(h + b_in, seed, 32);
+    LHB_CUDA(cudaMemcpyAsync(d_in, h, n * 8, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(d_seed, h + b_in, 32, cudaMemcpyHostToDevice, c.stream));
+    const uint64_t total = std::max<uint64_t>((uint64_t)rounds * n_blocks, rounds);
+    k_shuffle_hashes<<<(unsigned)ceil_div(total, 128), 128, 0, c.stream>>>(d_seed, rounds, n, n_blocks, d_piv, d_src);
+    k_shuffle_permute<<<(unsigned)ceil_div(n, 256), 256, 0, c.stream>>>(d_in, d_out, n, rounds, n_blocks, d_piv, d_src,
+                                                                        forwards ? 1 : 0);
+    count_launch(2);
+    LHB_CUDA(cudaGetLastError());
+    LHB_CUDA(cudaMemcpyAsync(h, d_out, n * 8, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(out, h, n * 8);
+    return LHB200_OK;
+}
+
 }  // extern "C"

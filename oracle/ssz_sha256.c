@@ -533,3 +533,65 @@ EXPORT void orc_merkle_tree_proof(const uint8_t *leaves, uint64_t n, uint32_t de
     free(cur);
 }
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * swap-or-not shuffle (consensus/swap_or_not_shuffle): restatement of shuffle_list (src/shuffle_list.rs:79-160,
+ * the in-place pivot/mirror sweep) and compute_shuffled_index (src/compute_shuffled_index.rs:20-58).
+ * TEST INFRASTRUCTURE (SURVEY §8f-4 widening). */
+static void shuffle_hash(const uint8_t seed[32], uint8_t round, int with_pos, uint32_t pos, uint8_t out[32]) {
+    uint8_t buf[37];
+    memcpy(buf, seed, 32);
+    buf[32] = round;
+    buf[33] = (uint8_t)pos; buf[34] = (uint8_t)(pos >> 8); buf[35] = (uint8_t)(pos >> 16); buf[36] = (uint8_t)(pos >> 24);
+    orc_sha256(buf, with_pos ? 37 : 33, out);
+}
+static uint64_t le64(const uint8_t *p) {
+    uint64_t v = 0;
+    for (int k = 7; k >= 0; k--) v = (v << 8) | p[k];
+    return v;
+}
+/* returns 0 on success, -1 where the reference returns None */
+EXPORT int orc_shuffle_list(uint64_t *list, uint64_t n, uint8_t rounds, const uint8_t seed[32], int forwards) {
+    if (n == 0 || n > (1ull << 24) || rounds == 0) return -1;
+    uint8_t r = forwards ? 0 : (uint8_t)(rounds - 1), d[32], source[32];
+    for (;;) {
+        shuffle_hash(seed, r, 0, 0, d);
+        uint64_t pivot = le64(d) % n;
+        uint64_t mirror = (pivot + 1) >> 1;
+        shuffle_hash(seed, r, 1, (uint32_t)(pivot >> 8), source);
+        uint8_t byte_v = source[(pivot & 0xff) >> 3];
+        for (uint64_t i = 0; i < mirror; i++) {
+            uint64_t j = pivot - i;
+            if ((j & 0xff) == 0xff) shuffle_hash(seed, r, 1, (uint32_t)(j >> 8), source);
+            if ((j & 0x07) == 0x07) byte_v = source[(j & 0xff) >> 3];
+            if ((byte_v >> (j & 0x07)) & 1) { uint64_t t = list[i]; list[i] = list[j]; list[j] = t; }
+        }
+        mirror = (pivot + n + 1) >> 1;
+        uint64_t end = n - 1;
+        shuffle_hash(seed, r, 1, (uint32_t)(end >> 8), source);
+        byte_v = source[(end & 0xff) >> 3];
+        uint64_t it = 0;
+        for (uint64_t i = pivot + 1; i < mirror; i++, it++) {
+            uint64_t j = end - it;
+            if ((j & 0xff) == 0xff) shuffle_hash(seed, r, 1, (uint32_t)(j >> 8), source);
+            if ((j & 0x07) == 0x07) byte_v = source[(j & 0xff) >> 3];
+            if ((byte_v >> (j & 0x07)) & 1) { uint64_t t = list[i]; list[i] = list[j]; list[j] = t; }
+        }
+        if (forwards) { r++; if (r == rounds) break; }
+        else { if (r == 0) break; r--; }
+    }
+    return 0;
+}
+EXPORT int64_t orc_compute_shuffled_index(uint64_t index, uint64_t n, const uint8_t seed[32], uint8_t rounds) {
+    if (n == 0 || index >= n || n > (1ull << 24)) return -1;
+    uint8_t d[32];
+    for (uint8_t r = 0; r < rounds; r++) {
+        shuffle_hash(seed, r, 0, 0, d);
+        uint64_t pivot = le64(d) % n;
+        uint64_t flip = (pivot + (n - index)) % n;
+        uint64_t pos = index > flip ? index : flip;
+        shuffle_hash(seed, r, 1, (uint32_t)(pos >> 8), d);
+        if ((d[(pos & 0xff) >> 3] >> (pos & 7)) & 1) index = flip;
+    }
+    return (int64_t)index;
+}

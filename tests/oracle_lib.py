@@ -126,3 +126,15 @@ def bls_sk_to_pk(sk_be32):
 
 def bls_sign(sk_be32, msg):
     o = C.create_string_buffer(96); L.orc_sign(sk_be32, msg, o); return o.raw
+
+
+def shuffle_list(values, rounds, seed, forwards):
+    a = _np.ascontiguousarray(values, dtype=_np.uint64).copy()
+    rc = L.orc_shuffle_list(C.c_void_p(a.ctypes.data), C.c_uint64(len(a)), C.c_uint8(rounds), seed, C.c_int(1 if forwards else 0))
+    return None if rc else a.tolist()
+
+
+def compute_shuffled_index(index, n, seed, rounds):
+    L.orc_compute_shuffled_index.restype = C.c_int64
+    v = L.orc_compute_shuffled_index(C.c_uint64(index), C.c_uint64(n), seed, C.c_uint8(rounds))
+    return None if v < 0 else int(v)
