@@ -120,6 +120,18 @@ LHB200_API int32_t lhb200_merkle_tree_proof(const uint8_t* leaves, uint64_t n, u
 LHB200_API int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branches, uint32_t depth,
                                     const uint64_t* indices, const uint8_t* roots, uint64_t n, uint8_t* ok);
 
+/* BeaconBlock::canonical_root for BeaconBlockDeneb SSZ bytes, mainnet preset (consensus/types/src/beacon_block.rs:
+ * 56-78,158-160; body beacon_block_body.rs:70-121,145-176; payload execution_payload.rs:54-95; operations
+ * proposer_slashing.rs:26, attester_slashing.rs:42, indexed_attestation.rs:53, attestation.rs:74, deposit.rs:27,
+ * signed_voluntary_exit.rs:25, sync_aggregate.rs:38, signed_bls_to_execution_change.rs:22, withdrawal.rs:22).
+ * `body_root` (32 B, optional) receives hash_tree_root(body) — the BeaconBlockHeader.body_root of the block.
+ * The batch form hashes n blocks (SSZ blobs concatenated, offsets[n+1]) in one pass: the 32 blocks of an epoch
+ * segment (BlockSignatureVerifier / ConsensusContext::get_current_block_root, consensus_context.rs:115-128).
+ * Malformed SSZ (bad offsets, over-limit lists, missing bitlist delimiter) -> LHB200_EINVAL. */
+LHB200_API int32_t lhb200_beacon_block_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* body_root);
+LHB200_API int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n,
+                                                   uint8_t* roots, uint8_t* body_roots);
+
 /* swap_or_not_shuffle::shuffle_list (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79-160):
  * out = shuffle (forwards != 0) or un-shuffle (forwards == 0, the direction the spec uses for committees) of the n
  * 64-bit values of `input`.  n == 0, n > 2^24 or rounds == 0 -> LHB200_EINVAL (the reference returns None). */

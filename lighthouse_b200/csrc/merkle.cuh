@@ -291,6 +291,158 @@ __global__ void __launch_bounds__(PROG_THREADS) k_hash_program(const HashOp* __r
     }
 }
 
+// One wave of a hash program spread over the whole grid (used when a wave is too wide for one CTA: block batches).
+__global__ void __launch_bounds__(PROG_THREADS) k_hash_ops(const HashOp* __restrict__ ops, int n) {
+    const int k = blockIdx.x * PROG_THREADS + threadIdx.x;
+    if (k >= n) return;
+    const HashOp op = ops[k];
+    uint32_t l[8], r[8];
+    load_operand(op.a, l);
+    load_operand(op.b, r);
+    hash_pair(l, r, l);
+    store_chunk(reinterpret_cast<uint8_t*>(op.dst), l);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Byte items: hash_tree_root of packed byte strings that sit at ARBITRARY byte offsets inside an SSZ blob
+// (transactions, signatures, pubkeys, bitlists, index lists, proofs ... of a BeaconBlock):
+//     root = merkleize(pack(bytes), limit = 2^depth) [ mixed in with `length` ]
+// One CTA per item.  256-chunk tiles are folded through shared memory; tile roots are combined by a binary-counter
+// stack (the streaming MerkleHasher shape, naive_aggregation_pool.rs:46-55) and the right-sparse ladder up to `depth`
+// uses ZERO_HASHES, so a ByteList[2^30] costs its data hashes + <= 25 ladder hashes.
+struct ByteItem {
+    const uint8_t* src;   // first byte (any alignment); the buffer is readable 8 bytes past the end
+    uint64_t nbytes;      // bytes that belong to the item (<= 32 << depth)
+    uint8_t* out;         // 32-byte root (16-B aligned)
+    uint64_t length;      // value mixed in when flags & 1
+    uint32_t depth;       // limit = 2^depth chunks
+    uint32_t flags;       // bit0: mix_in_length; bits 8..15: AND-mask applied to the item's last byte (bitlist delimiter)
+};
+constexpr int ITEM_THREADS = 128;
+constexpr int ITEM_TILE_LOG = 8;
+
+// chunk `c` of the item as 8 big-endian SHA words; bytes at or past nbytes read as zero
+__device__ __forceinline__ void load_item_chunk(const ByteItem& it, uint64_t c, uint32_t w[8]) {
+    const uint64_t off = 32 * c;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(it.src) + off;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = 8 * (uint32_t)(a & 3);
+    const uint64_t rem = it.nbytes - off;  // > 0 by construction
+    const uint32_t mask = (it.flags >> 8) & 0xff;
+    uint32_t lo = q[0];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t v = 0;
+        if (4u * i < rem) {
+            const uint32_t hi = q[i + 1];
+            v = __funnelshift_r(lo, hi, sh);  // little-endian bytes [4i, 4i+4)
+            lo = hi;
+            const uint64_t left = rem - 4u * i;  // valid bytes in this word (>= 1)
+            if (left < 4) v &= (1u << (8 * (uint32_t)left)) - 1;
+            if (left <= 4) v &= ~((uint32_t)(0xff ^ mask) << (8 * ((uint32_t)left - 1)));  // last byte of the item
+        }
+        w[i] = bswap32(v);
+    }
+}
+
+__global__ void __launch_bounds__(ITEM_THREADS) k_byte_items(const ByteItem* __restrict__ items) {
+    __shared__ uint32_t sm[2][ITEM_THREADS][8];
+    __shared__ uint32_t pending[40][8];  // thread 0's counter stack, one slot per height
+    const ByteItem it = items[blockIdx.x];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n = (it.nbytes + 31) / 32;
+    const uint32_t depth = it.depth;
+    const uint32_t th = depth < ITEM_TILE_LOG ? depth : ITEM_TILE_LOG;  // height of a tile root
+    const uint64_t n_tiles = (n + (1ull << th) - 1) >> th;
+    uint64_t have = 0;  // bit h set <=> pending[h] holds a complete left subtree (thread 0)
+    for (uint64_t tile = 0; tile < n_tiles; tile++) {
+        const uint64_t base = tile << th;
+        const uint32_t m = (uint32_t)min((uint64_t)(1u << th), n - base);  // valid chunks in this tile (>= 1)
+        uint32_t width;  // nodes in sm[cur]
+        int cur = 0;
+        uint32_t lvl;
+        if (th == 0) {
+            if (tid == 0) load_item_chunk(it, base, sm[0][0]);
+            width = 1; lvl = 0;
+        } else {
+            if (2 * tid < m) {
+                uint32_t l[8], r[8];
+                load_item_chunk(it, base + 2 * tid, l);
+                const bool rv = 2 * tid + 1 < m;
+                if (rv) load_item_chunk(it, base + 2 * tid + 1, r);
+                fold(l, r, rv, 0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) sm[0][tid][i] = l[i];
+            }
+            width = 1u << (th - 1); lvl = 1;
+        }
+        while (width > 1) {
+            __syncthreads();
+            const uint32_t half = width >> 1;
+            const uint32_t valid = (m + (1u << lvl) - 1) >> lvl;
+            if (tid < half && 2 * tid < valid) {
+                uint32_t l[8], r[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { l[i] = sm[cur][2 * tid][i]; r[i] = sm[cur][2 * tid + 1][i]; }
+                fold(l, r, 2 * tid + 1 < valid, lvl);
+#pragma unroll
+                for (int i = 0; i < 8; i++) sm[cur ^ 1][tid][i] = l[i];
+            }
+            cur ^= 1;
+            width = half;
+            lvl++;
+        }
+        __syncthreads();
+        if (tid == 0) {  // push the tile root (height th) onto the counter stack
+            uint32_t node[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) node[i] = sm[cur][0][i];
+            uint32_t h = th;
+            while ((have >> h) & 1) {
+                uint32_t l[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) l[i] = pending[h][i];
+                hash_pair(l, node, node);
+                have &= ~(1ull << h);
+                h++;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) pending[h][i] = node[i];
+            have |= 1ull << h;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t cur[8];
+        bool has = false;
+        for (uint32_t h = th; h < depth; h++) {
+            if ((have >> h) & 1) {
+                uint32_t l[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) l[i] = pending[h][i];
+                fold(l, cur, has, h);
+#pragma unroll
+                for (int i = 0; i < 8; i++) cur[i] = l[i];
+                has = true;
+            } else if (has) {
+                fold(cur, cur, false, h);
+            }
+        }
+        if ((have >> depth) & 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) cur[i] = pending[depth][i];
+        } else if (!has) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) cur[i] = g_zero_words[depth][i];
+        }
+        if (it.flags & 1) {
+            uint32_t len[8] = {bswap32((uint32_t)it.length), bswap32((uint32_t)(it.length >> 32)), 0, 0, 0, 0, 0, 0};
+            hash_pair(cur, len, cur);
+        }
+        store_chunk(it.out, cur);
+    }
+}
+
 // verify_merkle_proof batch (merkle_proof/src/lib.rs:357-389): one thread folds one branch bottom-up.
 __global__ void __launch_bounds__(128) k_verify_branches(const uint8_t* __restrict__ leaves,
                                                          const uint8_t* __restrict__ branches, uint32_t depth,

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <memory>
+#include <vector>
 #include "ctx.h"
 #include "merkle.cuh"
 
@@ -58,7 +59,12 @@ struct Plan {
     std::vector<std::vector<MerkleSeg>> passes;
     std::vector<HashOp> ops;
     std::vector<int> op_wave;
-    std::vector<std::pair<uint64_t, int>> ready_wave;  // dst addr -> wave producing it (small; linear scan)
+    std::vector<int16_t> slot_wave;                    // (dst - wave_origin) / 32 -> wave producing it (-1: ready at start)
+    uint64_t wave_origin = ~0ull;                      // lowest address an op may write (default: the first op's dst)
+    std::vector<ByteItem> items;                       // packed byte strings hashed straight from the staged blob
+    ByteItem* d_items = nullptr;
+    std::vector<int32_t> h_waves;                      // host copy of the wave table (wide waves get their own launch)
+    uint64_t forced_dst = 0;                           // destination of the next op_hash (0 = allocate)
     uint64_t hash_units = 0;
     // SSZ provenance of literal chunks (for lhb200_state_patch): chunk index <- n bytes at SSZ offset src_off
     struct LitSrc { uint32_t lit_index; uint32_t n; uint64_t src_off; };
@@ -71,8 +77,8 @@ struct Plan {
     int n_waves = 0;
     uint64_t root_addr = 0;
 
-    uint8_t* alloc(size_t nbytes) {  // device sub-allocation, 256-B aligned
-        size_t off = align_up(bump, 256);
+    uint8_t* alloc(size_t nbytes, size_t align = 256) {  // device sub-allocation
+        size_t off = align_up(bump, align);
         bump = off + nbytes;
         return arena ? arena + off : reinterpret_cast<uint8_t*>(off);
     }
@@ -98,33 +104,53 @@ struct Plan {
     }
     int wave_of(uint64_t operand) const {
         if (operand & OP_ZERO_FLAG) return -1;
-        for (auto it = ready_wave.rbegin(); it != ready_wave.rend(); ++it)
-            if (it->first == operand) return it->second;
-        return -1;  // staged data / literals / reduce outputs: ready before the program starts
+        const size_t slot = (operand - wave_origin) / 32;  // below the origin wraps to a huge slot
+        return slot < slot_wave.size() ? slot_wave[slot] : -1;  // staged data / literals / leaf outputs: ready at start
     }
     uint64_t op_hash(uint64_t a, uint64_t b) {
-        uint64_t dst = reinterpret_cast<uint64_t>(alloc(32));
+        uint64_t dst = forced_dst ? forced_dst : reinterpret_cast<uint64_t>(alloc(32, 32));
+        forced_dst = 0;
         int w = std::max(wave_of(a), wave_of(b)) + 1;
         ops.push_back({dst, a, b});
         op_wave.push_back(w);
-        ready_wave.push_back({dst, w});
+        if (wave_origin == ~0ull) wave_origin = dst;
+        const size_t slot = (dst - wave_origin) / 32;
+        if (slot >= slot_wave.size()) slot_wave.resize(std::max(slot + 1, 2 * slot_wave.size()), -1);
+        slot_wave[slot] = (int16_t)w;
         hash_units++;
         return dst;
     }
     uint64_t mix_in_length(uint64_t root, uint64_t len) { return op_hash(root, literal_u64(len)); }
     // merkleize k operands over next_pow2(k) leaves (container / small vectors), padding with zero hashes
-    uint64_t small_tree(std::vector<uint64_t> nodes, uint32_t depth) {
+    // `final_dst` (optional): device address that receives the root (depth >= 1)
+    uint64_t small_tree(std::vector<uint64_t> nodes, uint32_t depth, uint64_t final_dst = 0) {
         if (nodes.empty()) return zero_op(depth);
         for (uint32_t l = 0; l < depth; l++) {
             std::vector<uint64_t> nx;
-            for (size_t i = 0; i < nodes.size(); i += 2)
+            for (size_t i = 0; i < nodes.size(); i += 2) {
+                if (l + 1 == depth) forced_dst = final_dst;
                 nx.push_back(op_hash(nodes[i], i + 1 < nodes.size() ? nodes[i + 1] : zero_op(l)));
+            }
             nodes.swap(nx);
         }
         return nodes[0];
     }
-    uint64_t container(const std::vector<uint64_t>& fields) {
-        return small_tree(fields, ceil_log2(fields.size()));
+    uint64_t container(const std::vector<uint64_t>& fields, uint64_t final_dst = 0) {
+        return small_tree(fields, ceil_log2(fields.size()), final_dst);
+    }
+    // hash_tree_root of a packed byte string resident at d_src (any alignment): merkleize(pack(bytes), 2^depth),
+    // optionally mixed in with `length`; `last_mask` is ANDed onto the last byte (bitlist delimiter removal)
+    uint64_t bytes_item(const uint8_t* d_src, uint64_t nbytes, uint32_t depth, bool mix, uint64_t length = 0,
+                        uint32_t last_mask = 0xff) {
+        uint8_t* out = alloc(32, 32);
+        ByteItem it;
+        it.src = d_src; it.nbytes = nbytes; it.out = out; it.length = length; it.depth = depth;
+        it.flags = (mix ? 1u : 0u) | (last_mask << 8);
+        items.push_back(it);
+        uint64_t n = (nbytes + 31) / 32;
+        for (uint32_t l = 1; l <= depth && n > 1; l++) { n = (n + 1) / 2; hash_units += n; }
+        hash_units += mix ? 1 : 0;
+        return reinterpret_cast<uint64_t>(out);
     }
     // merkleize n chunks resident at d_in (16-B aligned) with limit 2^depth
     uint64_t merkle_list(const uint8_t* d_in, uint64_t n, uint32_t depth) {
@@ -203,8 +229,23 @@ static int32_t plan_enqueue(Plan& pl, cudaStream_t s, cudaEvent_t e0 = nullptr, 
             count_launch();
         }
     }
-    if (pl.n_waves > 0) {
-        k_hash_program<<<1, PROG_THREADS, 0, s>>>(pl.d_ops, pl.d_waves, pl.n_waves);
+    if (!pl.items.empty()) {
+        k_byte_items<<<(unsigned)pl.items.size(), ITEM_THREADS, 0, s>>>(pl.d_items);
+        count_launch();
+    }
+    // narrow waves run back to back inside one CTA; a wide wave (block batches) gets the whole grid
+    constexpr int WIDE_WAVE = 1024;
+    for (int w = 0; w < pl.n_waves;) {
+        const int cnt = pl.h_waves[w + 1] - pl.h_waves[w];
+        if (cnt >= WIDE_WAVE) {
+            k_hash_ops<<<(unsigned)ceil_div(cnt, PROG_THREADS), PROG_THREADS, 0, s>>>(pl.d_ops + pl.h_waves[w], cnt);
+            w++;
+        } else {
+            int e = w;
+            while (e < pl.n_waves && pl.h_waves[e + 1] - pl.h_waves[e] < WIDE_WAVE) e++;
+            k_hash_program<<<1, PROG_THREADS, 0, s>>>(pl.d_ops, pl.d_waves + w, e - w);
+            w = e;
+        }
         count_launch();
     }
     LHB_CUDA(cudaGetLastError());
@@ -223,6 +264,7 @@ static void plan_finalize_program(Plan& pl, std::vector<HashOp>& ops_sorted, std
         waves.push_back((int32_t)ops_sorted.size());
     }
     pl.n_waves = nw;
+    pl.h_waves = waves;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -265,6 +307,13 @@ static int32_t plan_upload(Plan& pl, cudaStream_t s, std::vector<HashOp>& ops_so
         pl.d_waves = reinterpret_cast<int32_t*>(pl.alloc(wb));
         memcpy(h + o, waves.data(), wb);
         LHB_CUDA(cudaMemcpyAsync(pl.d_waves, h + o, wb, cudaMemcpyHostToDevice, s));
+        o += align_up(wb, 256);
+    }
+    if (!pl.items.empty()) {
+        size_t ib = pl.items.size() * sizeof(ByteItem);
+        pl.d_items = reinterpret_cast<ByteItem*>(pl.alloc(ib));
+        memcpy(h + o, pl.items.data(), ib);
+        LHB_CUDA(cudaMemcpyAsync(pl.d_items, h + o, ib, cudaMemcpyHostToDevice, s));
     }
     return LHB200_OK;
 }
@@ -984,6 +1033,224 @@ int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint8_t* branch
     LHB_CUDA(cudaStreamSynchronize(c.stream));
     memcpy(ok, h + tot - b_ok, n);
     return LHB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BeaconBlockDeneb (mainnet preset): BeaconBlock::canonical_root (consensus/types/src/beacon_block.rs:158-160).
+// Layouts: beacon_block.rs:56-78 (84-byte fixed part), beacon_block_body.rs:70-121 (392), execution_payload.rs:54-95
+// (528); operation containers as cited in include/lhb200.h.  The host only walks SSZ offsets: every packed byte string
+// (transactions, signatures, pubkeys, bit lists, index lists, proofs, blooms) is hashed by k_byte_items straight
+// from the staged blob, fixed 8/20/32-byte fields become literal chunks, and the container structure above them is
+// a hash program.  `s` = host bytes, `d` = the same bytes on the device.
+}  // extern "C"
+namespace {
+struct BlockDescriber {
+    Plan& p;
+    const uint8_t* s;
+    const uint8_t* d;
+    bool bad = false;
+
+    uint64_t u64(uint64_t off) { return p.literal_bytes(s + off, 8); }
+    uint64_t h256(uint64_t off) { return p.literal_bytes(s + off, 32); }
+    uint64_t addr20(uint64_t off) { return p.literal_bytes(s + off, 20); }
+    uint64_t blob(uint64_t off, uint64_t n, uint32_t depth) { return p.bytes_item(d + off, n, depth, false); }
+    uint64_t sig(uint64_t off) { return blob(off, 96, 2); }
+    uint64_t pubkey(uint64_t off) { return blob(off, 48, 1); }
+    uint64_t checkpoint(uint64_t off) { return p.op_hash(u64(off), h256(off + 8)); }
+    uint64_t att_data(uint64_t off) {  // 128 B (attestation_data.rs:28)
+        return p.container({u64(off), u64(off + 8), h256(off + 16), checkpoint(off + 48), checkpoint(off + 88)});
+    }
+    uint64_t signed_header(uint64_t off) {  // 208 B
+        uint64_t h = p.container({u64(off), u64(off + 8), h256(off + 16), h256(off + 48), h256(off + 80)});
+        return p.op_hash(h, sig(off + 112));
+    }
+    uint64_t proposer_slashing(uint64_t off) { return p.op_hash(signed_header(off), signed_header(off + 208)); }
+    uint64_t indexed_attestation(uint64_t off, uint64_t len) {
+        if (len < 228 || rd32(s + off) != 228 || (len - 228) % 8 || (len - 228) / 8 > 2048) { bad = true; return 0; }
+        uint64_t idx = p.bytes_item(d + off + 228, len - 228, 9, true, (len - 228) / 8);
+        return p.container({idx, att_data(off + 4), sig(off + 132)});
+    }
+    uint64_t attestation(uint64_t off, uint64_t len) {
+        if (len < 229 || rd32(s + off) != 228 || s[off + len - 1] == 0) { bad = true; return 0; }
+        const uint64_t nb = len - 228;
+        const uint8_t last = s[off + len - 1];
+        int top = 7;
+        while (!((last >> top) & 1)) top--;
+        const uint64_t bitlen = 8 * (nb - 1) + (uint64_t)top;
+        if (bitlen > 2048) { bad = true; return 0; }
+        // drop the delimiter: either the whole last byte (top == 0) or its top bit
+        uint64_t bits = p.bytes_item(d + off + 228, (bitlen + 7) / 8, 3, true, bitlen, top ? (uint32_t)((1u << top) - 1) : 0xff);
+        return p.container({bits, att_data(off + 4), sig(off + 132)});
+    }
+    uint64_t deposit(uint64_t off) {  // 1240 B
+        uint64_t data = p.container({pubkey(off + 1056), h256(off + 1104), u64(off + 1136), sig(off + 1144)});
+        return p.op_hash(blob(off, 33 * 32, 6), data);
+    }
+    uint64_t voluntary_exit(uint64_t off) { return p.op_hash(p.op_hash(u64(off), u64(off + 8)), sig(off + 16)); }
+    uint64_t bls_change(uint64_t off) {
+        return p.op_hash(p.container({u64(off), pubkey(off + 8), addr20(off + 56)}), sig(off + 76));
+    }
+    uint64_t withdrawal(uint64_t off) { return p.container({u64(off), u64(off + 8), addr20(off + 16), u64(off + 36)}); }
+    uint64_t list_of(std::vector<uint64_t>& roots, uint32_t limit_log) {
+        uint64_t n = roots.size();
+        uint64_t r = p.small_tree(roots, std::min<uint32_t>(limit_log, ceil_log2(std::max<uint64_t>(n, 1))));
+        if (n == 0) r = Plan::zero_op(limit_log);
+        else for (uint32_t l = ceil_log2(n); l < limit_log; l++) r = p.op_hash(r, Plan::zero_op(l));
+        return p.mix_in_length(r, n);
+    }
+    template <class F>
+    uint64_t fixed_list(uint64_t off, uint64_t len, uint32_t item, uint32_t limit_log, F&& f) {
+        if (len % item || len / item > (1ull << limit_log)) { bad = true; return 0; }
+        std::vector<uint64_t> roots;
+        for (uint64_t i = 0; i < len / item; i++) roots.push_back(f(off + item * i));
+        return list_of(roots, limit_log);
+    }
+    // offsets table of a list of variable-size items occupying [off, off+len)
+    bool var_bounds(uint64_t off, uint64_t len, uint64_t max_n, std::vector<uint64_t>& b) {
+        b.clear();
+        if (len == 0) { b.push_back(0); return true; }
+        if (len < 4) return false;
+        const uint32_t first = rd32(s + off);
+        if (first % 4 || first == 0 || first > len || first / 4 > max_n) return false;
+        for (uint32_t i = 0; i < first / 4; i++) b.push_back(rd32(s + off + 4 * i));
+        b.push_back(len);
+        for (size_t i = 0; i + 1 < b.size(); i++)
+            if (b[i] > b[i + 1]) return false;
+        return true;
+    }
+    uint64_t payload(uint64_t off, uint64_t len) {
+        if (len < 528) { bad = true; return 0; }
+        const uint32_t o_extra = rd32(s + off + 436), o_tx = rd32(s + off + 504), o_wd = rd32(s + off + 508);
+        if (o_extra != 528 || o_tx < o_extra || o_tx - o_extra > 32 || o_wd < o_tx || o_wd > len || (len - o_wd) % 44 ||
+            (len - o_wd) / 44 > 16) { bad = true; return 0; }
+        std::vector<uint64_t> f(17);
+        f[0] = h256(off); f[1] = addr20(off + 32); f[2] = h256(off + 52); f[3] = h256(off + 84);
+        f[4] = blob(off + 116, 256, 3);
+        f[5] = h256(off + 372); f[6] = u64(off + 404); f[7] = u64(off + 412); f[8] = u64(off + 420); f[9] = u64(off + 428);
+        f[10] = p.bytes_item(d + off + o_extra, o_tx - o_extra, 0, true, o_tx - o_extra);
+        f[11] = h256(off + 440); f[12] = h256(off + 472);
+        std::vector<uint64_t> b, roots;
+        if (!var_bounds(off + o_tx, o_wd - o_tx, 1u << 20, b)) { bad = true; return 0; }
+        for (size_t i = 0; i + 1 < b.size(); i++)  // ByteList[2^30]: 2^25 chunks
+            roots.push_back(p.bytes_item(d + off + o_tx + b[i], b[i + 1] - b[i], 25, true, b[i + 1] - b[i]));
+        f[13] = list_of(roots, 20);
+        f[14] = fixed_list(off + o_wd, len - o_wd, 44, 4, [&](uint64_t o) { return withdrawal(o); });
+        f[15] = u64(off + 512); f[16] = u64(off + 520);
+        return p.container(f);
+    }
+    uint64_t body(uint64_t off, uint64_t len, uint64_t dst) {
+        if (len < 392) { bad = true; return 0; }
+        const uint32_t o_ps = rd32(s + off + 200), o_as = rd32(s + off + 204), o_at = rd32(s + off + 208),
+                       o_dp = rd32(s + off + 212), o_ex = rd32(s + off + 216), o_ep = rd32(s + off + 380),
+                       o_bc = rd32(s + off + 384), o_kz = rd32(s + off + 388);
+        if (o_ps != 392 || o_as < o_ps || o_at < o_as || o_dp < o_at || o_ex < o_dp || o_ep < o_ex || o_bc < o_ep ||
+            o_kz < o_bc || o_kz > len) { bad = true; return 0; }
+        std::vector<uint64_t> f(12), b, roots;
+        f[0] = sig(off);
+        f[1] = p.container({h256(off + 96), u64(off + 128), h256(off + 136)});  // eth1_data.rs:27
+        f[2] = h256(off + 168);
+        f[3] = fixed_list(off + o_ps, o_as - o_ps, 416, 4, [&](uint64_t o) { return proposer_slashing(o); });
+        if (!var_bounds(off + o_as, o_at - o_as, 2, b)) { bad = true; return 0; }
+        for (size_t i = 0; i + 1 < b.size(); i++) {
+            const uint64_t q = off + o_as + b[i], ql = b[i + 1] - b[i];
+            if (ql < 8) { bad = true; return 0; }
+            const uint32_t a1 = rd32(s + q), a2 = rd32(s + q + 4);
+            if (a1 != 8 || a2 < a1 || a2 > ql) { bad = true; return 0; }
+            uint64_t r1 = indexed_attestation(q + a1, a2 - a1), r2 = indexed_attestation(q + a2, ql - a2);
+            if (bad) return 0;
+            roots.push_back(p.op_hash(r1, r2));
+        }
+        f[4] = list_of(roots, 1);
+        roots.clear();
+        if (!var_bounds(off + o_at, o_dp - o_at, 128, b)) { bad = true; return 0; }
+        for (size_t i = 0; i + 1 < b.size(); i++) {
+            roots.push_back(attestation(off + o_at + b[i], b[i + 1] - b[i]));
+            if (bad) return 0;
+        }
+        f[5] = list_of(roots, 7);
+        f[6] = fixed_list(off + o_dp, o_ex - o_dp, 1240, 4, [&](uint64_t o) { return deposit(o); });
+        f[7] = fixed_list(off + o_ex, o_ep - o_ex, 112, 4, [&](uint64_t o) { return voluntary_exit(o); });
+        f[8] = p.op_hash(blob(off + 220, 64, 1), sig(off + 284));  // sync_aggregate.rs:38
+        f[9] = payload(off + o_ep, o_bc - o_ep);
+        f[10] = fixed_list(off + o_bc, o_kz - o_bc, 172, 4, [&](uint64_t o) { return bls_change(o); });
+        f[11] = fixed_list(off + o_kz, len - o_kz, 48, 12, [&](uint64_t o) { return pubkey(o); });  // kzg_commitment.rs:51
+        if (bad) return 0;
+        return p.container(f, dst);
+    }
+    uint64_t block(uint64_t off, uint64_t len, uint64_t dst_root, uint64_t dst_body) {
+        if (len < 84 || rd32(s + off + 80) != 84) { bad = true; return 0; }
+        uint64_t b = body(off + 84, len - 84, dst_body);
+        if (bad) return 0;
+        return p.container({u64(off), u64(off + 8), h256(off + 16), h256(off + 48), b}, dst_root);
+    }
+};
+}  // namespace
+extern "C" {
+
+// n BeaconBlockDeneb SSZ blobs, concatenated; offsets[n+1]; roots n*32; body_roots n*32 or NULL.
+int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
+                                        uint8_t* body_roots) {
+    LHB_REQUIRE_READY();
+    if (!ssz || !offsets || !roots || n == 0) { set_error("beacon_block_roots: null argument or zero blocks"); return LHB200_EINVAL; }
+    for (uint32_t i = 0; i < n; i++)
+        if (offsets[i] > offsets[i + 1]) { set_error("beacon_block_roots: offsets not monotone"); return LHB200_EINVAL; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const uint64_t base = offsets[0], total = offsets[n] - offsets[0];
+    const size_t in_pad = align_up(total + 64, 256);
+    const size_t lit_cap = align_up(8 * total + 4096, 256);  // every 4 input bytes yield at most one 32-byte literal
+    uint8_t *d_in = nullptr, *d_roots = nullptr, *d_body = nullptr;
+    bool bad = false;
+    auto build = [&](Plan& p) {
+        d_in = p.alloc(in_pad);
+        d_roots = p.alloc(32ull * n);
+        d_body = p.alloc(32ull * n);
+        p.wave_origin = reinterpret_cast<uint64_t>(d_roots);
+        BlockDescriber bd{p, ssz + base, d_in};
+        for (uint32_t i = 0; i < n && !bd.bad; i++)
+            bd.block(offsets[i] - base, offsets[i + 1] - offsets[i], reinterpret_cast<uint64_t>(d_roots + 32ull * i),
+                     reinterpret_cast<uint64_t>(d_body + 32ull * i));
+        bad = bd.bad;
+    };
+    // One planning pass over a conservatively sized arena (host time matters here: a block is only ~10^4 hashes).
+    // Nodes (ops + items) <= one per 4 input bytes + the zero ladders of the 10 lists of a block.
+    const size_t max_nodes = total / 4 + 512ull * n;
+    const size_t prog_bytes = align_up(max_nodes * sizeof(HashOp), 256) + align_up((max_nodes + 2) * 4, 256) +
+                              align_up(max_nodes * sizeof(ByteItem), 256) + 1024;
+    const size_t need = lit_cap + in_pad + 64ull * n + 32 * max_nodes + prog_bytes + 4096;
+    uint8_t* arena = static_cast<uint8_t*>(dev_scratch(need));
+    const size_t stage_bytes = align_up(total, 256) + lit_cap + prog_bytes + 64ull * n + 1024;
+    uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(stage_bytes));
+    if (!arena || !hst) return LHB200_ENOMEM;
+    Plan pl;
+    int32_t rc = build_plan(pl, arena, need, lit_cap, build);
+    if (bad) { set_error("BeaconBlockDeneb SSZ: malformed offsets or lengths"); return LHB200_EINVAL; }
+    if (rc) return rc;
+    if (pl.ops.size() + pl.items.size() > max_nodes || pl.bump + prog_bytes > need) {
+        set_error("internal: block plan exceeds its arena bound");
+        return LHB200_EINVAL;
+    }
+    memcpy(hst, ssz + base, total);
+    memset(hst + total, 0, align_up(total, 256) - total);
+    LHB_CUDA(cudaMemcpyAsync(d_in, hst, align_up(total, 256), cudaMemcpyHostToDevice, c.stream));
+    std::vector<HashOp> ops_sorted;
+    std::vector<int32_t> waves;
+    plan_finalize_program(pl, ops_sorted, waves);
+    rc = plan_upload(pl, c.stream, ops_sorted, waves, hst + align_up(total, 256));
+    if (rc) return rc;
+    rc = plan_enqueue(pl, c.stream);
+    if (rc) return rc;
+    uint8_t* h_out = hst + stage_bytes - 64ull * n - 64;
+    LHB_CUDA(cudaMemcpyAsync(h_out, d_roots, 32ull * n, cudaMemcpyDeviceToHost, c.stream));
+    if (body_roots) LHB_CUDA(cudaMemcpyAsync(h_out + 32ull * n, d_body, 32ull * n, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(roots, h_out, 32ull * n);
+    if (body_roots) memcpy(body_roots, h_out + 32ull * n, 32ull * n);
+    return LHB200_OK;
+}
+int32_t lhb200_beacon_block_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* body_root) {
+    const uint64_t offs[2] = {0, len};
+    return lhb200_beacon_block_roots_deneb(ssz, offs, 1, out, body_root);
 }
 
 // swap_or_not_shuffle::shuffle_list(input, rounds, seed, forwards) (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79).

@@ -1,0 +1,126 @@
+"""Minimal SSZ type descriptors + serializer for the Deneb BeaconBlock (mainnet preset), used to BUILD synthetic
+blocks (consensus/types/src/beacon_block.rs:56-78, beacon_block_body.rs:70-121, execution_payload.rs:54-95 and the
+operation containers).  Serialization only — hashing is the CUDA library's job (tests/ssz_spec.py holds the
+from-spec hashlib hash_tree_root used to pin the oracle).
+
+Types:  ("uint", nbytes) | ("bytes", n) fixed byte vector | ("bytelist", limit) | ("bitlist", limit) |
+        ("bitvector", nbits) | ("vector", elem, n) | ("list", elem, limit) | ("container", [(name, type), ...])
+Values: int | bytes | list[bool] for bit types | list | dict.
+"""
+
+U64 = ("uint", 8)
+U256 = ("uint", 32)
+B20, B32, B48, B96 = ("bytes", 20), ("bytes", 32), ("bytes", 48), ("bytes", 96)
+
+
+def C(*fields):
+    return ("container", list(fields))
+
+
+Checkpoint = C(("epoch", U64), ("root", B32))
+AttestationData = C(("slot", U64), ("index", U64), ("beacon_block_root", B32), ("source", Checkpoint),
+                    ("target", Checkpoint))
+BeaconBlockHeader = C(("slot", U64), ("proposer_index", U64), ("parent_root", B32), ("state_root", B32),
+                      ("body_root", B32))
+SignedBeaconBlockHeader = C(("message", BeaconBlockHeader), ("signature", B96))
+ProposerSlashing = C(("signed_header_1", SignedBeaconBlockHeader), ("signed_header_2", SignedBeaconBlockHeader))
+IndexedAttestation = C(("attesting_indices", ("list", U64, 2048)), ("data", AttestationData), ("signature", B96))
+AttesterSlashing = C(("attestation_1", IndexedAttestation), ("attestation_2", IndexedAttestation))
+Attestation = C(("aggregation_bits", ("bitlist", 2048)), ("data", AttestationData), ("signature", B96))
+Eth1Data = C(("deposit_root", B32), ("deposit_count", U64), ("block_hash", B32))
+DepositData = C(("pubkey", B48), ("withdrawal_credentials", B32), ("amount", U64), ("signature", B96))
+Deposit = C(("proof", ("vector", B32, 33)), ("data", DepositData))
+VoluntaryExit = C(("epoch", U64), ("validator_index", U64))
+SignedVoluntaryExit = C(("message", VoluntaryExit), ("signature", B96))
+SyncAggregate = C(("sync_committee_bits", ("bitvector", 512)), ("sync_committee_signature", B96))
+Withdrawal = C(("index", U64), ("validator_index", U64), ("address", B20), ("amount", U64))
+BlsToExecutionChange = C(("validator_index", U64), ("from_bls_pubkey", B48), ("to_execution_address", B20))
+SignedBlsToExecutionChange = C(("message", BlsToExecutionChange), ("signature", B96))
+ExecutionPayloadDeneb = C(
+    ("parent_hash", B32), ("fee_recipient", B20), ("state_root", B32), ("receipts_root", B32),
+    ("logs_bloom", ("bytes", 256)), ("prev_randao", B32), ("block_number", U64), ("gas_limit", U64),
+    ("gas_used", U64), ("timestamp", U64), ("extra_data", ("bytelist", 32)), ("base_fee_per_gas", U256),
+    ("block_hash", B32), ("transactions", ("list", ("bytelist", 1 << 30), 1 << 20)),
+    ("withdrawals", ("list", Withdrawal, 16)), ("blob_gas_used", U64), ("excess_blob_gas", U64))
+BeaconBlockBodyDeneb = C(
+    ("randao_reveal", B96), ("eth1_data", Eth1Data), ("graffiti", B32),
+    ("proposer_slashings", ("list", ProposerSlashing, 16)), ("attester_slashings", ("list", AttesterSlashing, 2)),
+    ("attestations", ("list", Attestation, 128)), ("deposits", ("list", Deposit, 16)),
+    ("voluntary_exits", ("list", SignedVoluntaryExit, 16)), ("sync_aggregate", SyncAggregate),
+    ("execution_payload", ExecutionPayloadDeneb),
+    ("bls_to_execution_changes", ("list", SignedBlsToExecutionChange, 16)),
+    ("blob_kzg_commitments", ("list", B48, 4096)))
+BeaconBlockDeneb = C(("slot", U64), ("proposer_index", U64), ("parent_root", B32), ("state_root", B32),
+                     ("body", BeaconBlockBodyDeneb))
+SignedBeaconBlockDeneb = C(("message", BeaconBlockDeneb), ("signature", B96))
+
+
+def is_fixed(t):
+    k = t[0]
+    if k in ("uint", "bytes", "bitvector"):
+        return True
+    if k in ("bytelist", "bitlist", "list"):
+        return False
+    if k == "vector":
+        return is_fixed(t[1])
+    return all(is_fixed(ft) for _, ft in t[1])
+
+
+def fixed_size(t):
+    k = t[0]
+    if k in ("uint", "bytes"):
+        return t[1]
+    if k == "bitvector":
+        return (t[1] + 7) // 8
+    if k == "vector":
+        return t[2] * fixed_size(t[1])
+    return sum(fixed_size(ft) if is_fixed(ft) else 4 for _, ft in t[1])
+
+
+def pack_bits(bits, delimiter):
+    bits = list(bits) + ([True] if delimiter else [])
+    out = bytearray((len(bits) + 7) // 8)
+    for i, b in enumerate(bits):
+        if b:
+            out[i // 8] |= 1 << (i % 8)
+    return bytes(out)
+
+
+def _sequence(parts, fixed_flags):
+    """SSZ layout of a heterogeneous sequence: fixed parts inline, variable parts behind 4-byte offsets."""
+    head = sum(len(p) if f else 4 for p, f in zip(parts, fixed_flags))
+    out, tail = bytearray(), bytearray()
+    for p, f in zip(parts, fixed_flags):
+        if f:
+            out += p
+        else:
+            out += (head + len(tail)).to_bytes(4, "little")
+            tail += p
+    return bytes(out + tail)
+
+
+def serialize(t, v):
+    k = t[0]
+    if k == "uint":
+        return int(v).to_bytes(t[1], "little")
+    if k == "bytes":
+        assert len(v) == t[1], (t, len(v))
+        return bytes(v)
+    if k == "bytelist":
+        assert len(v) <= t[1]
+        return bytes(v)
+    if k == "bitlist":
+        assert len(v) <= t[1]
+        return pack_bits(v, True)
+    if k == "bitvector":
+        assert len(v) == t[1]
+        return pack_bits(v, False)
+    if k in ("vector", "list"):
+        if k == "vector":
+            assert len(v) == t[2]
+        else:
+            assert len(v) <= t[2]
+        parts = [serialize(t[1], e) for e in v]
+        return _sequence(parts, [is_fixed(t[1])] * len(parts))
+    parts = [serialize(ft, v[name]) for name, ft in t[1]]
+    return _sequence(parts, [is_fixed(ft) for _, ft in t[1]])

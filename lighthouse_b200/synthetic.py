@@ -172,3 +172,73 @@ def attestation_batch(n_sets, keys_per_set=128, n_validators=16384, seed=0x11570
     pks = pk_tab[committees.reshape(-1)].tobytes()
     offsets = (np.arange(n_sets + 1, dtype=np.uint64) * keys_per_set).astype(np.uint32)
     return AttestationBatch(sigs, msgs, pks, offsets, committees, pk_tab)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Synthetic Deneb BeaconBlock (mainnet preset) — values + SSZ bytes.
+def beacon_block_deneb(seed=1, n_attestations=128, n_transactions=150, n_proposer_slashings=1,
+                       n_attester_slashings=1, n_deposits=2, n_exits=3, n_bls_changes=4, n_withdrawals=16,
+                       n_blobs=6, tx_sizes=None, committee=244, extra_data_len=13):
+    """-> (value, ssz_bytes) of a BeaconBlockDeneb filled with seeded pseudo-random content of mainnet shape."""
+    from . import ssz_schema as S
+    rng = np.random.default_rng(seed)
+
+    def rb(n):
+        return rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+
+    def u64():
+        return int(rng.integers(0, 1 << 62))
+
+    def checkpoint():
+        return {"epoch": u64(), "root": rb(32)}
+
+    def att_data():
+        return {"slot": u64(), "index": u64() % 64, "beacon_block_root": rb(32), "source": checkpoint(),
+                "target": checkpoint()}
+
+    def header():
+        return {"message": {"slot": u64(), "proposer_index": u64(), "parent_root": rb(32), "state_root": rb(32),
+                            "body_root": rb(32)}, "signature": rb(96)}
+
+    def indexed(n):
+        return {"attesting_indices": sorted(int(x) for x in rng.integers(0, 1 << 20, size=n)), "data": att_data(),
+                "signature": rb(96)}
+
+    if tx_sizes is None:
+        # mainnet-like mix: mostly a few hundred bytes, some multi-KB calldata, the odd empty / chunk-boundary size
+        tx_sizes = [int(x) for x in rng.choice([0, 1, 31, 32, 33, 110, 180, 256, 257, 700, 2_500, 20_000],
+                                               size=n_transactions)]
+    payload = {
+        "parent_hash": rb(32), "fee_recipient": rb(20), "state_root": rb(32), "receipts_root": rb(32),
+        "logs_bloom": rb(256), "prev_randao": rb(32), "block_number": u64(), "gas_limit": 30_000_000,
+        "gas_used": u64() % 30_000_000, "timestamp": u64(), "extra_data": rb(extra_data_len),
+        "base_fee_per_gas": int.from_bytes(rb(12), "little"), "block_hash": rb(32),
+        "transactions": [rb(n) for n in tx_sizes],
+        "withdrawals": [{"index": u64(), "validator_index": u64(), "address": rb(20), "amount": u64()}
+                        for _ in range(n_withdrawals)],
+        "blob_gas_used": 131072 * n_blobs, "excess_blob_gas": u64()}
+    body = {
+        "randao_reveal": rb(96),
+        "eth1_data": {"deposit_root": rb(32), "deposit_count": u64(), "block_hash": rb(32)},
+        "graffiti": rb(32),
+        "proposer_slashings": [{"signed_header_1": header(), "signed_header_2": header()}
+                               for _ in range(n_proposer_slashings)],
+        "attester_slashings": [{"attestation_1": indexed(committee), "attestation_2": indexed(committee // 2 + 1)}
+                               for _ in range(n_attester_slashings)],
+        "attestations": [{"aggregation_bits": [bool(b) for b in rng.integers(0, 2, size=min(2048, committee + (i % 7)))],
+                          "data": att_data(), "signature": rb(96)} for i in range(n_attestations)],
+        "deposits": [{"proof": [rb(32) for _ in range(33)],
+                      "data": {"pubkey": rb(48), "withdrawal_credentials": rb(32), "amount": 32_000_000_000,
+                               "signature": rb(96)}} for _ in range(n_deposits)],
+        "voluntary_exits": [{"message": {"epoch": u64(), "validator_index": u64()}, "signature": rb(96)}
+                            for _ in range(n_exits)],
+        "sync_aggregate": {"sync_committee_bits": [bool(b) for b in rng.integers(0, 2, size=512)],
+                           "sync_committee_signature": rb(96)},
+        "execution_payload": payload,
+        "bls_to_execution_changes": [{"message": {"validator_index": u64(), "from_bls_pubkey": rb(48),
+                                                  "to_execution_address": rb(20)}, "signature": rb(96)}
+                                     for _ in range(n_bls_changes)],
+        "blob_kzg_commitments": [rb(48) for _ in range(n_blobs)]}
+    block = {"slot": u64(), "proposer_index": u64() % 500_000, "parent_root": rb(32), "state_root": rb(32),
+             "body": body}
+    return block, S.serialize(S.BeaconBlockDeneb, block)

@@ -89,6 +89,29 @@ def beacon_state_root_deneb(ssz, want_field_roots=False):
     return out.raw
 
 
+def beacon_block_roots_deneb(blocks, want_body_roots=False):
+    """BeaconBlock::canonical_root (beacon_block.rs:158-160) of a batch of BeaconBlockDeneb SSZ blobs in one pass."""
+    blocks = [bytes(b) for b in blocks]
+    n = len(blocks)
+    offs = (C.c_uint64 * (n + 1))()
+    for i, b in enumerate(blocks):
+        offs[i + 1] = offs[i] + len(b)
+    p, keep = buf(b"".join(blocks))
+    out = C.create_string_buffer(32 * max(n, 1))
+    body = C.create_string_buffer(32 * max(n, 1)) if want_body_roots else None
+    check(lib.lhb200_beacon_block_roots_deneb(p, C.cast(offs, C.c_void_p), n, out, body), "lhb200_beacon_block_roots_deneb")
+    roots = [out.raw[32 * i: 32 * i + 32] for i in range(n)]
+    if want_body_roots:
+        return roots, [body.raw[32 * i: 32 * i + 32] for i in range(n)]
+    return roots
+
+
+def beacon_block_root_deneb(ssz, want_body_root=False):
+    """canonical_root of one BeaconBlockDeneb; optionally also hash_tree_root(body) (BeaconBlockHeader.body_root)."""
+    r = beacon_block_roots_deneb([ssz], want_body_root)
+    return (r[0][0], r[1][0]) if want_body_root else r[0]
+
+
 class ShardedState:
     """One rank's shard of a BeaconStateDeneb hashed over `world` GPUs."""
 

@@ -595,3 +595,257 @@ EXPORT int64_t orc_compute_shuffled_index(uint64_t index, uint64_t n, const uint
     }
     return (int64_t)index;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * hash_tree_root(BeaconBlockDeneb) from SSZ bytes, mainnet preset:
+ *   BeaconBlock ........................ consensus/types/src/beacon_block.rs:56-78, canonical_root :158-160
+ *   BeaconBlockBodyDeneb (12 fields) ... consensus/types/src/beacon_block_body.rs:70-121
+ *   ExecutionPayloadDeneb (17 fields) .. consensus/types/src/execution_payload.rs:54-95
+ *   operations ......................... proposer_slashing.rs:26, attester_slashing.rs:42, indexed_attestation.rs:53,
+ *                                        attestation.rs:74, deposit.rs:27, deposit_data.rs:25, signed_voluntary_exit.rs:25,
+ *                                        sync_aggregate.rs:38, signed_bls_to_execution_change.rs:22, withdrawal.rs:22
+ *   limits ............................. consensus/types/src/eth_spec.rs:394-432
+ * Pinned by tests/test_block_root.py against tests/ssz_spec.py (generic from-spec hashlib merkleization).  The
+ * reference's own pin (EF ssz_static) is not on disk: parity unpinned in-tree, pinned transitively. */
+static void bytes_root(const uint8_t *p, uint64_t n, uint32_t depth, uint8_t out[32]) { orc_merkleize_bytes(p, n, depth, out); }
+static void list_bytes_root(const uint8_t *p, uint64_t nbytes, uint32_t depth, uint64_t count, uint8_t out[32]) {
+    uint8_t r[32];
+    orc_merkleize_bytes(p, nbytes, depth, r);
+    orc_mix_in_length(r, count, out);
+}
+static void att_data_root(const uint8_t *p, uint8_t out[32]) { /* 128 B */
+    uint8_t l[5][32];
+    u64_chunk(p, l[0]);
+    u64_chunk(p + 8, l[1]);
+    memcpy(l[2], p + 16, 32);
+    checkpoint_root(p + 48, l[3]);
+    checkpoint_root(p + 88, l[4]);
+    container_root(l, 5, out);
+}
+static void signed_header_root(const uint8_t *p, uint8_t out[32]) { /* 208 B */
+    uint8_t h[5][32], l[2][32];
+    u64_chunk(p, h[0]);
+    u64_chunk(p + 8, h[1]);
+    memcpy(h[2], p + 16, 32);
+    memcpy(h[3], p + 48, 32);
+    memcpy(h[4], p + 80, 32);
+    container_root(h, 5, l[0]);
+    bytes_root(p + 112, 96, 2, l[1]);
+    container_root(l, 2, out);
+}
+static int indexed_attestation_root(const uint8_t *p, uint64_t len, uint8_t out[32]) {
+    if (len < 228 || rd32(p) != 228 || (len - 228) % 8 || (len - 228) / 8 > 2048) return -1;
+    uint8_t l[3][32];
+    list_bytes_root(p + 228, len - 228, 9, (len - 228) / 8, l[0]);
+    att_data_root(p + 4, l[1]);
+    bytes_root(p + 132, 96, 2, l[2]);
+    container_root(l, 3, out);
+    return 0;
+}
+static int attestation_root(const uint8_t *p, uint64_t len, uint8_t out[32]) {
+    if (len < 229 || rd32(p) != 228 || p[len - 1] == 0) return -1;
+    uint64_t nb = len - 228;
+    uint8_t last = p[len - 1];
+    int top = 7;
+    while (!((last >> top) & 1)) top--;
+    uint64_t bitlen = 8 * (nb - 1) + (uint64_t)top;
+    if (bitlen > 2048) return -1;
+    uint8_t bits[260];
+    memcpy(bits, p + 228, nb);
+    bits[nb - 1] = (uint8_t)(last & ~(1u << top));
+    uint8_t l[3][32];
+    list_bytes_root(bits, (bitlen + 7) / 8, 3, bitlen, l[0]);
+    att_data_root(p + 4, l[1]);
+    bytes_root(p + 132, 96, 2, l[2]);
+    container_root(l, 3, out);
+    return 0;
+}
+static void deposit_root(const uint8_t *p, uint8_t out[32]) { /* 1240 B */
+    uint8_t l[2][32], d[4][32];
+    orc_merkleize(p, 33, 6, l[0]);
+    pubkey_root(p + 1056, d[0]);
+    memcpy(d[1], p + 1104, 32);
+    u64_chunk(p + 1136, d[2]);
+    bytes_root(p + 1144, 96, 2, d[3]);
+    container_root(d, 4, l[1]);
+    container_root(l, 2, out);
+}
+static void exit_root(const uint8_t *p, uint8_t out[32]) { /* 112 B */
+    uint8_t m[2][32], l[2][32];
+    u64_chunk(p, m[0]);
+    u64_chunk(p + 8, m[1]);
+    container_root(m, 2, l[0]);
+    bytes_root(p + 16, 96, 2, l[1]);
+    container_root(l, 2, out);
+}
+static void bls_change_root(const uint8_t *p, uint8_t out[32]) { /* 172 B */
+    uint8_t m[3][32], l[2][32];
+    u64_chunk(p, m[0]);
+    pubkey_root(p + 8, m[1]);
+    memset(m[2], 0, 32);
+    memcpy(m[2], p + 56, 20);
+    container_root(m, 3, l[0]);
+    bytes_root(p + 76, 96, 2, l[1]);
+    container_root(l, 2, out);
+}
+static void withdrawal_root(const uint8_t *p, uint8_t out[32]) { /* 44 B */
+    uint8_t l[4][32];
+    u64_chunk(p, l[0]);
+    u64_chunk(p + 8, l[1]);
+    memset(l[2], 0, 32);
+    memcpy(l[2], p + 16, 20);
+    u64_chunk(p + 36, l[3]);
+    container_root(l, 4, out);
+}
+/* list of variable-size items: region [p, p+len) starts with n 4-byte offsets */
+static int var_list_bounds(const uint8_t *p, uint64_t len, uint64_t max_n, uint64_t *n, uint64_t **bounds) {
+    *n = 0;
+    *bounds = NULL;
+    if (len == 0) return 0;
+    if (len < 4) return -1;
+    uint32_t first = rd32(p);
+    if (first % 4 || first == 0 || first > len || first / 4 > max_n) return -1;
+    uint64_t k = first / 4;
+    uint64_t *b = (uint64_t *)malloc((k + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < k; i++) b[i] = rd32(p + 4 * i);
+    b[k] = len;
+    for (uint64_t i = 0; i < k; i++)
+        if (b[i] > b[i + 1]) { free(b); return -1; }
+    *n = k;
+    *bounds = b;
+    return 0;
+}
+static int payload_root_deneb(const uint8_t *p, uint64_t len, uint8_t out[32]) {
+    if (len < 528) return -1;
+    uint32_t o_extra = rd32(p + 436), o_tx = rd32(p + 504), o_wd = rd32(p + 508);
+    if (o_extra != 528 || o_tx < o_extra || o_tx - o_extra > 32 || o_wd < o_tx || o_wd > len || (len - o_wd) % 44 ||
+        (len - o_wd) / 44 > 16)
+        return -1;
+    uint8_t l[17][32];
+    memset(l, 0, sizeof l);
+    memcpy(l[0], p, 32);
+    memcpy(l[1], p + 32, 20);
+    memcpy(l[2], p + 52, 32);
+    memcpy(l[3], p + 84, 32);
+    orc_merkleize(p + 116, 8, 3, l[4]);
+    memcpy(l[5], p + 372, 32);
+    memcpy(l[6], p + 404, 8);
+    memcpy(l[7], p + 412, 8);
+    memcpy(l[8], p + 420, 8);
+    memcpy(l[9], p + 428, 8);
+    list_bytes_root(p + o_extra, o_tx - o_extra, 0, o_tx - o_extra, l[10]);
+    memcpy(l[11], p + 440, 32);
+    memcpy(l[12], p + 472, 32);
+    { /* transactions: List[ByteList[2^30], 2^20] */
+        uint64_t n, *b;
+        if (var_list_bounds(p + o_tx, o_wd - o_tx, 1u << 20, &n, &b)) return -1;
+        uint8_t *roots = (uint8_t *)malloc((size_t)(n ? n : 1) * 32);
+        for (uint64_t i = 0; i < n; i++)
+            list_bytes_root(p + o_tx + b[i], b[i + 1] - b[i], 25, b[i + 1] - b[i], roots + 32 * i);
+        uint8_t r[32];
+        orc_merkleize(roots, n, 20, r);
+        orc_mix_in_length(r, n, l[13]);
+        free(roots);
+        free(b);
+    }
+    { /* withdrawals: List[Withdrawal, 16] */
+        uint64_t n = (len - o_wd) / 44;
+        uint8_t roots[16][32], r[32];
+        for (uint64_t i = 0; i < n; i++) withdrawal_root(p + o_wd + 44 * i, roots[i]);
+        orc_merkleize(&roots[0][0], n, 4, r);
+        orc_mix_in_length(r, n, l[14]);
+    }
+    memcpy(l[15], p + 512, 8);
+    memcpy(l[16], p + 520, 8);
+    container_root(l, 17, out);
+    return 0;
+}
+/* fixed-size item list: n = len / item, depth = log2(limit) */
+static int fixed_list_root(const uint8_t *p, uint64_t len, uint32_t item, uint32_t limit_log, void (*f)(const uint8_t *, uint8_t *),
+                           uint8_t out[32]) {
+    if (len % item || len / item > (1ull << limit_log)) return -1;
+    uint64_t n = len / item;
+    uint8_t *roots = (uint8_t *)malloc((size_t)(n ? n : 1) * 32), r[32];
+    for (uint64_t i = 0; i < n; i++) f(p + (uint64_t)item * i, roots + 32 * i);
+    orc_merkleize(roots, n, limit_log, r);
+    orc_mix_in_length(r, n, out);
+    free(roots);
+    return 0;
+}
+static void proposer_slashing_root(const uint8_t *p, uint8_t out[32]) { /* 416 B */
+    uint8_t l[2][32];
+    signed_header_root(p, l[0]);
+    signed_header_root(p + 208, l[1]);
+    container_root(l, 2, out);
+}
+static void kzg_commitment_root(const uint8_t *p, uint8_t out[32]) { pubkey_root(p, out); } /* 48 B blob (kzg_commitment.rs:51) */
+
+EXPORT int orc_beacon_block_body_root_deneb(const uint8_t *p, uint64_t len, uint8_t out[32]) {
+    ensure_backend();
+    if (len < 392) return -1;
+    uint32_t o_ps = rd32(p + 200), o_as = rd32(p + 204), o_at = rd32(p + 208), o_dp = rd32(p + 212), o_ex = rd32(p + 216),
+             o_ep = rd32(p + 380), o_bc = rd32(p + 384), o_kz = rd32(p + 388);
+    if (o_ps != 392 || o_as < o_ps || o_at < o_as || o_dp < o_at || o_ex < o_dp || o_ep < o_ex || o_bc < o_ep || o_kz < o_bc ||
+        o_kz > len)
+        return -1;
+    uint8_t l[12][32];
+    bytes_root(p, 96, 2, l[0]);
+    eth1_data_root(p + 96, l[1]);
+    memcpy(l[2], p + 168, 32);
+    if (fixed_list_root(p + o_ps, o_as - o_ps, 416, 4, proposer_slashing_root, l[3])) return -1;
+    { /* attester_slashings: List[AttesterSlashing, 2] (variable-size items) */
+        uint64_t n, *b;
+        if (var_list_bounds(p + o_as, o_at - o_as, 2, &n, &b)) return -1;
+        uint8_t roots[2][32], r[32];
+        for (uint64_t i = 0; i < n; i++) {
+            const uint8_t *q = p + o_as + b[i];
+            uint64_t ql = b[i + 1] - b[i];
+            if (ql < 8) { free(b); return -1; }
+            uint32_t a1 = rd32(q), a2 = rd32(q + 4);
+            uint8_t pr[2][32];
+            if (a1 != 8 || a2 < a1 || a2 > ql || indexed_attestation_root(q + a1, a2 - a1, pr[0]) ||
+                indexed_attestation_root(q + a2, ql - a2, pr[1])) { free(b); return -1; }
+            container_root(pr, 2, roots[i]);
+        }
+        orc_merkleize(&roots[0][0], n, 1, r);
+        orc_mix_in_length(r, n, l[4]);
+        free(b);
+    }
+    { /* attestations: List[Attestation, 128] */
+        uint64_t n, *b;
+        if (var_list_bounds(p + o_at, o_dp - o_at, 128, &n, &b)) return -1;
+        uint8_t roots[128][32], r[32];
+        for (uint64_t i = 0; i < n; i++)
+            if (attestation_root(p + o_at + b[i], b[i + 1] - b[i], roots[i])) { free(b); return -1; }
+        orc_merkleize(&roots[0][0], n, 7, r);
+        orc_mix_in_length(r, n, l[5]);
+        free(b);
+    }
+    if (fixed_list_root(p + o_dp, o_ex - o_dp, 1240, 4, deposit_root, l[6])) return -1;
+    if (fixed_list_root(p + o_ex, o_ep - o_ex, 112, 4, exit_root, l[7])) return -1;
+    { /* sync_aggregate: {Bitvector[512], signature} */
+        uint8_t s[2][32];
+        orc_merkleize(p + 220, 2, 1, s[0]);
+        bytes_root(p + 284, 96, 2, s[1]);
+        container_root(s, 2, l[8]);
+    }
+    if (payload_root_deneb(p + o_ep, o_bc - o_ep, l[9])) return -1;
+    if (fixed_list_root(p + o_bc, o_kz - o_bc, 172, 4, bls_change_root, l[10])) return -1;
+    if (fixed_list_root(p + o_kz, len - o_kz, 48, 12, kzg_commitment_root, l[11])) return -1;
+    container_root(l, 12, out);
+    return 0;
+}
+
+/* BeaconBlock::canonical_root (beacon_block.rs:158-160).  body_root (32 B) optional. */
+EXPORT int orc_beacon_block_root_deneb(const uint8_t *p, uint64_t len, uint8_t out[32], uint8_t *body_root) {
+    if (len < 84 || rd32(p + 80) != 84) return -1;
+    uint8_t l[5][32];
+    u64_chunk(p, l[0]);
+    u64_chunk(p + 8, l[1]);
+    memcpy(l[2], p + 16, 32);
+    memcpy(l[3], p + 48, 32);
+    if (orc_beacon_block_body_root_deneb(p + 84, len - 84, l[4])) return -1;
+    if (body_root) memcpy(body_root, l[4], 32);
+    container_root(l, 5, out);
+    return 0;
+}

@@ -138,3 +138,10 @@ def compute_shuffled_index(index, n, seed, rounds):
     L.orc_compute_shuffled_index.restype = C.c_int64
     v = L.orc_compute_shuffled_index(C.c_uint64(index), C.c_uint64(n), seed, C.c_uint8(rounds))
     return None if v < 0 else int(v)
+
+
+def beacon_block_root_deneb(ssz):
+    """-> (root, body_root) or None when the oracle rejects the SSZ."""
+    out, body = (C.c_uint8 * 32)(), (C.c_uint8 * 32)()
+    rc = L.orc_beacon_block_root_deneb(bytes(ssz), C.c_uint64(len(ssz)), out, body)
+    return None if rc else (bytes(out), bytes(body))

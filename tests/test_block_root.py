@@ -1,0 +1,85 @@
+"""BeaconBlockDeneb canonical_root.  The oracle's hand-unrolled C restatement is pinned by the
+generic from-spec hashlib merkleization in tests/ssz_spec.py (the reference's own pin, EF ssz_static, is not on disk);
+the CUDA path is compared bit-exactly with the oracle through the C ABI."""
+import pytest
+
+from lighthouse_b200 import ssz_schema as S
+from lighthouse_b200 import synthetic
+from tests import oracle_lib as O
+from tests import ssz_spec
+
+EMPTY = dict(n_attestations=0, n_transactions=0, n_proposer_slashings=0, n_attester_slashings=0, n_deposits=0, n_exits=0,
+             n_bls_changes=0, n_withdrawals=0, n_blobs=0, extra_data_len=0)
+CASES = {
+    "mainnet_like": dict(),
+    "empty_body": EMPTY,
+    "full_operations": dict(seed=7, n_attester_slashings=2, n_proposer_slashings=16, n_deposits=16, n_exits=16,
+                            n_bls_changes=16, extra_data_len=32, n_blobs=64,
+                            tx_sizes=[0, 1, 31, 32, 33, 64, 255, 256, 257, 288, 8191, 8192, 8193, 100_000, 1 << 20]),
+    "max_committee": dict(seed=9, committee=2048, n_attestations=9, tx_sizes=[5]),
+    "bit_boundaries": dict(seed=11, committee=250, n_attestations=16, n_transactions=3),  # bit lengths 250..256
+    "one_empty_tx": dict(seed=12, tx_sizes=[0], n_attestations=1),
+}
+
+
+def _block(name):
+    return synthetic.beacon_block_deneb(**CASES[name])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_block_root_matches_spec_merkleization(name):
+    value, ssz = _block(name)
+    want = ssz_spec.hash_tree_root(S.BeaconBlockDeneb, value)
+    want_body = ssz_spec.hash_tree_root(S.BeaconBlockBodyDeneb, value["body"])
+    assert O.beacon_block_root_deneb(ssz) == (want, want_body)
+
+
+def _malformed():
+    _, ssz = _block("mainnet_like")
+    bad = []
+    bad.append(ssz[:83])                                          # shorter than the fixed part
+    b = bytearray(ssz); b[80:84] = (85).to_bytes(4, "little"); bad.append(bytes(b))      # body offset != 84
+    b = bytearray(ssz); b[84 + 208:84 + 212] = (1 << 30).to_bytes(4, "little"); bad.append(bytes(b))  # attestations offset past end
+    b = bytearray(ssz); b[-1:] = b""; bad.append(bytes(b))        # kzg commitments no longer a multiple of 48
+    return bad
+
+
+def test_oracle_rejects_malformed_blocks():
+    for b in _malformed():
+        assert O.beacon_block_root_deneb(b) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_block_root_matches_oracle(gpu, name):
+    from lighthouse_b200 import tree_hash
+    _, ssz = _block(name)
+    assert tree_hash.beacon_block_root_deneb(ssz, want_body_root=True) == O.beacon_block_root_deneb(ssz)
+
+
+@pytest.mark.gpu
+def test_gpu_block_batch_of_an_epoch_matches_oracle(gpu):
+    """32 blocks in one pass (BASELINE configs[3] shape): every root equals the oracle's, order preserved."""
+    from lighthouse_b200 import tree_hash
+    blocks = [synthetic.beacon_block_deneb(seed=100 + i, n_transactions=100 + 5 * i)[1] for i in range(32)]
+    roots, bodies = tree_hash.beacon_block_roots_deneb(blocks, want_body_roots=True)
+    want = [O.beacon_block_root_deneb(b) for b in blocks]
+    assert roots == [w[0] for w in want] and bodies == [w[1] for w in want]
+    assert tree_hash.beacon_block_roots_deneb(blocks[5:6]) == [want[5][0]]
+
+
+@pytest.mark.gpu
+def test_gpu_block_root_large_transaction(gpu):
+    from lighthouse_b200 import tree_hash
+    _, ssz = synthetic.beacon_block_deneb(seed=3, n_attestations=2, tx_sizes=[3_000_001, 17])
+    assert tree_hash.beacon_block_root_deneb(ssz) == O.beacon_block_root_deneb(ssz)[0]
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_malformed_blocks(gpu):
+    from lighthouse_b200 import tree_hash, Lhb200Error
+    from lighthouse_b200._ffi import EINVAL
+    for b in _malformed():
+        with pytest.raises(Lhb200Error) as e:
+            tree_hash.beacon_block_root_deneb(b)
+        assert e.value.code == EINVAL
