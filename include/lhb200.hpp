@@ -181,7 +181,27 @@ inline Hash256 beacon_state_root_deneb(const uint8_t* ssz, size_t len) {
     return out;
 }
 
+/// BeaconBlock::canonical_root (beacon_block.rs:158-160) for BeaconBlockDeneb SSZ bytes.
+inline Hash256 beacon_block_root_deneb(const uint8_t* ssz, size_t len, Hash256* body_root = nullptr) {
+    Hash256 out;
+    check(lhb200_beacon_block_root_deneb(ssz, len, out.data(), body_root ? body_root->data() : nullptr),
+          "lhb200_beacon_block_root_deneb");
+    return out;
+}
+
 }  // namespace tree_hash
+
+namespace swap_or_not_shuffle {
+/// shuffle_list(input, rounds, seed, forwards) -> Option<Vec<usize>> (shuffle_list.rs:79): empty vector = None.
+inline std::vector<uint64_t> shuffle_list(const std::vector<uint64_t>& input, uint8_t rounds, const Hash256& seed,
+                                          bool forwards) {
+    std::vector<uint64_t> out(input.size());
+    const int32_t rc = lhb200_shuffle_list(input.data(), input.size(), rounds, seed.data(), forwards ? 1 : 0, out.data());
+    if (rc == LHB200_EINVAL) return {};
+    check(rc, "lhb200_shuffle_list");
+    return out;
+}
+}  // namespace swap_or_not_shuffle
 
 namespace merkle_proof {
 
