@@ -143,6 +143,18 @@ inline bool eth_fast_aggregate_verify(const AggregateSignature& sig, const Hash2
     return fast_aggregate_verify(sig, msg, pks);
 }
 
+/// ParallelSignatureSets (state_processing/src/per_block_processing/block_signature_verifier.rs:84-96,392-418):
+/// accumulate the sets of 1..N blocks, verify them with one batch call.
+class ParallelSignatureSets {
+  public:
+    void push(SignatureSet set) { sets_.push_back(std::move(set)); }
+    size_t size() const { return sets_.size(); }
+    bool verify() const { return verify_signature_sets(sets_.begin(), sets_.end()); }
+
+  private:
+    std::vector<SignatureSet> sets_;
+};
+
 }  // namespace bls
 
 namespace tree_hash {

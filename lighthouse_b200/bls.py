@@ -268,6 +268,27 @@ def verify_signature_sets(sets, rands=None) -> bool:
     return verify_signature_sets_raw(sigs, msgs, pks, offs, rands)
 
 
+class ParallelSignatureSets:
+    """state_processing::per_block_processing::block_signature_verifier::ParallelSignatureSets
+    (block_signature_verifier.rs:84-96, :392-418): the sets of 1..N blocks are accumulated, then verified by ONE
+    verify_signature_sets call (what BlockSignatureVerifier::verify and the chain-segment import do)."""
+
+    def __init__(self, sets=None):
+        self.sets = list(sets) if sets else []
+
+    def push(self, signature_set: SignatureSet):
+        self.sets.append(signature_set)
+
+    def extend(self, sets):
+        self.sets.extend(sets)
+
+    def __len__(self):
+        return len(self.sets)
+
+    def verify(self) -> bool:
+        return verify_signature_sets(self.sets)
+
+
 class PubkeyTable:
     """Device-resident validator pubkey table (mirror of ValidatorPubkeyCache, validator_pubkey_cache.rs)."""
 

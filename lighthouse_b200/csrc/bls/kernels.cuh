@@ -195,6 +195,25 @@ __global__ void __launch_bounds__(MILLER_BLOCK) k_miller(const G1Proj3* __restri
     }
 }
 
+// Group g = sets [g*k, (g+1)*k): one thread runs their Miller loops with shared squarings; out_f[g] = the product.
+// The host picks k = ceil(n / resident threads) so that every resident thread gets one group (no partial last wave).
+__global__ void __launch_bounds__(MILLER_BLOCK) k_miller_multi(const G1Proj3* __restrict__ P, const G2Affine* __restrict__ H,
+                                                             const uint8_t* __restrict__ status, uint32_t n, uint32_t k,
+                                                             uint32_t n_groups, Fp12* __restrict__ out_f) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+        uint32_t idx[MILLER_KMAX];
+        int m = 0;
+        for (uint32_t j = 0; j < k; j++) {
+            const uint32_t i = g * k + j;
+            if (i < n && status[i] == SET_OK && !H[i].inf) idx[m++] = i;
+        }
+        Fp12 f;
+        if (m == 0) fp12_set_one(f);
+        else miller_loop_multi(f, P, H, idx, m);
+        out_f[g] = f;
+    }
+}
+
 // out[t] = prod in[t*chunk .. min(n,(t+1)*chunk))
 __global__ void __launch_bounds__(BLS_BLOCK) k_fp12_reduce(const Fp12* __restrict__ in, uint32_t n, uint32_t chunk,
                                                             Fp12* __restrict__ out) {

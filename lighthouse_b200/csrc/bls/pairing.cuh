@@ -134,6 +134,35 @@ LHB_HD LHB_NOINLINE void miller_loop(Fp12& f, const G1Proj3& P, const G2Affine& 
     fp12_conj(f, f);
 }
 
+// Multi-pairing Miller loop: prod_j f_{|x|,Q_j}(P_j) for m <= MILLER_KMAX pairs with ONE Fp12 squaring per bit shared by
+// all of them ((prod f_j)^2 prod l_j == prod (f_j^2 l_j) exactly in Fp12) — the shape of blst's miller_loop_n behind
+// verify_multiple_aggregate_signatures (crypto/bls/src/impls/blst.rs:114-118).  P and Q are read in place.
+constexpr int MILLER_KMAX = 4;
+LHB_HD LHB_NOINLINE void miller_loop_multi(Fp12& f, const G1Proj3* P, const G2Affine* Q, const uint32_t* idx, int m) {
+    G2Jac T[MILLER_KMAX];
+    for (int j = 0; j < m; j++) jac_from_affine(T[j], Q[idx[j]]);
+    Fp2 c0, c1, c4;
+    for (int i = 62; i >= 0; i--) {
+        if (i != 62) fp12_sqr(f, f);
+        for (int j = 0; j < m; j++) {
+            miller_dbl_step(T[j], c0, c1, c4, P[idx[j]]);
+            if (i == 62 && j == 0) {  // f = 1: f^2 * l = l
+                fp6_set_zero(f.c0); fp6_set_zero(f.c1);
+                f.c0.c0 = c0; f.c0.c1 = c1; f.c1.c1 = c4;
+            } else {
+                fp12_mul_by_014(f, f, c0, c1, c4);
+            }
+        }
+        if ((BLS_X_ABS >> i) & 1) {
+            for (int j = 0; j < m; j++) {
+                miller_add_step(T[j], c0, c1, c4, Q[idx[j]], P[idx[j]]);
+                fp12_mul_by_014(f, f, c0, c1, c4);
+            }
+        }
+    }
+    fp12_conj(f, f);
+}
+
 // f^|x| for f in the cyclotomic subgroup
 LHB_HD LHB_NOINLINE void fp12_cyc_pow_x_abs(Fp12& r, const Fp12& a) {
     Fp12 acc = a;

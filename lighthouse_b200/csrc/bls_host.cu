@@ -351,12 +351,25 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller reads the status bytes k_sig_prepare may set
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
-    k_miller<<<cdiv((uint64_t)grid * BLS_BLOCK, MILLER_BLOCK), MILLER_BLOCK, 0, s>>>(b->d_p, b->d_h, b->d_status, n, b->d_f);
+    // Sets per thread: k = ceil(n / resident threads) (<= MILLER_KMAX) share their Fp12 squarings in one thread, so a
+    // 100 k batch is ONE wave of 3-set groups instead of three waves of single Miller loops.  LHB_MILLER_K overrides.
+    static const int miller_occ = [] {
+        int v = 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_miller_multi, MILLER_BLOCK, 0);
+        return std::max(v, 1);
+    }();
+    static const int miller_k_env = [] { const char* e = getenv("LHB_MILLER_K"); return e ? atoi(e) : 0; }();
+    const uint32_t resident = (uint32_t)(n_sm * miller_occ) * MILLER_BLOCK;
+    uint32_t mk = miller_k_env > 0 ? (uint32_t)miller_k_env : cdiv(n, resident);
+    mk = std::min<uint32_t>(std::max<uint32_t>(mk, 1), MILLER_KMAX);
+    const uint32_t n_groups = cdiv(n, mk);
+    k_miller_multi<<<std::min<uint32_t>(cdiv(n_groups, MILLER_BLOCK), (uint32_t)(n_sm * miller_occ)), MILLER_BLOCK, 0, s>>>(
+        b->d_p, b->d_h, b->d_status, n, mk, n_groups, b->d_f);
     LHB_CUDA(cudaEventRecord(b->e_k1, s));
     launches += 3;
     const Fp12* cur = b->d_f;
     {
-        uint32_t m = n;
+        uint32_t m = n_groups;
         int flip = 0;
         while (m > 1) {
             const uint32_t mo = cdiv(m, REDUCE_CHUNK);

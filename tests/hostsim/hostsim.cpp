@@ -128,6 +128,23 @@ EXPORT int hs_pairing(const uint8_t* p96, const uint8_t* q96, int do_final, int 
     fp12_out(out576, f);
     return 0;
 }
+// m pairs (P_j uncompressed G1, Q_j compressed G2): out_multi = miller_loop_multi, out_prod = product of single loops
+EXPORT int hs_miller_multi(const uint8_t* p96, const uint8_t* q96, int m, uint8_t* out_multi, uint8_t* out_prod) {
+    G1Proj3 P[MILLER_KMAX]; G2Affine Q[MILLER_KMAX]; uint32_t idx[MILLER_KMAX];
+    if (m < 1 || m > MILLER_KMAX) return -2;
+    for (int j = 0; j < m; j++) {
+        G1Affine p;
+        if (g1_from_uncompressed(p, p96 + 96 * j) != DEC_OK || g2_decompress(Q[j], q96 + 96 * j) != DEC_OK) return -1;
+        G1Jac jj; jac_from_affine(jj, p); jac_dbl(jj, jj); g1proj3_from_jac(P[j], jj);
+        idx[j] = (uint32_t)(m - 1 - j);  // permuted on purpose: the index list need not be sorted
+    }
+    Fp12 f, g, t;
+    miller_loop_multi(f, P, Q, idx, m);
+    miller_loop(g, P[0], Q[0]);
+    for (int j = 1; j < m; j++) { miller_loop(t, P[j], Q[j]); fp12_mul(g, g, t); }
+    fp12_out(out_multi, f); fp12_out(out_prod, g);
+    return 0;
+}
 // full single verification e(pk, H(m)) * e(-g1, sig) == 1
 EXPORT int hs_verify(const uint8_t* pk96, const uint8_t* msg32, const uint8_t* sig96) {
     G1Affine pk, g1; G2Affine sig, h;

@@ -64,6 +64,14 @@ def test_deposit_vectors_golden(bls):
     bad[7] = bls.SignatureSet.single_pubkey(sets[7].signature, sets[7].signing_keys[0], bytes(32))
     assert not bls.verify_signature_sets(bad)
     assert not bad[7].verify()
+    # ParallelSignatureSets (block_signature_verifier.rs:84-96,392-418): accumulate, then one batch verify
+    acc = bls.ParallelSignatureSets()
+    assert not acc.verify()                       # nothing included: verify_signature_sets(empty) is false
+    for st in sets:
+        acc.push(st)
+    assert len(acc) == 22 and acc.verify()
+    acc.push(bad[7])
+    assert not acc.verify()
 
 
 def test_gt_value_matches_oracle(bls):
