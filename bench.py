@@ -171,8 +171,9 @@ def run_ours(args):
     vp = lambda t: C.c_void_p(t.data_ptr())
 
     def bls_e2e_step():
-        _ffi.check(_ffi.lib.lhb200_bls_batch_upload(batch._h, vp(h_sigs), vp(h_msgs), vp(h_pks), vp(h_offs),
-                                                    vp(h_rands), N_SETS), "upload")
+        # streamed upload: key chunks cross the host link while k_sig_prepare / k_hash_to_g2 already run
+        _ffi.check(_ffi.lib.lhb200_bls_batch_upload_async(batch._h, vp(h_sigs), vp(h_msgs), vp(h_pks), vp(h_offs),
+                                                          vp(h_rands), N_SETS, sp), "upload_async")
         batch.enqueue(sp)
         return batch.result(sp)
 

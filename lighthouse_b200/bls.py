@@ -332,6 +332,18 @@ class Batch:
         check(lib.lhb200_bls_batch_upload(self._h, ps, pm, pp, offs.ctypes.data, None if r is None else r.ctypes.data,
                                           self.n), "lhb200_bls_batch_upload")
 
+    def upload_async(self, sigs, msgs, pks, offsets, rands=None, stream=None):
+        """Streamed upload (lhb200_bls_batch_upload_async): key chunks overlap the kernels of the following enqueue().
+        The buffers are kept alive on the object until the next upload."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint32)
+        self.n = len(offs) - 1
+        r = None if rands is None else np.ascontiguousarray(rands, dtype=np.uint64)
+        ps, k1 = buf(sigs); pm, k2 = buf(msgs); pp, k3 = buf(pks)
+        self._keep = (k1, k2, k3, offs, r)
+        check(lib.lhb200_bls_batch_upload_async(self._h, ps, pm, pp, offs.ctypes.data,
+                                                None if r is None else r.ctypes.data, self.n, stream),
+              "lhb200_bls_batch_upload_async")
+
     def upload_indexed(self, table, sigs, msgs, indices, offsets, rands=None):
         offs = np.ascontiguousarray(offsets, dtype=np.uint32)
         idx = np.ascontiguousarray(indices, dtype=np.uint32)

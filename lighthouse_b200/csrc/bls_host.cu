@@ -66,6 +66,15 @@ struct lhb200_bls_batch {
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller), for the roofline
     uint64_t launches_last = 0;
+    // streamed key upload (lhb200_bls_batch_upload_async): the key copy is cut into chunks of whole sets on its own
+    // stream; k_pk_aggregate runs per chunk as it lands while the signature / hash-to-curve kernels already compute
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t s_copy = nullptr;
+    cudaEvent_t e_small = nullptr, e_copy_free = nullptr;
+    cudaEvent_t e_chunk[MAX_CHUNKS] = {};
+    uint32_t chunk_lo[MAX_CHUNKS + 1] = {};  // set ranges
+    int n_chunks = 0;                        // 0: inputs already complete on the device
+    std::vector<uint64_t> rbuf;              // scalars drawn by the library (must outlive the async copy)
 };
 
 static void batch_free(lhb200_bls_batch* b) {
@@ -85,6 +94,11 @@ static void batch_free(lhb200_bls_batch* b) {
     if (b->e_join) cudaEventDestroy(b->e_join);
     if (b->e_k0) cudaEventDestroy(b->e_k0);
     if (b->e_k1) cudaEventDestroy(b->e_k1);
+    if (b->s_copy) cudaStreamDestroy(b->s_copy);
+    if (b->e_small) cudaEventDestroy(b->e_small);
+    if (b->e_copy_free) cudaEventDestroy(b->e_copy_free);
+    for (cudaEvent_t e : b->e_chunk)
+        if (e) cudaEventDestroy(e);
     delete b;
 }
 
@@ -131,10 +145,18 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
         (e = cudaEventCreateWithFlags(&b->e_sig, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreate(&b->e_k0)) != cudaSuccess || (e = cudaEventCreate(&b->e_k1)) != cudaSuccess) {
+        (e = cudaEventCreate(&b->e_k0)) != cudaSuccess || (e = cudaEventCreate(&b->e_k1)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_small, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_copy_free, cudaEventDisableTiming)) != cudaSuccess) {
         batch_free(b);
         return cuda_fail(e, "stream/event create");
     }
+    for (cudaEvent_t& ev : b->e_chunk)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
+            batch_free(b);
+            return cuda_fail(e, "event create");
+        }
     *out = b;
     return LHB200_OK;
 }
@@ -187,6 +209,66 @@ int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* sigs, const 
     LHB_CUDA(cudaMemcpyAsync(b->d_offsets, pk_offsets, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, s));
     LHB_CUDA(cudaMemcpyAsync(b->d_rands, rands, (size_t)n_sets * 8, cudaMemcpyHostToDevice, s));
     LHB_CUDA(cudaStreamSynchronize(s));  // rbuf / caller buffers may go away
+    b->n = n_sets;
+    b->n_chunks = 0;
+    b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = b->d_pks;
+    b->in_offsets = b->d_offsets; b->in_rands = b->d_rands;
+    b->table = nullptr;
+    return LHB200_OK;
+}
+
+// Streamed form of lhb200_bls_batch_upload: returns as soon as the copies are QUEUED.  The host buffers must stay
+// valid and unchanged until lhb200_bls_batch_result returns.  The small arrays go first; the keys (96 B x K, 1.2 GB at
+// 100 k x 128) follow in chunks of whole sets on a copy stream, and lhb200_bls_batch_verify_enqueue aggregates each
+// chunk as it lands while k_sig_prepare / k_hash_to_g2 already run — the host link hides behind the ALU-bound kernels.
+int32_t lhb200_bls_batch_upload_async(lhb200_bls_batch* b, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks,
+                                      const uint32_t* pk_offsets, const uint64_t* rands, uint32_t n_sets, void* stream) {
+    LHB_REQUIRE_READY();
+    if (!b || n_sets == 0 || n_sets > b->cap_sets || !sigs || !msgs || !pk_offsets) {
+        set_error("bls_batch_upload_async: bad arguments");
+        return LHB200_EINVAL;
+    }
+    const uint64_t n_keys = pk_offsets[n_sets];
+    if (n_keys > b->cap_keys || (n_keys && !pks)) { set_error("bls_batch_upload_async: key buffer too small"); return LHB200_EINVAL; }
+    for (uint32_t i = 0; i < n_sets; i++)
+        if (pk_offsets[i] > pk_offsets[i + 1]) { set_error("bls_batch_upload_async: offsets not monotone"); return LHB200_EINVAL; }
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+    if (!rands) {
+        b->rbuf.resize(n_sets);
+        gen_rands(b->rbuf.data(), n_sets);
+        rands = b->rbuf.data();
+    } else {
+        for (uint32_t i = 0; i < n_sets; i++)
+            if (rands[i] == 0) { set_error("bls_batch_upload_async: zero random scalar"); return LHB200_EINVAL; }
+    }
+    // the previous verify on this batch may still be reading d_pks: order the new copies behind it
+    LHB_CUDA(cudaEventRecord(b->e_copy_free, s));
+    LHB_CUDA(cudaStreamWaitEvent(b->s_copy, b->e_copy_free, 0));
+    LHB_CUDA(cudaMemcpyAsync(b->d_sigs, sigs, (size_t)n_sets * 96, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_msgs, msgs, (size_t)n_sets * 32, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_offsets, pk_offsets, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaMemcpyAsync(b->d_rands, rands, (size_t)n_sets * 8, cudaMemcpyHostToDevice, s));
+    LHB_CUDA(cudaEventRecord(b->e_small, s));
+    // chunks of whole sets, ~equal key counts
+    int nc = (int)std::min<uint64_t>(lhb200_bls_batch::MAX_CHUNKS, std::max<uint64_t>(1, n_keys * 96 / (32u << 20)));
+    nc = std::min<int>(nc, (int)n_sets);
+    b->chunk_lo[0] = 0;
+    uint32_t lo = 0;
+    for (int c = 0; c < nc; c++) {
+        uint32_t hi;
+        if (c == nc - 1) hi = n_sets;
+        else {
+            const uint64_t target = n_keys * (uint64_t)(c + 1) / nc;
+            hi = (uint32_t)(std::lower_bound(pk_offsets + lo, pk_offsets + n_sets + 1, target) - pk_offsets);
+            hi = std::min<uint32_t>(std::max<uint32_t>(hi, lo), n_sets);
+        }
+        const uint64_t k0 = pk_offsets[lo], k1 = pk_offsets[hi];
+        if (k1 > k0) LHB_CUDA(cudaMemcpyAsync(b->d_pks + k0 * 96, pks + k0 * 96, (k1 - k0) * 96, cudaMemcpyHostToDevice, b->s_copy));
+        LHB_CUDA(cudaEventRecord(b->e_chunk[c], b->s_copy));
+        b->chunk_lo[c + 1] = hi;
+        lo = hi;
+    }
+    b->n_chunks = nc;
     b->n = n_sets;
     b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = b->d_pks;
     b->in_offsets = b->d_offsets; b->in_rands = b->d_rands;
@@ -273,6 +355,7 @@ int32_t lhb200_bls_batch_upload_indexed(lhb200_bls_batch* b, const lhb200_pubkey
     b->n = n_sets;
     b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = nullptr;
     b->in_offsets = b->d_offsets; b->in_rands = b->d_rands; b->in_indices = b->d_indices;
+    b->n_chunks = 0;
     b->table = table;
     return LHB200_OK;
 }
@@ -293,6 +376,7 @@ int32_t lhb200_bls_batch_set_device_inputs(lhb200_bls_batch* b, const void* d_si
     b->in_pks = static_cast<const uint8_t*>(d_pks);
     b->in_offsets = static_cast<const uint32_t*>(d_offsets);
     b->in_rands = static_cast<const uint64_t*>(d_rands);
+    b->n_chunks = 0;
     b->table = nullptr;
     return LHB200_OK;
 }
@@ -313,6 +397,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         grid = cdiv(n, (uint64_t)per_thread * BLS_BLOCK);
     }
     uint64_t launches = 0;
+    if (b->n_chunks) LHB_CUDA(cudaStreamWaitEvent(s, b->e_small, 0));  // streamed upload: small arrays first
     LHB_CUDA(cudaMemsetAsync(b->d_status, 0, n, s));
     LHB_CUDA(cudaMemsetAsync(b->d_fail, 0, 4, s));
     LHB_CUDA(cudaMemsetAsync(b->d_ok, 0, 4, s));
@@ -346,7 +431,17 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     if (b->table)
         k_pk_aggregate_indexed<<<grid, BLS_BLOCK, 0, s>>>(b->table->d_keys, (uint32_t)b->table->len, b->in_indices,
                                                          b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
-    else
+    else if (b->n_chunks) {
+        for (int c = 0; c < b->n_chunks; c++) {  // aggregate each chunk of sets as soon as its keys have landed
+            const uint32_t lo = b->chunk_lo[c], cnt = b->chunk_lo[c + 1] - lo;
+            LHB_CUDA(cudaStreamWaitEvent(s, b->e_chunk[c], 0));
+            if (cnt == 0) continue;
+            k_pk_aggregate<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt,
+                                                                      b->d_p + lo, b->d_status + lo, b->d_fail);
+            launches++;
+        }
+        launches--;  // (the single-launch form below counts one)
+    } else
         k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller reads the status bytes k_sig_prepare may set
@@ -493,7 +588,7 @@ int32_t lhb200_verify_signature_sets(const uint8_t* sigs, const uint8_t* msgs, c
         if (rc0) { cached = nullptr; return rc0; }
     }
     lhb200_bls_batch* b = cached;
-    int32_t rc = lhb200_bls_batch_upload(b, sigs, msgs, pks, pk_offsets, rands, n_sets);
+    int32_t rc = lhb200_bls_batch_upload_async(b, sigs, msgs, pks, pk_offsets, rands, n_sets, c.stream);
     if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, c.stream);
     if (!rc) rc = lhb200_bls_batch_result(b, c.stream, ok, set_status);
     cudaStreamSynchronize(b->s2);

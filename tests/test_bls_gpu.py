@@ -336,6 +336,34 @@ def test_full_size_batch_properties(bls):
     b.destroy(); table.destroy()
 
 
+def test_streamed_upload_matches_blocking_upload(bls):
+    """lhb200_bls_batch_upload_async (key chunks overlapped with the kernels) gives the verdict of the blocking upload:
+    valid batch, a wrong key in the LAST chunk, a wrong key in the first, a set without keys; and the one-shot
+    lhb200_verify_signature_sets (which uses the streamed path) agrees."""
+    from lighthouse_b200.synthetic import attestation_batch
+    n, k = 6000, 128                                    # 73.7 MB of keys -> 2 chunks
+    ab = attestation_batch(n, keys_per_set=k, n_validators=4096, seed=0xA51C)
+    b = bls.Batch(n, n * k)
+
+    def both(sigs, msgs, pks, offs):
+        b.upload(sigs, msgs, pks, offs); b.enqueue(); r0 = b.result()
+        b.upload_async(sigs, msgs, pks, offs); b.enqueue(); r1 = b.result()
+        assert r0 == r1
+        return r1
+
+    assert both(ab.sigs, ab.msgs, ab.pks, ab.offsets) is True
+    assert bls.verify_signature_sets_raw(ab.sigs, ab.msgs, ab.pks, ab.offsets) is True
+    for victim in (n * k - 1, 5):
+        pks = bytearray(ab.pks)
+        other = (victim + 1000) % (n * k)
+        pks[96 * victim:96 * victim + 96] = ab.pks[96 * other:96 * other + 96]
+        if pks != bytearray(ab.pks):
+            assert both(ab.sigs, ab.msgs, bytes(pks), ab.offsets) is False
+    offs = ab.offsets.copy(); offs[n - 1] = offs[n]      # set n-2 swallows the keys of n-1, which has none
+    assert both(ab.sigs, ab.msgs, ab.pks, offs) is False
+    b.destroy()
+
+
 def test_block_signature_batch_shape(bls):
     """BASELINE configs[3] shape at reduced scale: the sets BlockSignatureVerifier::include_all_signatures collects
     for consecutive blocks (block_signature_verifier.rs:141-393) — 1-key sets (proposal, randao, exits,
