@@ -168,9 +168,9 @@ LHB200_API int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* s
 LHB200_API int32_t lhb200_bls_batch_set_device_inputs(lhb200_bls_batch* b, const void* d_sigs, const void* d_msgs,
                                                       const void* d_pks, const void* d_offsets, const void* d_rands,
                                                       uint32_t n_sets);
-/* Streamed upload: returns once the copies are queued on `stream` (small arrays) and on the batch's copy stream (keys,
- * in chunks of whole sets).  The host buffers must stay valid and unchanged until lhb200_bls_batch_result returns.
- * verify_enqueue then aggregates each key chunk as it lands while the signature and hash-to-curve kernels already run,
+/* Streamed upload: queues the small arrays on `stream` and binds the host key buffer; the host buffers must stay valid
+ * and unchanged until lhb200_bls_batch_result returns.  verify_enqueue copies the keys in chunks of whole sets on
+ * high-priority streams and aggregates each chunk as it lands while the signature and hash-to-curve kernels already run,
  * so the 1.2 GB of keys of a 100 k x 128 batch cross the host link behind the ALU-bound kernels (SURVEY.md §8d (ii):
  * "H2D must be double-buffered against compute").  lhb200_verify_signature_sets uses this path. */
 LHB200_API int32_t lhb200_bls_batch_upload_async(lhb200_bls_batch* b, const uint8_t* sigs, const uint8_t* msgs,

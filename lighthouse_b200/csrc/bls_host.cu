@@ -69,10 +69,14 @@ struct lhb200_bls_batch {
     // streamed key upload (lhb200_bls_batch_upload_async): the key copy is cut into chunks of whole sets on its own
     // stream; k_pk_aggregate runs per chunk as it lands while the signature / hash-to-curve kernels already compute
     static constexpr int MAX_CHUNKS = 16;
-    cudaStream_t s_copy = nullptr;
+    static constexpr int N_PK_STREAMS = 4;
+    cudaStream_t s_pk[N_PK_STREAMS] = {};    // high priority: chunk c is copied AND aggregated on s_pk[c % 4]
+    cudaEvent_t e_pk[N_PK_STREAMS] = {};
     cudaEvent_t e_small = nullptr, e_copy_free = nullptr;
     cudaEvent_t e_chunk[MAX_CHUNKS] = {};
     uint32_t chunk_lo[MAX_CHUNKS + 1] = {};  // set ranges
+    uint64_t chunk_key[MAX_CHUNKS + 1] = {}; // key ranges
+    const uint8_t* h_pks = nullptr;          // caller's host keys (valid until result)
     int n_chunks = 0;                        // 0: inputs already complete on the device
     std::vector<uint64_t> rbuf;              // scalars drawn by the library (must outlive the async copy)
 };
@@ -94,7 +98,10 @@ static void batch_free(lhb200_bls_batch* b) {
     if (b->e_join) cudaEventDestroy(b->e_join);
     if (b->e_k0) cudaEventDestroy(b->e_k0);
     if (b->e_k1) cudaEventDestroy(b->e_k1);
-    if (b->s_copy) cudaStreamDestroy(b->s_copy);
+    for (cudaStream_t st : b->s_pk)
+        if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : b->e_pk)
+        if (e) cudaEventDestroy(e);
     if (b->e_small) cudaEventDestroy(b->e_small);
     if (b->e_copy_free) cudaEventDestroy(b->e_copy_free);
     for (cudaEvent_t e : b->e_chunk)
@@ -146,7 +153,6 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
         (e = cudaEventCreateWithFlags(&b->e_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&b->e_k0)) != cudaSuccess || (e = cudaEventCreate(&b->e_k1)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_small, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_copy_free, cudaEventDisableTiming)) != cudaSuccess) {
         batch_free(b);
@@ -156,6 +162,14 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
             batch_free(b);
             return cuda_fail(e, "event create");
+        }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the key chunks must not queue behind the 1563-CTA kernels
+    for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++)
+        if ((e = cudaStreamCreateWithPriority(&b->s_pk[j], cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&b->e_pk[j], cudaEventDisableTiming)) != cudaSuccess) {
+            batch_free(b);
+            return cuda_fail(e, "stream create");
         }
     *out = b;
     return LHB200_OK;
@@ -217,7 +231,8 @@ int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* sigs, const 
     return LHB200_OK;
 }
 
-// Streamed form of lhb200_bls_batch_upload: returns as soon as the copies are QUEUED.  The host buffers must stay
+// Streamed form of lhb200_bls_batch_upload: queues the small arrays and BINDS the host key buffer; the key chunks are
+// copied by lhb200_bls_batch_verify_enqueue, interleaved with their aggregation kernels.  The host buffers must stay
 // valid and unchanged until lhb200_bls_batch_result returns.  The small arrays go first; the keys (96 B x K, 1.2 GB at
 // 100 k x 128) follow in chunks of whole sets on a copy stream, and lhb200_bls_batch_verify_enqueue aggregates each
 // chunk as it lands while k_sig_prepare / k_hash_to_g2 already run — the host link hides behind the ALU-bound kernels.
@@ -243,7 +258,7 @@ int32_t lhb200_bls_batch_upload_async(lhb200_bls_batch* b, const uint8_t* sigs, 
     }
     // the previous verify on this batch may still be reading d_pks: order the new copies behind it
     LHB_CUDA(cudaEventRecord(b->e_copy_free, s));
-    LHB_CUDA(cudaStreamWaitEvent(b->s_copy, b->e_copy_free, 0));
+    for (cudaStream_t st : b->s_pk) LHB_CUDA(cudaStreamWaitEvent(st, b->e_copy_free, 0));
     LHB_CUDA(cudaMemcpyAsync(b->d_sigs, sigs, (size_t)n_sets * 96, cudaMemcpyHostToDevice, s));
     LHB_CUDA(cudaMemcpyAsync(b->d_msgs, msgs, (size_t)n_sets * 32, cudaMemcpyHostToDevice, s));
     LHB_CUDA(cudaMemcpyAsync(b->d_offsets, pk_offsets, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, s));
@@ -262,13 +277,13 @@ int32_t lhb200_bls_batch_upload_async(lhb200_bls_batch* b, const uint8_t* sigs, 
             hi = (uint32_t)(std::lower_bound(pk_offsets + lo, pk_offsets + n_sets + 1, target) - pk_offsets);
             hi = std::min<uint32_t>(std::max<uint32_t>(hi, lo), n_sets);
         }
-        const uint64_t k0 = pk_offsets[lo], k1 = pk_offsets[hi];
-        if (k1 > k0) LHB_CUDA(cudaMemcpyAsync(b->d_pks + k0 * 96, pks + k0 * 96, (k1 - k0) * 96, cudaMemcpyHostToDevice, b->s_copy));
-        LHB_CUDA(cudaEventRecord(b->e_chunk[c], b->s_copy));
+        b->chunk_key[c] = pk_offsets[lo];
+        b->chunk_key[c + 1] = pk_offsets[hi];
         b->chunk_lo[c + 1] = hi;
         lo = hi;
     }
     b->n_chunks = nc;
+    b->h_pks = pks;
     b->n = n_sets;
     b->in_sigs = b->d_sigs; b->in_msgs = b->d_msgs; b->in_pks = b->d_pks;
     b->in_offsets = b->d_offsets; b->in_rands = b->d_rands;
@@ -432,13 +447,22 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         k_pk_aggregate_indexed<<<grid, BLS_BLOCK, 0, s>>>(b->table->d_keys, (uint32_t)b->table->len, b->in_indices,
                                                          b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     else if (b->n_chunks) {
-        for (int c = 0; c < b->n_chunks; c++) {  // aggregate each chunk of sets as soon as its keys have landed
+        // aggregate each chunk of sets on the (high-priority) stream that copies it, as soon as its keys have landed
+        for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++) LHB_CUDA(cudaStreamWaitEvent(b->s_pk[j], b->e_fork, 0));
+        for (int c = 0; c < b->n_chunks; c++) {
             const uint32_t lo = b->chunk_lo[c], cnt = b->chunk_lo[c + 1] - lo;
-            LHB_CUDA(cudaStreamWaitEvent(s, b->e_chunk[c], 0));
+            const uint64_t k0 = b->chunk_key[c], k1 = b->chunk_key[c + 1];
+            if (k1 > k0)
+                LHB_CUDA(cudaMemcpyAsync(b->d_pks + k0 * 96, b->h_pks + k0 * 96, (k1 - k0) * 96, cudaMemcpyHostToDevice,
+                                         b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]));
             if (cnt == 0) continue;
-            k_pk_aggregate<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt,
-                                                                      b->d_p + lo, b->d_status + lo, b->d_fail);
+            k_pk_aggregate<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]>>>(
+                b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
             launches++;
+        }
+        for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++) {
+            LHB_CUDA(cudaEventRecord(b->e_pk[j], b->s_pk[j]));
+            LHB_CUDA(cudaStreamWaitEvent(s, b->e_pk[j], 0));
         }
         launches--;  // (the single-launch form below counts one)
     } else
