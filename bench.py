@@ -324,8 +324,8 @@ def run_ours(args):
                             "h2d_bytes_per_step": int(h2d_idx), "d2h_bytes_per_step": 1, "ms_per_step": bls_e2e_idx_ms,
                             "note": "keys referenced by u32 index into the device-resident pubkey table (ValidatorPubkeyCache mirror)"},
             "gpu_launches": int(bls_launches),
-            "roofline": {"kernel": "k_miller", "bound": "hbm", "achieved": bls_ach, "peak": peak, "unit": "GB/s",
-                         "frac": (bls_ach / peak) if bls_ach else None, "traffic": profile_traffic("k_miller"),
+            "roofline": {"kernel": "k_miller_multi", "bound": "hbm", "achieved": bls_ach, "peak": peak, "unit": "GB/s",
+                         "frac": (bls_ach / peak) if bls_ach else None, "traffic": profile_traffic("k_miller_multi"),
                          "peak_source": peak_src, "kernel_ms": dom_bls,
                          "note": "integer-ALU bound by construction (SURVEY §8d): see alu_frac in DESIGN.md / profiles/"},
             "alu": {"pipe": "fmaheavy (IMAD.WIDE.U32: 1 warp-instruction / cycle / SM, measured, DESIGN.md §2.2)",
