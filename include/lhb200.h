@@ -91,6 +91,15 @@ LHB200_API int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t*
  * (beacon_state.rs:2459-2481): bytes [ssz_offset, ssz_offset+len) of the SSZ encoding are replaced; the next
  * lhb200_state_root re-hashes everything on the device (warm path = patch + full re-hash). */
 LHB200_API int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t* data, uint64_t len);
+/* Warm path (the reference's steady state: BeaconState::update_tree_hash_cache re-hashes only dirty
+ * paths, beacon_state.rs:2031-2038,2459-2481).  After this call the handle keeps every level of its big lists
+ * (validators, balances, inactivity scores, participation x2, randao mixes, block/state roots, slashings) resident:
+ * lhb200_state_patch marks the leaves it touches and lhb200_state_root / _enqueue re-hash only the paths above them
+ * plus the tail program.  The first root after enabling is cold (it builds the levels); patches to other lists, or
+ * more than 65 536 dirty leaves, fall back to a cold root.  Unsharded handles only.
+ * lhb200_state_last_root_hashes: hash32_concat units the last root actually computed. */
+LHB200_API int32_t lhb200_state_enable_incremental(lhb200_state* st);
+LHB200_API uint64_t lhb200_state_last_root_hashes(const lhb200_state* st);
 /* Same as lhb200_state_root but only enqueues; the root lands in device memory (returned pointer valid until
  * the next call on this handle).  Used by bench.py to time kernels with CUDA events. */
 LHB200_API int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root);

@@ -115,3 +115,5 @@ _sig("lhb200_shuffle_list", C.c_int32, vp, C.c_uint64, C.c_uint8, vp, C.c_int32,
 _sig("lhb200_beacon_block_root_deneb", C.c_int32, vp, C.c_uint64, vp, vp)
 _sig("lhb200_beacon_block_roots_deneb", C.c_int32, vp, vp, C.c_uint32, vp, vp)
 _sig("lhb200_bls_batch_upload_async", C.c_int32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp)
+_sig("lhb200_state_enable_incremental", C.c_int32, vp)
+_sig("lhb200_state_last_root_hashes", C.c_uint64, vp)

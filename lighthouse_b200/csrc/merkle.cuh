@@ -55,25 +55,9 @@ __device__ __forceinline__ void le64_words(const uint8_t* p, uint32_t& w0, uint3
     w1 = be_word(p + 4);
 }
 
-__global__ void __launch_bounds__(VAL_PER_CTA) k_validator_roots(const uint8_t* __restrict__ ssz, uint64_t n,
-                                                                 uint8_t* __restrict__ out) {
-    __shared__ __align__(16) uint8_t sm[VAL_PER_CTA * VAL_SSZ];
-    const uint64_t first = (uint64_t)blockIdx.x * VAL_PER_CTA;
-    const uint64_t cnt = min((uint64_t)VAL_PER_CTA, n - first);
-    const uint32_t nbytes = (uint32_t)cnt * VAL_SSZ;
-    const uint8_t* src = ssz + first * VAL_SSZ;
-    {
-        const uint4* s4 = reinterpret_cast<const uint4*>(src);
-        uint4* d4 = reinterpret_cast<uint4*>(sm);
-        const uint32_t nvec = nbytes / 16;
-        for (uint32_t i = threadIdx.x; i < nvec; i += VAL_PER_CTA) d4[i] = __ldg(s4 + i);
-        for (uint32_t i = nvec * 16 + threadIdx.x; i < nbytes; i += VAL_PER_CTA) sm[i] = src[i];
-    }
-    __syncthreads();
-    if (threadIdx.x >= cnt) return;
-    const uint8_t* v = sm + threadIdx.x * VAL_SSZ;
-
-    uint32_t a[8], b[8], h01[8], h23[8];
+// hash_tree_root of one 121-byte Validator record (validator.rs:25-35): 8 leaves, 8 hashes.  `v`: shared or global.
+__device__ __forceinline__ void validator_root_words(const uint8_t* v, uint32_t h01[8]) {
+    uint32_t a[8], b[8], h23[8];
     // leaf0 = H(pubkey[0:32] || pubkey[32:48] || 0^16)
 #pragma unroll
     for (int i = 0; i < 8; i++) a[i] = be_word(v + 4 * i);
@@ -104,6 +88,28 @@ __global__ void __launch_bounds__(VAL_PER_CTA) k_validator_roots(const uint8_t* 
     hash_pair(a, b, a);      // h67
     hash_pair(h23, a, h23);  // h4567
     hash_pair(h01, h23, h01);
+}
+
+__global__ void __launch_bounds__(VAL_PER_CTA) k_validator_roots(const uint8_t* __restrict__ ssz, uint64_t n,
+                                                                 uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t sm[VAL_PER_CTA * VAL_SSZ];
+    const uint64_t first = (uint64_t)blockIdx.x * VAL_PER_CTA;
+    const uint64_t cnt = min((uint64_t)VAL_PER_CTA, n - first);
+    const uint32_t nbytes = (uint32_t)cnt * VAL_SSZ;
+    const uint8_t* src = ssz + first * VAL_SSZ;
+    {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(sm);
+        const uint32_t nvec = nbytes / 16;
+        for (uint32_t i = threadIdx.x; i < nvec; i += VAL_PER_CTA) d4[i] = __ldg(s4 + i);
+        for (uint32_t i = nvec * 16 + threadIdx.x; i < nbytes; i += VAL_PER_CTA) sm[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x >= cnt) return;
+    const uint8_t* v = sm + threadIdx.x * VAL_SSZ;
+
+    uint32_t h01[8];
+    validator_root_words(v, h01);
     store_chunk(out + 32 * (first + threadIdx.x), h01);
 }
 
@@ -301,6 +307,70 @@ __global__ void __launch_bounds__(PROG_THREADS) k_hash_ops(const HashOp* __restr
     load_operand(op.b, r);
     hash_pair(l, r, l);
     store_chunk(reinterpret_cast<uint8_t*>(op.dst), l);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident Merkle trees for the warm path (the reference's steady state is the tree-hash
+// cache: BeaconState::update_tree_hash_cache re-hashes only dirty paths, beacon_state.rs:2031-2038,2459-2481).
+// Every big list of a resident state keeps ALL its levels; after lhb200_state_patch marks leaves dirty, one CTA per
+// tree re-hashes just the paths above them, level by level.
+struct TreeDev {
+    const uint8_t* src;     // kind 0: the staged 121-byte validator records (leaf roots are recomputed from them)
+    uint8_t* lvl[41];       // lvl[0] = leaf chunks, lvl[top] = one node
+    uint64_t n_leaves;
+    uint32_t top;           // ceil_log2(n_leaves)
+    uint32_t kind;          // 0: validators, 1: chunks are the data
+    uint8_t* top_dst;       // where the plan's tail program reads this list's data root
+    const uint32_t* dirty;  // sorted, unique leaf indices
+    uint32_t n_dirty;
+    uint32_t pad_;
+};
+constexpr int TREE_THREADS = 1024;
+
+// out[i] = H(in[2i], in[2i+1] or ZERO[zlevel]) for i < ceil(n_in / 2)   (full build of one level)
+__global__ void __launch_bounds__(256) k_tree_level(const uint8_t* __restrict__ in, uint64_t n_in,
+                                                    uint8_t* __restrict__ out, uint32_t zlevel) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * i >= n_in) return;
+    uint32_t l[8], r[8];
+    load_chunk(in + 64 * i, l);
+    const bool rv = 2 * i + 1 < n_in;
+    if (rv) load_chunk(in + 64 * i + 32, r);
+    fold(l, r, rv, zlevel);
+    store_chunk(out + 32 * i, l);
+}
+
+__global__ void __launch_bounds__(TREE_THREADS) k_tree_update(const TreeDev* __restrict__ trees) {
+    const TreeDev& t = trees[blockIdx.x];
+    const uint32_t nd = t.n_dirty;
+    if (nd == 0) return;
+    const uint32_t tid = threadIdx.x;
+    if (t.kind == 0) {
+        for (uint32_t j = tid; j < nd; j += TREE_THREADS) {
+            const uint32_t i = t.dirty[j];
+            uint32_t w[8];
+            validator_root_words(t.src + (uint64_t)VAL_SSZ * i, w);
+            store_chunk(t.lvl[0] + 32ull * i, w);
+        }
+        __syncthreads();
+    }
+    uint64_t n_l = t.n_leaves;
+    for (uint32_t l = 0; l < t.top; l++) {
+        for (uint32_t j = tid; j < nd; j += TREE_THREADS) {
+            const uint32_t p = t.dirty[j] >> (l + 1);
+            if (j == 0 || (t.dirty[j - 1] >> (l + 1)) != p) {   // first dirty leaf under this parent does the hash
+                uint32_t a[8], b[8];
+                load_operand(reinterpret_cast<uint64_t>(t.lvl[l] + 64ull * p), a);   // plain loads: written this launch
+                const bool rv = 2ull * p + 1 < n_l;
+                if (rv) load_operand(reinterpret_cast<uint64_t>(t.lvl[l] + 64ull * p + 32), b);
+                fold(a, b, rv, l);
+                store_chunk(t.lvl[l + 1] + 32ull * p, a);
+                if (l + 1 == t.top) store_chunk(t.top_dst, a);
+            }
+        }
+        __syncthreads();
+        n_l = (n_l + 1) >> 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

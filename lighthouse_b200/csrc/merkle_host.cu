@@ -65,6 +65,11 @@ struct Plan {
     ByteItem* d_items = nullptr;
     std::vector<int32_t> h_waves;                      // host copy of the wave table (wide waves get their own launch)
     uint64_t forced_dst = 0;                           // destination of the next op_hash (0 = allocate)
+    // lists big enough for reduce passes: where their leaf chunks live and where the tail program reads their data
+    // root (for the warm path, lhb200_state_enable_incremental)
+    struct TreeSpec { const uint8_t* chunks; uint64_t n_chunks; uint64_t top_addr; const uint8_t* src; int kind;
+                      uint64_t src_off, src_bytes; uint32_t item_bytes; };
+    std::vector<TreeSpec> trees;
     uint64_t hash_units = 0;
     // SSZ provenance of literal chunks (for lhb200_state_patch): chunk index <- n bytes at SSZ offset src_off
     struct LitSrc { uint32_t lit_index; uint32_t n; uint64_t src_off; };
@@ -166,6 +171,7 @@ struct Plan {
         uint32_t level = 0;
         const uint8_t* in = d_in;
         size_t p = 0;
+        const uint64_t hash_units_n0 = n;  // leaf count of this list
         while (n > 1 && level < depth) {
             uint32_t tl = std::min<uint32_t>(MAX_TILE_LOG, depth - level);
             tl = std::min<uint32_t>(tl, ceil_log2(n));  // do not fold past the single-root level here
@@ -183,6 +189,7 @@ struct Plan {
             in = out;
         }
         uint64_t r = reinterpret_cast<uint64_t>(in);
+        trees.push_back({d_in, hash_units_n0, r, nullptr, 1, ~0ull, 0, 32});
         for (uint32_t l = level; l < depth; l++) r = op_hash(r, zero_op(l));
         return r;
     }
@@ -195,6 +202,7 @@ struct Plan {
     }
 };
 
+static int32_t plan_enqueue_tail(Plan& pl, cudaStream_t s);
 // Enqueue a finished plan on `s`.  Literals must already be in the arena.
 static int32_t plan_enqueue(Plan& pl, cudaStream_t s, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
     for (const LeafLaunch& L : pl.leaves) {
@@ -233,6 +241,10 @@ static int32_t plan_enqueue(Plan& pl, cudaStream_t s, cudaEvent_t e0 = nullptr, 
         k_byte_items<<<(unsigned)pl.items.size(), ITEM_THREADS, 0, s>>>(pl.d_items);
         count_launch();
     }
+    return plan_enqueue_tail(pl, s);
+}
+// The tail hash program only (zero ladders, length mix-ins, containers): all a warm root needs after the trees.
+static int32_t plan_enqueue_tail(Plan& pl, cudaStream_t s) {
     // narrow waves run back to back inside one CTA; a wide wave (block batches) gets the whole grid
     constexpr int WIDE_WAVE = 1024;
     for (int w = 0; w < pl.n_waves;) {
@@ -436,6 +448,15 @@ struct lhb200_state {
     lhb200::ShardCfg shard;
     std::vector<lhb200::ShardedList> sharded;
     std::vector<lhb200::StageCopy> copies;  // SSZ ranges resident in the arena (for lhb200_state_patch)
+    // warm path (lhb200_state_enable_incremental): full level arrays per big list + dirty leaves since the last root
+    struct Tree { lhb200::TreeDev dev; uint64_t src_off, src_bytes; uint32_t item_bytes; std::vector<uint32_t> dirty; };
+    bool incremental = false, need_full = false;
+    std::vector<Tree> trees;
+    uint8_t* d_levels = nullptr;
+    lhb200::TreeDev* d_trees = nullptr;
+    uint32_t* d_dirty = nullptr;
+    uint64_t last_root_hashes = 0;       // hash32_concat units of the last root (full or incremental)
+    static constexpr uint32_t DIRTY_CAP = 1u << 16;
 };
 
 namespace lhb200 {
@@ -484,7 +505,13 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
         if (!shard) {
             const uint8_t* src = place(src_off, n_items * item_bytes);
             const uint8_t* chunks = leaf_kind >= 0 ? p.leaf_kernel(leaf_kind, src, n_items) : src;
+            const size_t nt = p.trees.size();
             uint64_t r = p.merkle_list(chunks, n_chunks, limit_depth);
+            if (p.trees.size() > nt && leaf_kind <= 0) {   // warm-path provenance: validators (kind 0) or packed bytes
+                Plan::TreeSpec& t = p.trees.back();
+                t.src = src; t.kind = leaf_kind == 0 ? 0 : 1; t.src_off = src_off; t.src_bytes = n_items * item_bytes;
+                t.item_bytes = leaf_kind == 0 ? item_bytes : 32;
+            }
             return mix_len == UINT64_MAX ? r : p.mix_in_length(r, mix_len);
         }
         const uint32_t sub = d0 - lg_world;
@@ -511,8 +538,18 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
                         p.literal_bytes(s + O_FORK + 8, 8)});
     f[4] = p.container({p.literal_bytes(s + O_LBH, 8), p.literal_bytes(s + O_LBH + 8, 8), chunk(O_LBH + 16),
                         chunk(O_LBH + 48), chunk(O_LBH + 80)});
-    f[5] = p.merkle_list(place(O_BLOCK_ROOTS, 8192 * 32), 8192, 13);
-    f[6] = p.merkle_list(place(O_STATE_ROOTS, 8192 * 32), 8192, 13);
+    auto plain_vector = [&](uint32_t off, uint64_t nbytes, uint32_t depth) {   // fixed vectors of chunks / packed u64
+        const uint8_t* src = place(off, nbytes);
+        const size_t nt = p.trees.size();
+        uint64_t r = p.merkle_list(src, nbytes / 32, depth);
+        if (p.trees.size() > nt) {
+            Plan::TreeSpec& t = p.trees.back();
+            t.src = src; t.kind = 1; t.src_off = off; t.src_bytes = nbytes; t.item_bytes = 32;
+        }
+        return r;
+    };
+    f[5] = plain_vector(O_BLOCK_ROOTS, 8192 * 32, 13);
+    f[6] = plain_vector(O_STATE_ROOTS, 8192 * 32, 13);
     f[7] = p.mix_in_length(p.merkle_list(place(o_hist, n_hist * 32), n_hist, 24), n_hist);
     f[8] = p.container({chunk(O_ETH1_DATA), p.literal_bytes(s + O_ETH1_DATA + 32, 8), chunk(O_ETH1_DATA + 40)});
     f[9] = p.mix_in_length(p.merkle_list(p.leaf_kernel(2, place(o_votes, n_votes * 72), n_votes), n_votes, 11), n_votes);
@@ -520,7 +557,7 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
     f[11] = big_list(11, o_val, n_val, 121, 0, n_val, 40, n_val);
     f[12] = big_list(12, o_bal, n_bal, 8, -1, ceil_div(n_bal * 8, 32), 38, n_bal);
     f[13] = big_list(13, O_RANDAO, 65536, 32, -1, 65536, 16, UINT64_MAX);
-    f[14] = p.merkle_list(place(O_SLASHINGS, 8192 * 8), 2048, 11);
+    f[14] = plain_vector(O_SLASHINGS, 8192 * 8, 11);
     f[15] = big_list(15, o_pp, n_pp, 1, -1, ceil_div(n_pp, 32), 35, n_pp);
     f[16] = big_list(16, o_cp, n_cp, 1, -1, ceil_div(n_cp, 32), 35, n_cp);
     f[17] = p.literal_bytes(s + O_JUST, 1);
@@ -858,6 +895,17 @@ int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t*
         if (a < b) {
             LHB_CUDA(cudaMemcpyAsync(cp.dst + (a - cp.src_off), h + (a - lo), b - a, cudaMemcpyHostToDevice, c.stream));
             touched = true;
+            if (st->incremental && !st->need_full) {   // warm path: which leaves of which tree does this touch?
+                bool found = false;
+                for (lhb200_state::Tree& t : st->trees) {
+                    if (t.src_off != cp.src_off) continue;
+                    found = true;
+                    const uint64_t i0 = (a - t.src_off) / t.item_bytes, i1 = (b - 1 - t.src_off) / t.item_bytes;
+                    if (t.dirty.size() + (i1 - i0 + 1) > lhb200_state::DIRTY_CAP) { st->need_full = true; break; }
+                    for (uint64_t i = i0; i <= i1; i++) t.dirty.push_back((uint32_t)i);
+                }
+                if (!found) st->need_full = true;      // a list without a resident tree (votes, summaries, committees)
+            }
         }
     }
     Plan& pl = st->plan;
@@ -876,12 +924,119 @@ int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t*
     return LHB200_OK;
 }
 
+// (Re)build every level of every resident tree from its leaf chunks (which a cold root has just refreshed).
+static int32_t state_build_levels(lhb200_state* st, cudaStream_t s) {
+    for (lhb200_state::Tree& t : st->trees) {
+        uint64_t n = t.dev.n_leaves;
+        for (uint32_t l = 0; l < t.dev.top; l++) {
+            k_tree_level<<<(unsigned)ceil_div(ceil_div(n, 2), 256), 256, 0, s>>>(t.dev.lvl[l], n, t.dev.lvl[l + 1], l);
+            count_launch();
+            n = ceil_div(n, 2);
+        }
+        t.dirty.clear();
+    }
+    st->need_full = false;
+    LHB_CUDA(cudaGetLastError());
+    return LHB200_OK;
+}
+// Warm root: re-hash the paths above the dirty leaves (one CTA per tree), then the tail program.
+static int32_t state_incremental_enqueue(lhb200_state* st, cudaStream_t s) {
+    uint32_t total = 0;
+    for (lhb200_state::Tree& t : st->trees) {
+        std::sort(t.dirty.begin(), t.dirty.end());
+        t.dirty.erase(std::unique(t.dirty.begin(), t.dirty.end()), t.dirty.end());
+        total += (uint32_t)t.dirty.size();
+    }
+    uint64_t hashes = st->plan.ops.size();
+    if (total) {
+        const size_t tb = st->trees.size() * sizeof(TreeDev);
+        uint8_t* h = static_cast<uint8_t*>(pinned_scratch(tb + (size_t)total * 4 + 256));
+        if (!h) return LHB200_ENOMEM;
+        uint32_t* hd = reinterpret_cast<uint32_t*>(h + align_up(tb, 256));
+        uint32_t off = 0;
+        for (size_t k = 0; k < st->trees.size(); k++) {
+            lhb200_state::Tree& t = st->trees[k];
+            t.dev.dirty = st->d_dirty + off;
+            t.dev.n_dirty = (uint32_t)t.dirty.size();
+            if (!t.dirty.empty()) memcpy(hd + off, t.dirty.data(), t.dirty.size() * 4);
+            off += t.dev.n_dirty;
+            memcpy(h + k * sizeof(TreeDev), &t.dev, sizeof(TreeDev));
+            // hashes: distinct parents per level (upper bound: one path per dirty leaf) + 8 per dirty validator
+            uint64_t prev = ~0ull, cnt = 0;
+            for (uint32_t l = 1; l <= t.dev.top; l++) {
+                prev = ~0ull;
+                for (uint32_t d : t.dirty) { if ((uint64_t)(d >> l) != prev) { cnt++; prev = d >> l; } }
+            }
+            hashes += cnt + (t.dev.kind == 0 ? 8ull * t.dirty.size() : 0);
+            t.dirty.clear();
+        }
+        LHB_CUDA(cudaMemcpyAsync(st->d_trees, h, tb, cudaMemcpyHostToDevice, s));
+        LHB_CUDA(cudaMemcpyAsync(st->d_dirty, hd, (size_t)total * 4, cudaMemcpyHostToDevice, s));
+        k_tree_update<<<(unsigned)st->trees.size(), TREE_THREADS, 0, s>>>(st->d_trees);
+        count_launch();
+    }
+    st->last_root_hashes = hashes;
+    return plan_enqueue_tail(st->plan, s);
+}
+
+// Switch a resident (unsharded) state to the warm path: allocate and build the level arrays of its big lists
+// (validators, balances, inactivity scores, participation x2, randao mixes, block/state roots, slashings).
+// Afterwards lhb200_state_patch marks dirty leaves and lhb200_state_root re-hashes only the paths above them
+// (plus the tail program); patches outside those lists, or more than 65 536 dirty leaves, fall back to a cold root.
+int32_t lhb200_state_enable_incremental(lhb200_state* st) {
+    LHB_REQUIRE_READY();
+    if (!st) return LHB200_EINVAL;
+    if (st->shard.world != 1) { set_error("incremental roots need the whole state on this handle (world == 1)"); return LHB200_EINVAL; }
+    if (st->incremental) return LHB200_OK;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    size_t bytes = 0;
+    for (const Plan::TreeSpec& ts : st->plan.trees) {
+        if (ts.src_off == ~0ull) continue;
+        for (uint64_t n = ceil_div(ts.n_chunks, 2);; n = ceil_div(n, 2)) { bytes += align_up(n * 32, 256); if (n == 1) break; }
+    }
+    LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->d_levels), bytes + 256));
+    size_t off = 0;
+    for (const Plan::TreeSpec& ts : st->plan.trees) {
+        if (ts.src_off == ~0ull) continue;
+        lhb200_state::Tree t;
+        memset(&t.dev, 0, sizeof t.dev);
+        t.dev.src = ts.src;
+        t.dev.kind = (uint32_t)ts.kind;
+        t.dev.n_leaves = ts.n_chunks;
+        t.dev.top = ceil_log2(ts.n_chunks);
+        t.dev.top_dst = reinterpret_cast<uint8_t*>(ts.top_addr);
+        t.dev.lvl[0] = const_cast<uint8_t*>(ts.chunks);
+        uint64_t n = ts.n_chunks;
+        for (uint32_t l = 1; l <= t.dev.top; l++) {
+            n = ceil_div(n, 2);
+            t.dev.lvl[l] = st->d_levels + off;
+            off += align_up(n * 32, 256);
+        }
+        t.src_off = ts.src_off; t.src_bytes = ts.src_bytes; t.item_bytes = ts.item_bytes;
+        st->trees.push_back(t);
+    }
+    LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->d_trees), st->trees.size() * sizeof(TreeDev) + 256));
+    LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->d_dirty), (size_t)lhb200_state::DIRTY_CAP * 4 * st->trees.size()));
+    st->incremental = true;
+    st->need_full = true;   // the first root after enabling is cold and builds the levels
+    return LHB200_OK;
+}
+uint64_t lhb200_state_last_root_hashes(const lhb200_state* st) { return st ? st->last_root_hashes : 0; }
+
 int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d_root) {
     LHB_REQUIRE_READY();
     if (!st) return LHB200_EINVAL;
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
     if (!st->e_k0) { cudaEventCreate(&st->e_k0); cudaEventCreate(&st->e_k1); }
-    int32_t rc = plan_enqueue(st->plan, s, st->e_k0, st->e_k1);
+    int32_t rc;
+    if (st->incremental && !st->need_full) {
+        rc = state_incremental_enqueue(st, s);
+    } else {
+        rc = plan_enqueue(st->plan, s, st->e_k0, st->e_k1);
+        st->last_root_hashes = st->plan.hash_units;
+        if (!rc && st->incremental) rc = state_build_levels(st, s);   // a cold root leaves the level arrays stale
+    }
     if (rc) return rc;
     k_gather_nodes<<<1, 32, 0, s>>>(reinterpret_cast<const HashOp*>(st->plan.root_addr), 29, st->d_result);
     count_launch();
@@ -917,6 +1072,9 @@ int32_t lhb200_state_release(lhb200_state* st) {
     }
     if (st->e_k0) cudaEventDestroy(st->e_k0);
     if (st->e_k1) cudaEventDestroy(st->e_k1);
+    if (st->d_levels) cudaFree(st->d_levels);
+    if (st->d_trees) cudaFree(st->d_trees);
+    if (st->d_dirty) cudaFree(st->d_dirty);
     delete st;
     return LHB200_OK;
 }

@@ -168,6 +168,16 @@ class ResidentState:
         p, keep = buf(data)
         check(lib.lhb200_state_patch(self._h, ssz_offset, p, len(data)), "lhb200_state_patch")
 
+    def enable_incremental(self):
+        """Warm path: keep every level of the big lists resident; later root() calls re-hash only the paths above
+        the leaves patch() touched (the reference's tree-hash-cache behaviour, beacon_state.rs:2031-2038)."""
+        check(lib.lhb200_state_enable_incremental(self._h), "lhb200_state_enable_incremental")
+
+    @property
+    def last_root_hashes(self):
+        """hash32_concat units the last root() actually computed (cold: all of them; warm: dirty paths + tail)."""
+        return lib.lhb200_state_last_root_hashes(self._h)
+
     def enqueue(self, stream=None):
         d = C.c_void_p()
         check(lib.lhb200_state_root_enqueue(self._h, stream, C.byref(d)), "lhb200_state_root_enqueue")

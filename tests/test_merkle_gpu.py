@@ -212,6 +212,63 @@ def test_resident_state_patch_matches_oracle(gpu):
     st.release()
 
 
+@pytest.mark.parametrize("n_validators", [20_000, 300_001])
+def test_incremental_state_root_matches_oracle(gpu, n_validators):
+    """Warm path with resident level arrays (lhb200_state_enable_incremental): several rounds of slot-like mutations —
+    scattered validator records, balances, participation flags, inactivity scores, one randao mix, block/state roots,
+    slashings, small fixed fields — each followed by a root that re-hashes only dirty paths; every root and every field
+    root must equal the oracle on the mutated SSZ.  A patch to a list without a resident tree (historical_roots)
+    falls back to a cold root; the following round is warm again."""
+    from lighthouse_b200 import tree_hash as T
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    rng = np.random.default_rng(n_validators)
+    ssz = bytearray(beacon_state_deneb_ssz(n_validators, seed=5))
+    st = T.ResidentState(bytes(ssz))
+    cold_units = st.hash_units
+    st.enable_incremental()
+    assert st.root() == O.beacon_state_root_deneb(bytes(ssz))[0]
+    assert st.last_root_hashes == cold_units                        # first root after enabling is cold
+    o_hist = struct.unpack_from("<I", ssz, 524464)[0]
+    o_val, o_bal = struct.unpack_from("<II", ssz, 524552)
+    o_pp, o_cp = struct.unpack_from("<II", ssz, 2687248)
+    o_inact = struct.unpack_from("<I", ssz, 2687377)[0]
+
+    def apply(off, data):
+        ssz[off:off + len(data)] = data
+        st.patch(off, data)
+
+    for rnd in range(4):
+        for vi in rng.choice(n_validators, size=300, replace=False):          # effective balances / exit epochs
+            apply(o_val + 121 * int(vi) + 80, struct.pack("<Q", int(rng.integers(1, 1 << 40))))
+            if vi % 3 == 0:
+                apply(o_val + 121 * int(vi) + 105, struct.pack("<Q", int(rng.integers(1, 1 << 30))))
+        apply(o_val + 121 * (n_validators - 1) + 88, bytes([1]))              # slashed flag of the last validator
+        for bi in rng.choice(n_validators, size=500, replace=False):
+            apply(o_bal + 8 * int(bi), struct.pack("<Q", int(rng.integers(1, 1 << 45))))
+        apply(o_cp + int(rng.integers(0, n_validators - 2000)), rb(rng, 2000))  # a committee's participation flags
+        apply(o_pp + n_validators - 1, bytes([3]))                            # last (partial) chunk of a packed list
+        apply(o_inact + 8 * int(rng.integers(0, n_validators)), struct.pack("<Q", rnd + 1))
+        apply(524560 + 32 * int(rng.integers(0, 65536)), rb(rng, 32))         # randao mix
+        apply(176 + 32 * int(rng.integers(0, 8192)), rb(rng, 32))             # block_roots[i]
+        apply(262320 + 32 * int(rng.integers(0, 8192)), rb(rng, 32))          # state_roots[i]
+        apply(2621712 + 8 * int(rng.integers(0, 8192)), struct.pack("<Q", int(rng.integers(1, 1 << 40))))  # slashings
+        apply(40, struct.pack("<Q", 1000 + rnd))                              # slot
+        apply(64, rb(rng, 112))                                               # latest_block_header
+        if rnd == 2:
+            apply(o_hist + 32, rb(rng, 32))                                   # historical_roots: no resident tree
+        want, want_fields = O.beacon_state_root_deneb(bytes(ssz))
+        got, got_fields = st.root(want_field_roots=True)
+        for i, (g, w) in enumerate(zip(got_fields, want_fields)):
+            assert g == w, f"round {rnd} field {i}"
+        assert got == want
+        if rnd == 2:
+            assert st.last_root_hashes == cold_units                          # fell back to a cold root
+        else:
+            assert st.last_root_hashes < cold_units // 20                     # warm: dirty paths + tail only
+    assert st.root() == O.beacon_state_root_deneb(bytes(ssz))[0]              # nothing dirty: tail only, same root
+    st.release()
+
+
 def test_signing_root_and_domain_helpers(gpu):
     """signing_root / compute_domain (signing_data.rs:27-35, chain_spec.rs:548-566) against hashlib and the
     synthetic generator's own CPU restatement."""
