@@ -91,6 +91,10 @@ LHB200_API int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t*
  * (beacon_state.rs:2459-2481): bytes [ssz_offset, ssz_offset+len) of the SSZ encoding are replaced; the next
  * lhb200_state_root re-hashes everything on the device (warm path = patch + full re-hash). */
 LHB200_API int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t* data, uint64_t len);
+/* n non-overlapping same-length mutations in one call (offsets[i], lens[i], bytes concatenated in `data`): one H2D copy
+ * and one scatter kernel instead of n round trips — what a slot's worth of milhouse pending updates looks like. */
+LHB200_API int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* offsets, const uint32_t* lens,
+                                            const uint8_t* data, uint32_t n);
 /* Warm path (the reference's steady state: BeaconState::update_tree_hash_cache re-hashes only dirty
  * paths, beacon_state.rs:2031-2038,2459-2481).  After this call the handle keeps every level of its big lists
  * (validators, balances, inactivity scores, participation x2, randao mixes, block/state roots, slashings) resident:

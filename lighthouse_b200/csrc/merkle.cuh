@@ -325,7 +325,6 @@ struct TreeDev {
     uint32_t n_dirty;
     uint32_t pad_;
 };
-constexpr int TREE_THREADS = 1024;
 
 // out[i] = H(in[2i], in[2i+1] or ZERO[zlevel]) for i < ceil(n_in / 2)   (full build of one level)
 __global__ void __launch_bounds__(256) k_tree_level(const uint8_t* __restrict__ in, uint64_t n_in,
@@ -340,37 +339,47 @@ __global__ void __launch_bounds__(256) k_tree_level(const uint8_t* __restrict__ 
     store_chunk(out + 32 * i, l);
 }
 
-__global__ void __launch_bounds__(TREE_THREADS) k_tree_update(const TreeDev* __restrict__ trees) {
-    const TreeDev& t = trees[blockIdx.x];
-    const uint32_t nd = t.n_dirty;
-    if (nd == 0) return;
-    const uint32_t tid = threadIdx.x;
-    if (t.kind == 0) {
-        for (uint32_t j = tid; j < nd; j += TREE_THREADS) {
-            const uint32_t i = t.dirty[j];
-            uint32_t w[8];
-            validator_root_words(t.src + (uint64_t)VAL_SSZ * i, w);
-            store_chunk(t.lvl[0] + 32ull * i, w);
-        }
-        __syncthreads();
+// One level of the dirty-path update for ALL trees of a state: blockIdx.y = tree, one thread per dirty leaf.
+// level < 0: recompute the leaf roots of dirty validators.  Otherwise the first dirty leaf under each parent at
+// `level + 1` hashes that parent from its two children at `level`.
+__global__ void __launch_bounds__(256) k_tree_update_level(const TreeDev* __restrict__ trees, int level) {
+    const TreeDev& t = trees[blockIdx.y];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.n_dirty) return;
+    if (level < 0) {
+        if (t.kind != 0) return;
+        const uint32_t i = t.dirty[j];
+        uint32_t w[8];
+        validator_root_words(t.src + (uint64_t)VAL_SSZ * i, w);
+        store_chunk(t.lvl[0] + 32ull * i, w);
+        return;
     }
-    uint64_t n_l = t.n_leaves;
-    for (uint32_t l = 0; l < t.top; l++) {
-        for (uint32_t j = tid; j < nd; j += TREE_THREADS) {
-            const uint32_t p = t.dirty[j] >> (l + 1);
-            if (j == 0 || (t.dirty[j - 1] >> (l + 1)) != p) {   // first dirty leaf under this parent does the hash
-                uint32_t a[8], b[8];
-                load_operand(reinterpret_cast<uint64_t>(t.lvl[l] + 64ull * p), a);   // plain loads: written this launch
-                const bool rv = 2ull * p + 1 < n_l;
-                if (rv) load_operand(reinterpret_cast<uint64_t>(t.lvl[l] + 64ull * p + 32), b);
-                fold(a, b, rv, l);
-                store_chunk(t.lvl[l + 1] + 32ull * p, a);
-                if (l + 1 == t.top) store_chunk(t.top_dst, a);
-            }
-        }
-        __syncthreads();
-        n_l = (n_l + 1) >> 1;
-    }
+    const uint32_t l = (uint32_t)level;
+    if (l >= t.top) return;
+    const uint32_t p = t.dirty[j] >> (l + 1);
+    if (j != 0 && (t.dirty[j - 1] >> (l + 1)) == p) return;
+    const uint64_t n_l = (t.n_leaves + ((1ull << l) - 1)) >> l;   // nodes at this level
+    uint32_t a[8], b[8];
+    load_operand(reinterpret_cast<uint64_t>(t.lvl[l] + 64ull * p), a);
+    const bool rv = 2ull * p + 1 < n_l;
+    if (rv) load_operand(reinterpret_cast<uint64_t>(t.lvl[l] + 64ull * p + 32), b);
+    fold(a, b, rv, l);
+    store_chunk(t.lvl[l + 1] + 32ull * p, a);
+    if (l + 1 == t.top) store_chunk(t.top_dst, a);
+}
+
+// Scatter a batch of same-length byte patches from one staged blob into resident buffers: one warp per patch.
+struct ScatterOp {
+    uint8_t* dst;
+    uint32_t len;
+    uint32_t blob_off;
+};
+__global__ void __launch_bounds__(256) k_scatter_bytes(const ScatterOp* __restrict__ ops, uint32_t n,
+                                                       const uint8_t* __restrict__ blob) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const ScatterOp op = ops[w];
+    for (uint32_t i = lane; i < op.len; i += 32) op.dst[i] = blob[op.blob_off + i];
 }
 
 // ---------------------------------------------------------------------------------------------

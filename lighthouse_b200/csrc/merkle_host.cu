@@ -879,21 +879,30 @@ int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t 
 // encoding the handle was staged from.  Big-field bytes are patched in place in HBM, small-field bytes re-pack their
 // literal chunks.  List lengths / variable-part offsets must not change (re-stage for that).  The next
 // lhb200_state_root re-hashes the whole state (0.85 ms at 500 k validators - cheaper than tracking dirty paths).
-int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t* data, uint64_t len) {
+// n same-length mutations in one call: offsets[i], lens[i], bytes concatenated in `data`.  Ranges must not overlap.
+// One H2D copy of the blob + one scatter kernel; dirty leaves are recorded for the warm path.
+int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* offsets, const uint32_t* lens, const uint8_t* data,
+                                 uint32_t n) {
     LHB_REQUIRE_READY();
-    if (!st || (len && !data)) return LHB200_EINVAL;
-    if (len == 0) return LHB200_OK;
+    if (!st || (n && (!offsets || !lens || !data))) return LHB200_EINVAL;
+    if (n == 0) return LHB200_OK;
     Ctx& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
-    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(len + 64));
-    if (!h) return LHB200_ENOMEM;
-    memcpy(h, data, len);
-    const uint64_t lo = ssz_offset, hi = ssz_offset + len;
-    bool touched = false;
-    for (const StageCopy& cp : st->copies) {
-        const uint64_t a = std::max<uint64_t>(lo, cp.src_off), b = std::min<uint64_t>(hi, cp.src_off + cp.nbytes);
-        if (a < b) {
-            LHB_CUDA(cudaMemcpyAsync(cp.dst + (a - cp.src_off), h + (a - lo), b - a, cudaMemcpyHostToDevice, c.stream));
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += lens[i];
+    std::vector<ScatterOp> ops;
+    ops.reserve(n);
+    Plan& pl = st->plan;
+    uint64_t blob_off = 0;
+    uint32_t lit_lo = ~0u, lit_hi = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t lo = offsets[i], hi = lo + lens[i];
+        const uint8_t* src = data + blob_off;
+        bool touched = lens[i] == 0;
+        for (const StageCopy& cp : st->copies) {
+            const uint64_t a = std::max<uint64_t>(lo, cp.src_off), b = std::min<uint64_t>(hi, cp.src_off + cp.nbytes);
+            if (a >= b) continue;
+            ops.push_back({cp.dst + (a - cp.src_off), (uint32_t)(b - a), (uint32_t)(blob_off + (a - lo))});
             touched = true;
             if (st->incremental && !st->need_full) {   // warm path: which leaves of which tree does this touch?
                 bool found = false;
@@ -902,26 +911,52 @@ int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t*
                     found = true;
                     const uint64_t i0 = (a - t.src_off) / t.item_bytes, i1 = (b - 1 - t.src_off) / t.item_bytes;
                     if (t.dirty.size() + (i1 - i0 + 1) > lhb200_state::DIRTY_CAP) { st->need_full = true; break; }
-                    for (uint64_t i = i0; i <= i1; i++) t.dirty.push_back((uint32_t)i);
+                    for (uint64_t k = i0; k <= i1; k++) t.dirty.push_back((uint32_t)k);
                 }
                 if (!found) st->need_full = true;      // a list without a resident tree (votes, summaries, committees)
             }
         }
-    }
-    Plan& pl = st->plan;
-    for (const Plan::LitSrc& ls : pl.lit_src) {
-        const uint64_t a = std::max<uint64_t>(lo, ls.src_off), b = std::min<uint64_t>(hi, ls.src_off + ls.n);
-        if (a < b) {
-            uint8_t* chunk = &pl.lit[(size_t)ls.lit_index * 32];
-            memcpy(chunk + (a - ls.src_off), data + (a - lo), b - a);
-            LHB_CUDA(cudaMemcpyAsync(pl.arena + pl.lit_off + (size_t)ls.lit_index * 32, chunk, 32, cudaMemcpyHostToDevice,
-                                     c.stream));
+        for (const Plan::LitSrc& ls : pl.lit_src) {      // small fixed fields live in host-packed literal chunks
+            const uint64_t a = std::max<uint64_t>(lo, ls.src_off), b = std::min<uint64_t>(hi, ls.src_off + ls.n);
+            if (a >= b) continue;
+            memcpy(&pl.lit[(size_t)ls.lit_index * 32] + (a - ls.src_off), src + (a - lo), b - a);
+            lit_lo = std::min(lit_lo, ls.lit_index);
+            lit_hi = std::max(lit_hi, ls.lit_index + 1);
             touched = true;
         }
+        if (!touched) {
+            set_error("state_patch: range [%llu, %llu) is not resident on this handle (offset table or another rank's shard)",
+                      (unsigned long long)lo, (unsigned long long)hi);
+            return LHB200_EINVAL;
+        }
+        blob_off += lens[i];
     }
-    LHB_CUDA(cudaStreamSynchronize(c.stream));
-    if (!touched) { set_error("state_patch: range is not resident on this handle (offset table or another rank's shard)"); return LHB200_EINVAL; }
+    const size_t ob = align_up(ops.size() * sizeof(ScatterOp), 256), bb = align_up(total + 16, 256);
+    const size_t lb = lit_lo < lit_hi ? (size_t)(lit_hi - lit_lo) * 32 : 0;
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(ob + bb + lb + 256));
+    if (!h) return LHB200_ENOMEM;
+    if (!ops.empty()) {
+        uint8_t* d = static_cast<uint8_t*>(dev_scratch(ob + bb));
+        if (!d) return LHB200_ENOMEM;
+        memcpy(h, ops.data(), ops.size() * sizeof(ScatterOp));
+        memcpy(h + ob, data, total);
+        LHB_CUDA(cudaMemcpyAsync(d, h, ob + total, cudaMemcpyHostToDevice, c.stream));
+        k_scatter_bytes<<<(unsigned)ceil_div(ops.size(), 8), 256, 0, c.stream>>>(reinterpret_cast<const ScatterOp*>(d),
+                                                                                 (uint32_t)ops.size(), d + ob);
+        count_launch();
+        LHB_CUDA(cudaGetLastError());
+    }
+    if (lb) {
+        memcpy(h + ob + bb, &pl.lit[(size_t)lit_lo * 32], lb);
+        LHB_CUDA(cudaMemcpyAsync(pl.arena + pl.lit_off + (size_t)lit_lo * 32, h + ob + bb, lb, cudaMemcpyHostToDevice, c.stream));
+    }
+    LHB_CUDA(cudaStreamSynchronize(c.stream));   // the staging slabs are reused by the next call
     return LHB200_OK;
+}
+int32_t lhb200_state_patch(lhb200_state* st, uint64_t ssz_offset, const uint8_t* data, uint64_t len) {
+    if (len > 0xffffffffull) { set_error("state_patch: a single patch is limited to 4 GiB"); return LHB200_EINVAL; }
+    const uint32_t l32 = (uint32_t)len;
+    return lhb200_state_patch_batch(st, &ssz_offset, &l32, data, len ? 1 : 0);
 }
 
 // (Re)build every level of every resident tree from its leaf chunks (which a cold root has just refreshed).
@@ -943,7 +978,7 @@ static int32_t state_build_levels(lhb200_state* st, cudaStream_t s) {
 static int32_t state_incremental_enqueue(lhb200_state* st, cudaStream_t s) {
     uint32_t total = 0;
     for (lhb200_state::Tree& t : st->trees) {
-        std::sort(t.dirty.begin(), t.dirty.end());
+        if (!std::is_sorted(t.dirty.begin(), t.dirty.end())) std::sort(t.dirty.begin(), t.dirty.end());
         t.dirty.erase(std::unique(t.dirty.begin(), t.dirty.end()), t.dirty.end());
         total += (uint32_t)t.dirty.size();
     }
@@ -961,19 +996,32 @@ static int32_t state_incremental_enqueue(lhb200_state* st, cudaStream_t s) {
             if (!t.dirty.empty()) memcpy(hd + off, t.dirty.data(), t.dirty.size() * 4);
             off += t.dev.n_dirty;
             memcpy(h + k * sizeof(TreeDev), &t.dev, sizeof(TreeDev));
-            // hashes: distinct parents per level (upper bound: one path per dirty leaf) + 8 per dirty validator
-            uint64_t prev = ~0ull, cnt = 0;
-            for (uint32_t l = 1; l <= t.dev.top; l++) {
-                prev = ~0ull;
-                for (uint32_t d : t.dirty) { if ((uint64_t)(d >> l) != prev) { cnt++; prev = d >> l; } }
+            // hashes = distinct parents per level (+ 8 per dirty validator): neighbours d[j-1] < d[j] have distinct
+            // ancestors exactly at the levels up to the highest bit in which they differ
+            if (!t.dirty.empty()) {
+                uint64_t cnt = t.dev.top;  // the path of the first dirty leaf
+                for (size_t j = 1; j < t.dirty.size(); j++) {
+                    const uint32_t hb = 32 - (uint32_t)__builtin_clz(t.dirty[j] ^ t.dirty[j - 1]);  // ancestors equal from level hb up
+                    cnt += std::min<uint32_t>(hb - 1, t.dev.top);
+                }
+                hashes += cnt + (t.dev.kind == 0 ? 8ull * t.dirty.size() : 0);
             }
-            hashes += cnt + (t.dev.kind == 0 ? 8ull * t.dirty.size() : 0);
             t.dirty.clear();
         }
         LHB_CUDA(cudaMemcpyAsync(st->d_trees, h, tb, cudaMemcpyHostToDevice, s));
         LHB_CUDA(cudaMemcpyAsync(st->d_dirty, hd, (size_t)total * 4, cudaMemcpyHostToDevice, s));
-        k_tree_update<<<(unsigned)st->trees.size(), TREE_THREADS, 0, s>>>(st->d_trees);
-        count_launch();
+        // one launch per level covers every tree (blockIdx.y); levels are ordered by the stream
+        uint32_t max_nd = 0, max_top = 0;
+        bool any_validators = false;
+        for (const lhb200_state::Tree& t : st->trees) {
+            max_nd = std::max(max_nd, t.dev.n_dirty);
+            if (t.dev.n_dirty) { max_top = std::max(max_top, t.dev.top); any_validators |= t.dev.kind == 0; }
+        }
+        const dim3 grid((unsigned)ceil_div(max_nd, 256), (unsigned)st->trees.size());
+        for (int l = any_validators ? -1 : 0; l < (int)max_top; l++) {
+            k_tree_update_level<<<grid, 256, 0, s>>>(st->d_trees, l);
+            count_launch();
+        }
     }
     st->last_root_hashes = hashes;
     return plan_enqueue_tail(st->plan, s);

@@ -168,6 +168,18 @@ class ResidentState:
         p, keep = buf(data)
         check(lib.lhb200_state_patch(self._h, ssz_offset, p, len(data)), "lhb200_state_patch")
 
+    def patch_batch(self, edits):
+        """[(ssz_offset, bytes), ...] non-overlapping same-length mutations in one call (one copy + one scatter kernel)."""
+        import numpy as np
+        edits = list(edits)
+        if not edits:
+            return
+        offs = np.array([o for o, _ in edits], dtype=np.uint64)
+        lens = np.array([len(d) for _, d in edits], dtype=np.uint32)
+        p, keep = buf(b"".join(d for _, d in edits))
+        check(lib.lhb200_state_patch_batch(self._h, offs.ctypes.data, lens.ctypes.data, p, len(edits)),
+              "lhb200_state_patch_batch")
+
     def enable_incremental(self):
         """Warm path: keep every level of the big lists resident; later root() calls re-hash only the paths above
         the leaves patch() touched (the reference's tree-hash-cache behaviour, beacon_state.rs:2031-2038)."""

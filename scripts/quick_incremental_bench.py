@@ -28,9 +28,11 @@ rng = np.random.default_rng(1)
 res = {"n_validators": n, "cold_resident_ms": round(cold, 4), "cold_hash_units": int(st.hash_units)}
 for n_dirty in (0, 64, 2048, 16384):
     def slot():
+        edits = []
         for vi in rng.choice(n, size=n_dirty, replace=False) if n_dirty else []:
-            off = o_val + 121 * int(vi) + 80; d = struct.pack("<Q", int(rng.integers(1, 1 << 40))); ssz[off:off+8] = d; st.patch(off, d)
-            off = o_bal + 8 * int(vi); ssz[off:off+8] = d; st.patch(off, d)
+            off = o_val + 121 * int(vi) + 80; d = struct.pack("<Q", int(rng.integers(1, 1 << 40))); ssz[off:off+8] = d; edits.append((off, d))
+            off = o_bal + 8 * int(vi); ssz[off:off+8] = d; edits.append((off, d))
+        st.patch_batch(edits)
     # device time of the warm root alone (patches applied beforehand)
     ms = []
     for _ in range(5):

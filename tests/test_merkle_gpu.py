@@ -233,9 +233,14 @@ def test_incremental_state_root_matches_oracle(gpu, n_validators):
     o_pp, o_cp = struct.unpack_from("<II", ssz, 2687248)
     o_inact = struct.unpack_from("<I", ssz, 2687377)[0]
 
+    pending = []
+
     def apply(off, data):
         ssz[off:off + len(data)] = data
-        st.patch(off, data)
+        if rnd % 2:
+            pending.append((off, data))          # odd rounds: one lhb200_state_patch_batch call for the whole slot
+        else:
+            st.patch(off, data)
 
     for rnd in range(4):
         for vi in rng.choice(n_validators, size=300, replace=False):          # effective balances / exit epochs
@@ -256,6 +261,12 @@ def test_incremental_state_root_matches_oracle(gpu, n_validators):
         apply(64, rb(rng, 112))                                               # latest_block_header
         if rnd == 2:
             apply(o_hist + 32, rb(rng, 32))                                   # historical_roots: no resident tree
+        if pending:                                                           # later edits of the same bytes win:
+            last = {}                                                         # keep the batch non-overlapping
+            for off, data in pending:
+                last[(off, len(data))] = data
+            st.patch_batch([(o, d) for (o, _), d in last.items()])
+            pending.clear()
         want, want_fields = O.beacon_state_root_deneb(bytes(ssz))
         got, got_fields = st.root(want_field_roots=True)
         for i, (g, w) in enumerate(zip(got_fields, want_fields)):
