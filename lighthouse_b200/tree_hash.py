@@ -53,6 +53,33 @@ def merkle_root(data: bytes, minimum_leaf_count: int = 0) -> bytes:
     return merkleize_chunks(padded, depth)
 
 
+class MerkleHasher:
+    """tree_hash::MerkleHasher {with_leaves, write, finish} as used by AttestationKey::tree_hash_root
+    (beacon_node/beacon_chain/src/naive_aggregation_pool.rs:46-55): written bytes are concatenated, cut into 32-byte
+    leaves (the last one zero-padded at finish) and merkleized over `num_leaves`.  The crate (tree_hash 0.6.0) is not
+    vendored; the only in-tree call site writes a 32-byte root then an 8-byte index, where this is unambiguous."""
+
+    def __init__(self, num_leaves: int):
+        self.num_leaves = max(int(num_leaves), 1)
+        self._chunks = bytearray()
+
+    @classmethod
+    def with_leaves(cls, num_leaves: int):
+        return cls(num_leaves)
+
+    def write(self, data: bytes):
+        data = bytes(data)
+        if len(self._chunks) + len(data) > 32 * self.num_leaves:
+            raise ValueError("MerkleHasher: MaximumLeavesExceeded")
+        self._chunks += data
+        return self
+
+    def finish(self) -> bytes:
+        depth = (self.num_leaves - 1).bit_length()
+        data = bytes(self._chunks)
+        return merkleize_chunks(data + b"\0" * (-len(data) % 32), depth)
+
+
 def mix_in_length(root: bytes, length: int) -> bytes:
     out = C.create_string_buffer(32)
     p, keep = buf(root)

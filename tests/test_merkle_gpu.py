@@ -280,6 +280,19 @@ def test_incremental_state_root_matches_oracle(gpu, n_validators):
     st.release()
 
 
+def test_merkle_hasher_attestation_key(gpu):
+    """AttestationKey::tree_hash_root (naive_aggregation_pool.rs:44-58): MerkleHasher::with_leaves(2), write the data
+    root, write the committee index -> H(data_root || le64(index) zero-padded)."""
+    from lighthouse_b200 import tree_hash as T
+    data_root = hashlib.sha256(b"attestation data").digest()
+    got = T.MerkleHasher.with_leaves(2).write(data_root).write((37).to_bytes(8, "little")).finish()
+    assert got == hashlib.sha256(data_root + (37).to_bytes(8, "little") + bytes(24)).digest()
+    h = T.MerkleHasher.with_leaves(4).write(data_root)
+    assert h.finish() == O.merkleize(data_root, 2)                      # right-sparse: zero-hash padding
+    with pytest.raises(ValueError):
+        T.MerkleHasher.with_leaves(1).write(data_root).write(b"\x01")
+
+
 def test_signing_root_and_domain_helpers(gpu):
     """signing_root / compute_domain (signing_data.rs:27-35, chain_spec.rs:548-566) against hashlib and the
     synthetic generator's own CPU restatement."""
