@@ -224,6 +224,87 @@ LHB_HD LHB_INLINE void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
     fp_final_sub(r, even, 0);
 }
 
+// ---- split form: full 768-bit product and separate Montgomery reduction (lazy reduction in Fp2, fp2.cuh) ----
+// Same even/odd carry-chain rows as mont_row, but the product rows carry no reduction (the low limb of every row is
+// an output limb) and the reduction rows carry no product.  fp_redc_inl(fp_mulw_inl(a, b)) == fp_mul_inl(a, b).
+LHB_HD LHB_INLINE void mulw_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi, bool first, uint32_t& out) {
+    if (first) {
+#pragma unroll
+        for (int j = 0; j < NL; j += 2) {
+            mul_pair(odd[j], odd[j + 1], a[j + 1], bi);
+            mul_pair(even[j], even[j + 1], a[j], bi);
+        }
+    } else {
+        add_cc(even[0], even[0], odd[1]);   // the previous row's low limb has been emitted: shift by one limb
+#pragma unroll
+        for (int j = 0; j < NL - 2; j += 2) mad_pair_sh(odd[j], odd[j + 1], a[j + 1], bi, odd[j + 2], odd[j + 3]);
+        mad_pair_last(odd[NL - 2], odd[NL - 1], a[NL - 1], bi);
+        mad_pair_first(even[0], even[1], a[0], bi);
+#pragma unroll
+        for (int j = 2; j < NL; j += 2) mad_pair(even[j], even[j + 1], a[j], bi);
+        addc(odd[NL - 1], odd[NL - 1], 0);
+    }
+    out = even[0];
+}
+// w[0..23] = a * b   (a, b < 2^384; no reduction)
+LHB_HD LHB_INLINE void fp_mulw_inl(uint32_t* w, const Fp& a, const Fp& b) {
+    uint32_t even[NL], odd[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i += 2) {
+        mulw_row(even, odd, a.v, b.v[i], i == 0, w[i]);
+        mulw_row(odd, even, a.v, b.v[i + 1], false, w[i + 1]);
+    }
+    add_cc(w[NL], even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) addc_cc(w[NL + i], even[i], odd[i + 1]);
+    addc(w[2 * NL - 1], even[NL - 1], 0);
+}
+// one reduction row: m = T[0] * M0; T += m * p; (shift of the previous row fused, T[0] becomes 0)
+LHB_HD LHB_INLINE void redc_row(uint32_t* even, uint32_t* odd, bool first) {
+    if (first) {
+        const uint32_t mi = even[0] * LHB_FP_M0;
+        mad_pair_first(odd[0], odd[1], FP_P.v[1], mi);
+#pragma unroll
+        for (int j = 2; j < NL; j += 2) mad_pair(odd[j], odd[j + 1], FP_P.v[j + 1], mi);
+        mad_pair_first(even[0], even[1], FP_P.v[0], mi);
+#pragma unroll
+        for (int j = 2; j < NL; j += 2) mad_pair(even[j], even[j + 1], FP_P.v[j], mi);
+        addc(odd[NL - 1], odd[NL - 1], 0);
+    } else {
+        add_cc(even[0], even[0], odd[1]);
+        const uint32_t mi = even[0] * LHB_FP_M0;   // mul.lo leaves the carry flag alone
+#pragma unroll
+        for (int j = 0; j < NL - 2; j += 2) mad_pair_sh(odd[j], odd[j + 1], FP_P.v[j + 1], mi, odd[j + 2], odd[j + 3]);
+        mad_pair_last(odd[NL - 2], odd[NL - 1], FP_P.v[NL - 1], mi);
+        mad_pair_first(even[0], even[1], FP_P.v[0], mi);
+#pragma unroll
+        for (int j = 2; j < NL; j += 2) mad_pair(even[j], even[j + 1], FP_P.v[j], mi);
+        addc(odd[NL - 1], odd[NL - 1], 0);
+    }
+}
+// r = w / 2^384 mod p   for w < p * 2^384
+LHB_HD LHB_INLINE void fp_redc_inl(Fp& r, const uint32_t* w) {
+    uint32_t even[NL], odd[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) { even[i] = w[i]; odd[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < NL; i += 2) {
+        redc_row(even, odd, i == 0);
+        redc_row(odd, even, false);
+    }
+    // U = (w_low + M p) / 2^384 <= p, then + w_high (< p): below 2p, 13th bit in `top`
+    uint32_t top;
+    add_cc(even[0], even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) addc_cc(even[i], even[i], odd[i + 1]);
+    addc(even[NL - 1], even[NL - 1], 0);
+    add_cc(even[0], even[0], w[NL]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) addc_cc(even[i], even[i], w[NL + i]);
+    addc(top, 0, 0);
+    fp_final_sub(r, even, top);
+}
+
 #ifdef LHB_FP_DECL_ONLY
 LHB_HD void fp_mul(Fp& r, const Fp& a, const Fp& b);
 #else

@@ -85,6 +85,62 @@ LHB_HD LHB_NOINLINE void fp2_conj(Fp2& r, const Fp2& a) {
 #else
 #define LHB_BARRIER() do { } while (0)
 #endif
+#ifdef LHB_FP2_LAZY
+// Karatsuba with LAZY REDUCTION: three full 768-bit products, the recombination in double width, two Montgomery
+// reductions instead of three (744 multiply instructions instead of 900).  Operand sums stay unreduced (< 2p < 2^382),
+// a0 b0 - a1 b1 is lifted by p 2^384 when negative so both reductions see a value in [0, p 2^384).
+LHB_HD LHB_INLINE void fp_add_nored(Fp& r, const Fp& a, const Fp& b) {
+    add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) addc_cc(r.v[i], a.v[i], b.v[i]);
+    addc(r.v[NL - 1], a.v[NL - 1], b.v[NL - 1]);
+}
+// EXPERIMENT (-DLHB_FP2_LAZY, not the shipped default — DESIGN.md §9): in isolation this leaf is 22 % faster than the
+// eager one (scripts/ubench/fp2_leaf.cu), but with three products and two reductions inlined it is 20 KB of code and
+// the Fp2 kernels fall out of the instruction cache (no_instruction stall 0.19 -> 1.62 in k_miller_multi; 92.5 ->
+// 95.8-100.6 ms per 100 k sets); with the product and the reduction as shared out-of-line bodies the 24-limb values
+// travel through local memory and the step is 107-113 ms.
+struct FpW {
+    uint32_t v[2 * NL];
+};
+LHB_HD LHB_INLINE FpW fp_mulw_rr(Fp a, Fp b) { FpW o; fp_mulw_inl(o.v, a, b); return o; }
+LHB_HD LHB_INLINE Fp fp_redc_rr(FpW w) { Fp o; fp_redc_inl(o, w.v); return o; }
+LHB_HD LHB_NOINLINE void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+    FpW w0, w1, w2;
+    { Fp p = a.c0, q = b.c0; w0 = fp_mulw_rr(p, q); }
+    { Fp p = a.c1, q = b.c1; w1 = fp_mulw_rr(p, q); }
+    {
+        Fp s0, s1;
+        { Fp p = a.c0, q = a.c1; fp_add_nored(s0, p, q); }
+        { Fp p = b.c0, q = b.c1; fp_add_nored(s1, p, q); }
+        w2 = fp_mulw_rr(s0, s1);
+    }
+    uint32_t *t0 = w0.v, *t1 = w1.v, *t2 = w2.v;
+    // c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1  (= a0 b1 + a1 b0 >= 0, < 2 p^2)
+    sub_cc(t2[0], t2[0], t0[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * NL - 1; i++) subc_cc(t2[i], t2[i], t0[i]);
+    subc(t2[2 * NL - 1], t2[2 * NL - 1], t0[2 * NL - 1]);
+    sub_cc(t2[0], t2[0], t1[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * NL - 1; i++) subc_cc(t2[i], t2[i], t1[i]);
+    subc(t2[2 * NL - 1], t2[2 * NL - 1], t1[2 * NL - 1]);
+    // c0 = a0 b0 - a1 b1, + p 2^384 when negative
+    uint32_t m;
+    sub_cc(t0[0], t0[0], t1[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * NL; i++) subc_cc(t0[i], t0[i], t1[i]);
+    subc(m, 0, 0);  // 0xffffffff on borrow
+    add_cc(t0[NL], t0[NL], FP_P.v[0] & m);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) addc_cc(t0[NL + i], t0[NL + i], FP_P.v[i] & m);
+    addc(t0[2 * NL - 1], t0[2 * NL - 1], FP_P.v[NL - 1] & m);
+    const Fp o0 = fp_redc_rr(w0);
+    const Fp o1 = fp_redc_rr(w2);
+    r.c0 = o0;
+    r.c1 = o1;
+}
+#else
 // Karatsuba: 3 Montgomery products
 LHB_HD LHB_NOINLINE void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
     Fp t0, t1, s0, s1;
@@ -102,6 +158,7 @@ LHB_HD LHB_NOINLINE void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
     r.c0 = o0;
     r.c1 = s0;
 }
+#endif  // LHB_FP2_LAZY
 // (a0+a1)(a0-a1), 2 a0 a1 : 2 Montgomery products
 LHB_HD LHB_NOINLINE void fp2_sqr(Fp2& r, const Fp2& a) {
     Fp s, d, m;

@@ -140,10 +140,13 @@ LHB_HD LHB_NOINLINE void miller_loop(Fp12& f, const G1Proj3& P, const G2Affine& 
 constexpr int MILLER_KMAX = 4;
 LHB_HD LHB_NOINLINE void miller_loop_multi(Fp12& f, const G1Proj3* P, const G2Affine* Q, const uint32_t* idx, int m) {
     G2Jac T[MILLER_KMAX];
+#pragma unroll 1
     for (int j = 0; j < m; j++) jac_from_affine(T[j], Q[idx[j]]);
     Fp2 c0, c1, c4;
+#pragma unroll 1
     for (int i = 62; i >= 0; i--) {
         if (i != 62) fp12_sqr(f, f);
+#pragma unroll 1
         for (int j = 0; j < m; j++) {
             miller_dbl_step(T[j], c0, c1, c4, P[idx[j]]);
             if (i == 62 && j == 0) {  // f = 1: f^2 * l = l
@@ -154,6 +157,7 @@ LHB_HD LHB_NOINLINE void miller_loop_multi(Fp12& f, const G1Proj3* P, const G2Af
             }
         }
         if ((BLS_X_ABS >> i) & 1) {
+#pragma unroll 1
             for (int j = 0; j < m; j++) {
                 miller_add_step(T[j], c0, c1, c4, Q[idx[j]], P[idx[j]]);
                 fp12_mul_by_014(f, f, c0, c1, c4);

@@ -38,6 +38,13 @@ EXPORT void hs_mont_mul_raw(const uint32_t* a, const uint32_t* b, uint32_t* out)
     Fp x, y, r; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fp_mul(r, x, y); memcpy(out, r.v, 48);
 }
 // op: 0 mul 1 sqr 2 inv 3 sqrt(ok) 4 sgn0
+// split multiplier: redc(mulw(a, b)) in Montgomery limbs (raw)
+EXPORT void hs_mont_mul_split(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    Fp x, y, o; uint32_t w[24];
+    for (int i = 0; i < 12; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+    fp_mulw_inl(w, x, y); fp_redc_inl(o, w);
+    for (int i = 0; i < 12; i++) out[i] = o.v[i];
+}
 EXPORT int hs_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     Fp2 x, y, r; fp2_in(x, a); fp2_in(y, b);
     int ok = 1;

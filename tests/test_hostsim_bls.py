@@ -50,6 +50,27 @@ def test_fp_ops(L):
             assert s * s % P == a
 
 
+def test_split_multiplier_matches_montgomery_product(L):
+    """fp_redc_inl(fp_mulw_inl(a, b)) (the lazy-reduction building blocks) == a b R^-1 mod p on raw limbs, including
+    unreduced operands up to 2^384 - 1 on one side (what Karatsuba's operand sums can look like)."""
+    rnd = random.Random(7)
+    R = 1 << 384
+    Rinv = pow(R, -1, P)
+
+    def limbs(x):
+        return (C.c_uint32 * 12)(*[(x >> (32 * i)) & 0xffffffff for i in range(12)])
+
+    cases = [(0, 0), (1, 1), (P - 1, P - 1), (2 * P - 2, 2 * P - 2), (R - 1, 1), (P - 1, 2 * P - 1)]
+    cases += [(rnd.randrange(2 * P), rnd.randrange(2 * P)) for _ in range(300)]
+    for a, b in cases:
+        if a * b >= P * R:
+            continue
+        out = (C.c_uint32 * 12)()
+        L.hs_mont_mul_split(limbs(a), limbs(b), out)
+        got = sum(int(out[i]) << (32 * i) for i in range(12))
+        assert got == a * b * Rinv % P, (hex(a), hex(b))
+
+
 def test_fp2_ops(L):
     rnd = random.Random(2)
     def op(o, a, b=(0, 0)):
