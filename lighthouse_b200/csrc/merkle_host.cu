@@ -59,8 +59,13 @@ struct Plan {
     std::vector<std::vector<MerkleSeg>> passes;
     std::vector<HashOp> ops;
     std::vector<int> op_wave;
-    std::vector<int16_t> slot_wave;                    // (dst - wave_origin) / 32 -> wave producing it (-1: ready at start)
-    uint64_t wave_origin = ~0ull;                      // lowest address an op may write (default: the first op's dst)
+    // op outputs come from a dense node pool right after the literals, so "which wave produces this operand" is an
+    // array lookup (a slot table over the whole 72 MB state arena cost ~2 ms per plan build)
+    size_t node_off = 0, node_cap = 0, node_used = 0;
+    bool node_overflow = false;
+    std::vector<int16_t> slot_wave;                    // pool slot -> wave producing it
+    uint64_t forced_base = 0;                          // forced destinations (block batch outputs): one dense range
+    std::vector<int16_t> forced_wave;
     std::vector<ByteItem> items;                       // packed byte strings hashed straight from the staged blob
     ByteItem* d_items = nullptr;
     std::vector<int32_t> h_waves;                      // host copy of the wave table (wide waves get their own launch)
@@ -109,19 +114,28 @@ struct Plan {
     }
     int wave_of(uint64_t operand) const {
         if (operand & OP_ZERO_FLAG) return -1;
-        const size_t slot = (operand - wave_origin) / 32;  // below the origin wraps to a huge slot
-        return slot < slot_wave.size() ? slot_wave[slot] : -1;  // staged data / literals / leaf outputs: ready at start
+        const size_t slot = (operand - reinterpret_cast<uint64_t>(arena) - node_off) / 32;  // outside the pool: huge
+        if (slot < slot_wave.size()) return slot_wave[slot];
+        const size_t fs = (operand - forced_base) / 32;
+        if (fs < forced_wave.size()) return forced_wave[fs];
+        return -1;  // staged data / literals / leaf outputs: ready at start
     }
     uint64_t op_hash(uint64_t a, uint64_t b) {
-        uint64_t dst = forced_dst ? forced_dst : reinterpret_cast<uint64_t>(alloc(32, 32));
-        forced_dst = 0;
-        int w = std::max(wave_of(a), wave_of(b)) + 1;
+        const int w = std::max(wave_of(a), wave_of(b)) + 1;
+        uint64_t dst;
+        if (forced_dst) {
+            dst = forced_dst;
+            forced_dst = 0;
+            const size_t fs = (dst - forced_base) / 32;
+            if (fs < forced_wave.size()) forced_wave[fs] = (int16_t)w;
+        } else {
+            if (node_used >= node_cap) { node_overflow = true; node_used = 0; }  // reported by build_plan
+            dst = reinterpret_cast<uint64_t>(arena) + node_off + 32 * node_used;
+            if (node_used >= slot_wave.size()) slot_wave.resize(std::max<size_t>(node_used + 1, 2 * slot_wave.size()), -1);
+            slot_wave[node_used++] = (int16_t)w;
+        }
         ops.push_back({dst, a, b});
         op_wave.push_back(w);
-        if (wave_origin == ~0ull) wave_origin = dst;
-        const size_t slot = (dst - wave_origin) / 32;
-        if (slot >= slot_wave.size()) slot_wave.resize(std::max(slot + 1, 2 * slot_wave.size()), -1);
-        slot_wave[slot] = (int16_t)w;
         hash_units++;
         return dst;
     }
@@ -283,16 +297,23 @@ static void plan_finalize_program(Plan& pl, std::vector<HashOp>& ops_sorted, std
 // A "session": dry-run the planner to size the arena, allocate, then plan for real.  `build` must be
 // deterministic in its allocation sequence.
 template <class F>
-static int32_t build_plan(Plan& pl, uint8_t* arena, size_t arena_bytes, size_t lit_cap, F&& build) {
+static int32_t build_plan(Plan& pl, uint8_t* arena, size_t arena_bytes, size_t lit_cap, F&& build,
+                          size_t node_cap = 8192) {
     pl = Plan();
     pl.arena = arena;
     pl.arena_bytes = arena_bytes;
     pl.lit_cap = lit_cap;
     pl.lit_off = 0;
-    pl.bump = lit_cap;  // literals first
+    pl.node_off = align_up(lit_cap, 256);   // literals first, then the node pool
+    pl.node_cap = node_cap;
+    pl.bump = pl.node_off + node_cap * 32;
     build(pl);
     if (pl.lit.size() > lit_cap) {
         set_error("internal: literal block overflow (%zu > %zu)", pl.lit.size(), lit_cap);
+        return LHB200_EINVAL;
+    }
+    if (pl.node_overflow) {
+        set_error("internal: hash program larger than its node pool (%zu nodes)", node_cap);
         return LHB200_EINVAL;
     }
     return LHB200_OK;
@@ -1409,9 +1430,10 @@ int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offs
     bool bad = false;
     auto build = [&](Plan& p) {
         d_in = p.alloc(in_pad);
-        d_roots = p.alloc(32ull * n);
-        d_body = p.alloc(32ull * n);
-        p.wave_origin = reinterpret_cast<uint64_t>(d_roots);
+        d_roots = p.alloc(64ull * n);
+        d_body = d_roots + 32ull * n;
+        p.forced_base = reinterpret_cast<uint64_t>(d_roots);
+        p.forced_wave.assign(2ull * n, -1);
         BlockDescriber bd{p, ssz + base, d_in};
         for (uint32_t i = 0; i < n && !bd.bad; i++)
             bd.block(offsets[i] - base, offsets[i + 1] - offsets[i], reinterpret_cast<uint64_t>(d_roots + 32ull * i),
@@ -1429,7 +1451,7 @@ int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offs
     uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(stage_bytes));
     if (!arena || !hst) return LHB200_ENOMEM;
     Plan pl;
-    int32_t rc = build_plan(pl, arena, need, lit_cap, build);
+    int32_t rc = build_plan(pl, arena, need, lit_cap, build, max_nodes);
     if (bad) { set_error("BeaconBlockDeneb SSZ: malformed offsets or lengths"); return LHB200_EINVAL; }
     if (rc) return rc;
     if (pl.ops.size() + pl.items.size() > max_nodes || pl.bump + prog_bytes > need) {
