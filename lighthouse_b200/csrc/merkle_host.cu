@@ -1445,7 +1445,8 @@ int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offs
     const size_t max_nodes = total / 4 + 512ull * n;
     const size_t prog_bytes = align_up(max_nodes * sizeof(HashOp), 256) + align_up((max_nodes + 2) * 4, 256) +
                               align_up(max_nodes * sizeof(ByteItem), 256) + 1024;
-    const size_t need = lit_cap + in_pad + 64ull * n + 32 * max_nodes + prog_bytes + 4096;
+    // literals | node pool (op outputs) | staged blob | roots | item outputs | program blobs
+    const size_t need = lit_cap + 32 * max_nodes + in_pad + 64ull * n + 32 * max_nodes + prog_bytes + 8192;
     uint8_t* arena = static_cast<uint8_t*>(dev_scratch(need));
     const size_t stage_bytes = align_up(total, 256) + lit_cap + prog_bytes + 64ull * n + 1024;
     uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(stage_bytes));
