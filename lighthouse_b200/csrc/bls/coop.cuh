@@ -191,8 +191,17 @@ __device__ __noinline__ void coop_final_exp(CoopFinalSmem& m) {
 
 constexpr int COOP_THREADS = 64;
 
-// verdict = !fail && final_exp(prod * f_last) == 1
-__global__ void __launch_bounds__(COOP_THREADS) k_final_coop(const Fp12* __restrict__ prod, const Fp12* __restrict__ f_last,
+// the w-basis coefficient k of a tower element (see the table at the top of this file)
+__device__ __forceinline__ const Fp2& coop_tower_coeff(const Fp12& a, int k) {
+    return k == 0 ? a.c0.c0 : k == 1 ? a.c1.c0 : k == 2 ? a.c0.c1 : k == 3 ? a.c1.c1 : k == 4 ? a.c0.c2 : a.c1.c2;
+}
+// Largest tail of the Miller product tree that k_final_coop folds itself (a cooperative Fp12 product is ~6 us, one level
+// of the single-thread tree ~350 us of latency).
+constexpr uint32_t COOP_TAIL = 16;
+
+// verdict = !fail && final_exp(prod[0] * ... * prod[n_prod-1] * f_last) == 1
+__global__ void __launch_bounds__(COOP_THREADS) k_final_coop(const Fp12* __restrict__ prod, uint32_t n_prod,
+                                                              const Fp12* __restrict__ f_last,
                                                               const uint32_t* __restrict__ fail, uint8_t* __restrict__ ok,
                                                               Fp12* __restrict__ gt_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -201,12 +210,14 @@ __global__ void __launch_bounds__(COOP_THREADS) k_final_coop(const Fp12* __restr
         if (threadIdx.x == 0) *ok = 0;
         return;
     }
-    if (threadIdx.x == 0) {
-        coop_from_tower(m.t0, *prod);
-        coop_from_tower(m.t1, *f_last);
-    }
+    const int t = threadIdx.x;
+    if (t < 6) m.f.k[t] = coop_tower_coeff(*f_last, t);
     __syncthreads();
-    coop_mul(m.f, m.t0, m.t1, m.s);
+    for (uint32_t i = 0; i < n_prod; i++) {
+        if (t < 6) m.t1.k[t] = coop_tower_coeff(prod[i], t);
+        __syncthreads();
+        coop_mul(m.f, m.f, m.t1, m.s);
+    }
     coop_final_exp(m);
     if (threadIdx.x == 0) {
         Fp12 g;

@@ -487,10 +487,11 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaEventRecord(b->e_k1, s));
     launches += 3;
     const Fp12* cur = b->d_f;
+    uint32_t n_tail = n_groups;
     {
         uint32_t m = n_groups;
         int flip = 0;
-        while (m > 1) {
+        while (m > COOP_TAIL) {   // the last <= 16 values are folded cooperatively inside k_final_coop
             const uint32_t mo = cdiv(m, REDUCE_CHUNK);
             k_fp12_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, s>>>(cur, m, REDUCE_CHUNK, b->d_f_tmp[flip]);
             launches++;
@@ -498,9 +499,10 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
             flip ^= 1;
             m = mo;
         }
+        n_tail = m;
     }
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));
-    k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, b->d_flast, b->d_fail, b->d_ok, b->d_gt);
+    k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, n_tail, b->d_flast, b->d_fail, b->d_ok, b->d_gt);
     launches++;
     LHB_CUDA(cudaGetLastError());
     count_launch(launches);
