@@ -124,3 +124,33 @@ def serialize(t, v):
         return _sequence(parts, [is_fixed(t[1])] * len(parts))
     parts = [serialize(ft, v[name]) for name, ft in t[1]]
     return _sequence(parts, [is_fixed(ft) for _, ft in t[1]])
+
+
+# ---- BeaconStateDeneb (consensus/types/src/beacon_state.rs:339-490, mainnet sizes eth_spec.rs:389-430) ----------
+B4 = ("bytes", 4)
+Fork = C(("previous_version", B4), ("current_version", B4), ("epoch", U64))
+Validator = C(("pubkey", B48), ("withdrawal_credentials", B32), ("effective_balance", U64), ("slashed", ("uint", 1)),
+              ("activation_eligibility_epoch", U64), ("activation_epoch", U64), ("exit_epoch", U64),
+              ("withdrawable_epoch", U64))
+SyncCommittee = C(("pubkeys", ("vector", B48, 512)), ("aggregate_pubkey", B48))
+ExecutionPayloadHeaderDeneb = C(
+    ("parent_hash", B32), ("fee_recipient", B20), ("state_root", B32), ("receipts_root", B32),
+    ("logs_bloom", ("bytes", 256)), ("prev_randao", B32), ("block_number", U64), ("gas_limit", U64),
+    ("gas_used", U64), ("timestamp", U64), ("extra_data", ("bytelist", 32)), ("base_fee_per_gas", U256),
+    ("block_hash", B32), ("transactions_root", B32), ("withdrawals_root", B32), ("blob_gas_used", U64),
+    ("excess_blob_gas", U64))
+HistoricalSummary = C(("block_summary_root", B32), ("state_summary_root", B32))
+BeaconStateDeneb = C(
+    ("genesis_time", U64), ("genesis_validators_root", B32), ("slot", U64), ("fork", Fork),
+    ("latest_block_header", BeaconBlockHeader), ("block_roots", ("vector", B32, 8192)),
+    ("state_roots", ("vector", B32, 8192)), ("historical_roots", ("list", B32, 1 << 24)), ("eth1_data", Eth1Data),
+    ("eth1_data_votes", ("list", Eth1Data, 2048)), ("eth1_deposit_index", U64),
+    ("validators", ("list", Validator, 1 << 40)), ("balances", ("list", U64, 1 << 40)),
+    ("randao_mixes", ("vector", B32, 65536)), ("slashings", ("vector", U64, 8192)),
+    ("previous_epoch_participation", ("list", ("uint", 1), 1 << 40)),
+    ("current_epoch_participation", ("list", ("uint", 1), 1 << 40)), ("justification_bits", ("bitvector", 4)),
+    ("previous_justified_checkpoint", Checkpoint), ("current_justified_checkpoint", Checkpoint),
+    ("finalized_checkpoint", Checkpoint), ("inactivity_scores", ("list", U64, 1 << 40)),
+    ("current_sync_committee", SyncCommittee), ("next_sync_committee", SyncCommittee),
+    ("latest_execution_payload_header", ExecutionPayloadHeaderDeneb), ("next_withdrawal_index", U64),
+    ("next_withdrawal_validator_index", U64), ("historical_summaries", ("list", HistoricalSummary, 1 << 24)))

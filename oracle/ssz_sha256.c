@@ -21,7 +21,9 @@
  * Pinned by (tests/test_oracle_merkle.py): hashlib SHA-256, the genesis_validators_root embedded in the
  * reference's vendored mainnet/sepolia/gnosis genesis.ssz.zip, and deposit_message_root/deposit_data_root
  * of validator_manager/test_vectors.  Full Deneb BeaconState root: parity unpinned in-tree (only EF
- * ssz_static pins it; not on disk) — pinned transitively through the per-field rules above.
+ * ssz_static pins it; not on disk) — pinned transitively through the per-field rules above AND, field root by
+ * field root, against an independent generic from-spec merkleization (tests/ssz_spec.py driven by the type
+ * descriptors of lighthouse_b200/ssz_schema.py; tests/test_oracle_merkle.py).
  */
 #include <stdint.h>
 #include <stdlib.h>

@@ -68,3 +68,53 @@ def hash_tree_root(t, v):
             root = merkleize([hash_tree_root(t[1], e) for e in v], t[2])
         return mix_in_length(root, len(v))
     return merkleize([hash_tree_root(ft, v[name]) for name, ft in t[1]])
+
+
+# ---- generic SSZ decoder (test side only): lets the spec merkleization run on SSZ blobs the generators emit as bytes
+from lighthouse_b200.ssz_schema import fixed_size, is_fixed  # noqa: E402
+
+
+def deserialize(t, b):
+    b = bytes(b)
+    k = t[0]
+    if k == "uint":
+        assert len(b) == t[1]
+        return int.from_bytes(b, "little")
+    if k == "bytes":
+        assert len(b) == t[1]
+        return b
+    if k == "bytelist":
+        assert len(b) <= t[1]
+        return b
+    if k == "bitvector":
+        assert len(b) == (t[1] + 7) // 8
+        return [bool((b[i // 8] >> (i % 8)) & 1) for i in range(t[1])]
+    if k == "bitlist":
+        assert b and b[-1]
+        n = 8 * (len(b) - 1) + b[-1].bit_length() - 1
+        return [bool((b[i // 8] >> (i % 8)) & 1) for i in range(n)]
+    if k in ("vector", "list"):
+        et = t[1]
+        if is_fixed(et):
+            sz = fixed_size(et)
+            assert len(b) % sz == 0
+            return [deserialize(et, b[i:i + sz]) for i in range(0, len(b), sz)]
+        if not b:
+            return []
+        first = int.from_bytes(b[:4], "little")
+        offs = [int.from_bytes(b[4 * i:4 * i + 4], "little") for i in range(first // 4)] + [len(b)]
+        return [deserialize(et, b[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
+    # container
+    out, pos, var = {}, 0, []
+    for name, ft in t[1]:
+        if is_fixed(ft):
+            sz = fixed_size(ft)
+            out[name] = deserialize(ft, b[pos:pos + sz])
+            pos += sz
+        else:
+            var.append((name, ft, int.from_bytes(b[pos:pos + 4], "little")))
+            pos += 4
+    for i, (name, ft, off) in enumerate(var):
+        end = var[i + 1][2] if i + 1 < len(var) else len(b)
+        out[name] = deserialize(ft, b[off:end])
+    return out

@@ -83,3 +83,23 @@ def test_gpu_rejects_malformed_blocks(gpu):
         with pytest.raises(Lhb200Error) as e:
             tree_hash.beacon_block_root_deneb(b)
         assert e.value.code == EINVAL
+
+
+def test_oracle_block_root_random_shapes():
+    """Seeded sweep over block shapes (list lengths 0..limit, transaction sizes across chunk and tile boundaries,
+    committee sizes across bit-list byte boundaries): oracle == generic spec merkleization, and the generic decoder
+    round-trips the serialisation."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        kw = dict(seed=1000 + it, n_attestations=int(rng.integers(0, 129)), n_proposer_slashings=int(rng.integers(0, 17)),
+                  n_attester_slashings=int(rng.integers(0, 3)), n_deposits=int(rng.integers(0, 17)),
+                  n_exits=int(rng.integers(0, 17)), n_bls_changes=int(rng.integers(0, 17)),
+                  n_withdrawals=int(rng.integers(0, 17)), n_blobs=int(rng.integers(0, 7)),
+                  committee=int(rng.integers(1, 2049)), extra_data_len=int(rng.integers(0, 33)),
+                  tx_sizes=[int(x) for x in rng.choice([0, 1, 31, 32, 33, 63, 64, 65, 255, 256, 257, 1000, 8191, 8192, 8193, 40000],
+                                                       size=int(rng.integers(0, 40)))])
+        value, ssz = synthetic.beacon_block_deneb(**kw)
+        assert S.serialize(S.BeaconBlockDeneb, ssz_spec.deserialize(S.BeaconBlockDeneb, ssz)) == ssz
+        want = (ssz_spec.hash_tree_root(S.BeaconBlockDeneb, value), ssz_spec.hash_tree_root(S.BeaconBlockBodyDeneb, value["body"]))
+        assert O.beacon_block_root_deneb(ssz) == want, kw

@@ -102,3 +102,24 @@ def test_beacon_state_field_rules():
     bal += b"\0" * (-len(bal) % 32)
     assert fr[12] == hashlib.sha256(py_merkleize(bal, 38) + struct.pack("<Q", 300) + b"\0" * 24).digest()
     assert fr[17] == bytes([ssz[2687256]]) + b"\0" * 31
+
+
+@pytest.mark.parametrize("kw", [dict(n_validators=37, seed=3, n_hist_roots=5, n_votes=7, n_summaries=3),
+                                dict(n_validators=0, all_default=True),
+                                dict(n_validators=1, seed=4, n_hist_roots=0, n_votes=0, n_summaries=0, extra_data_len=0),
+                                dict(n_validators=1000, seed=9, extra_data_len=32)])
+def test_state_oracle_matches_generic_spec_merkleization(kw):
+    """Second, independent pin of the hand-unrolled BeaconStateDeneb oracle (the reference's own pin, EF ssz_static,
+    is not on disk): decode the synthetic SSZ with the generic decoder of tests/ssz_spec.py, re-serialise (must be
+    identical), and compare the root and ALL 28 field roots with the from-spec hashlib merkleization driven by the
+    type descriptors in lighthouse_b200/ssz_schema.py (beacon_state.rs:339-490)."""
+    from lighthouse_b200 import ssz_schema as S
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    from tests import ssz_spec
+    ssz = beacon_state_deneb_ssz(**kw)
+    value = ssz_spec.deserialize(S.BeaconStateDeneb, ssz)
+    assert S.serialize(S.BeaconStateDeneb, value) == ssz
+    want_fields = [ssz_spec.hash_tree_root(ft, value[name]) for name, ft in S.BeaconStateDeneb[1]]
+    root, fields = O.beacon_state_root_deneb(ssz)
+    assert list(fields) == want_fields
+    assert root == ssz_spec.hash_tree_root(S.BeaconStateDeneb, value)
