@@ -66,6 +66,38 @@ def verify_signature_sets_sharded(sigs, msgs, pks, offsets, verify_fn, device=No
     return allreduce_verdict(ok, device)
 
 
+def shard_ranges_by_bytes(sizes, world):
+    """Split items [0, n) into `world` contiguous ranges with ~equal byte totals (blocks differ a lot in size)."""
+    offs = np.concatenate([[0], np.cumsum(np.asarray(sizes, dtype=np.uint64))])
+    return shard_ranges_by_keys(offs, world)
+
+
+def beacon_block_roots_sharded(blocks, roots_fn=None, device=None):
+    """canonical_root of every BeaconBlockDeneb in `blocks` (BASELINE configs[3]: the 32 blocks of a chain segment over
+    the GPUs of one box): independent units, so each rank hashes a contiguous, byte-balanced slice in one pass and one
+    all-gather of 32 B x len(blocks) returns all roots, in order, on every rank.  `roots_fn(list of ssz) -> list of 32-byte
+    roots` defaults to the CUDA path (tree_hash.beacon_block_roots_deneb)."""
+    import torch
+    import torch.distributed as dist
+    if roots_fn is None:
+        from . import tree_hash as T
+        roots_fn = T.beacon_block_roots_deneb
+    n = len(blocks)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    ranges = shard_ranges_by_bytes([len(b) for b in blocks], world)
+    lo, hi = ranges[rank]
+    mine = roots_fn(blocks[lo:hi]) if hi > lo else []
+    if world == 1:
+        return [bytes(r) for r in mine]
+    buf = torch.zeros(32 * n, dtype=torch.uint8, device=device)   # every rank fills its own slots; sum == gather
+    if mine:
+        buf[32 * lo:32 * hi] = torch.tensor(list(b"".join(mine)), dtype=torch.uint8, device=device)
+    dist.all_reduce(buf.view(torch.int32) if buf.numel() % 4 == 0 else buf, op=dist.ReduceOp.SUM)
+    raw = bytes(buf.cpu().tolist())
+    return [raw[32 * i:32 * i + 32] for i in range(n)]
+
+
 def beacon_state_root_sharded(ssz, device=None):
     """hash_tree_root(BeaconStateDeneb) with the big lists sharded over the ranks of the default process group:
     per-rank subtree roots -> one all-gather (32 bytes x lists x ranks) -> every rank folds the top.  world must be

@@ -54,6 +54,11 @@ def _worker(rank, world, port, q):
     bad = parallel.verify_signature_sets_sharded(sigs, bytes(bad_msgs), pks, offs, verify)
     empty = parallel.verify_signature_sets_sharded(b"", b"", b"", np.array([0], dtype=np.uint32), verify)
     roots = parallel.allgather_roots(hashlib.sha256(bytes([rank])).digest())
+    # block roots: 5 blocks of very different sizes over 2 ranks, hashed by the CPU oracle here
+    from lighthouse_b200.synthetic import beacon_block_deneb
+    blocks = [beacon_block_deneb(seed=40 + i, n_attestations=3 * i, n_transactions=1 + 30 * (i % 2))[1] for i in range(5)]
+    block_roots = parallel.beacon_block_roots_sharded(blocks, roots_fn=lambda bs: [O.beacon_block_root_deneb(b)[0] for b in bs])
+    assert block_roots == [O.beacon_block_root_deneb(b)[0] for b in blocks]
     q.put((rank, good, bad, empty, roots))
     dist.destroy_process_group()
 
