@@ -27,8 +27,14 @@ LHB_HD LHB_INLINE void fp2_cmov(Fp2& r, const Fp2& a, bool c) { fp_cmov(r.c0, a.
 #ifdef LHB_FP_DECL_ONLY
 LHB_HD void fp2_add(Fp2& r, const Fp2& a, const Fp2& b);
 LHB_HD void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b);
+#ifdef LHB_FP2_ALIAS_LIGHT
+LHB_CONST Fp2 FP2_ZERO_C = {{{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}}, {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}}};
+LHB_HD LHB_INLINE void fp2_dbl(Fp2& r, const Fp2& a) { fp2_add(r, a, a); }
+LHB_HD LHB_INLINE void fp2_neg(Fp2& r, const Fp2& a) { fp2_sub(r, FP2_ZERO_C, a); }
+#else
 LHB_HD void fp2_dbl(Fp2& r, const Fp2& a);
 LHB_HD void fp2_neg(Fp2& r, const Fp2& a);
+#endif
 LHB_HD void fp2_conj(Fp2& r, const Fp2& a);
 LHB_HD void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b);
 LHB_HD void fp2_sqr(Fp2& r, const Fp2& a);
@@ -57,6 +63,12 @@ LHB_HD LHB_NOINLINE void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) {
     fp_sub_inl(o.c1, x.c1, y.c1);
     r = o;
 }
+#ifdef LHB_FP2_ALIAS_LIGHT
+// fewer distinct leaf bodies in the instruction cache: 2a = a + a, -a = 0 - a
+LHB_CONST Fp2 FP2_ZERO_C = {{{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}}, {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}}};
+LHB_HD LHB_INLINE void fp2_dbl(Fp2& r, const Fp2& a) { fp2_add(r, a, a); }
+LHB_HD LHB_INLINE void fp2_neg(Fp2& r, const Fp2& a) { fp2_sub(r, FP2_ZERO_C, a); }
+#else
 LHB_HD LHB_NOINLINE void fp2_dbl(Fp2& r, const Fp2& a) {
     Fp2 x = a, o;
     fp_add_inl(o.c0, x.c0, x.c0);
@@ -69,6 +81,7 @@ LHB_HD LHB_NOINLINE void fp2_neg(Fp2& r, const Fp2& a) {
     fp_neg(o.c1, x.c1);
     r = o;
 }
+#endif
 LHB_HD LHB_NOINLINE void fp2_conj(Fp2& r, const Fp2& a) {
     Fp2 x = a, o;
     o.c0 = x.c0;
@@ -104,7 +117,25 @@ struct FpW {
     uint32_t v[2 * NL];
 };
 LHB_HD LHB_INLINE FpW fp_mulw_rr(Fp a, Fp b) { FpW o; fp_mulw_inl(o.v, a, b); return o; }
-LHB_HD LHB_INLINE Fp fp_redc_rr(FpW w) { Fp o; fp_redc_inl(o, w.v); return o; }
+#ifdef LHB_FP2_LAZY_SHARED_REDC
+// the reduction as ONE shared body; the 768-bit value travels as two 12-limb register arguments (like fp_mul_rr's)
+LHB_HD LHB_NOINLINE Fp fp_redc_rr2(Fp lo, Fp hi) {
+    uint32_t w[2 * NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) { w[i] = lo.v[i]; w[NL + i] = hi.v[i]; }
+    Fp o;
+    fp_redc_inl(o, w);
+    return o;
+}
+LHB_HD LHB_INLINE Fp fp_redc_rr(const FpW& w) {
+    Fp lo, hi;
+#pragma unroll
+    for (int i = 0; i < NL; i++) { lo.v[i] = w.v[i]; hi.v[i] = w.v[NL + i]; }
+    return fp_redc_rr2(lo, hi);
+}
+#else
+LHB_HD LHB_INLINE Fp fp_redc_rr(const FpW& w) { Fp o; fp_redc_inl(o, w.v); return o; }
+#endif
 LHB_HD LHB_NOINLINE void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
     FpW w0, w1, w2;
     { Fp p = a.c0, q = b.c0; w0 = fp_mulw_rr(p, q); }
