@@ -167,16 +167,14 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate_indexed(const G1Mont
 }
 
 __global__ void __launch_bounds__(BLS_BLOCK) k_hash_to_g2(const uint8_t* __restrict__ msgs, uint32_t n,
-                                                           G2Affine* __restrict__ out_h) {
+                                                           G2Jac* __restrict__ out_h) {
     // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         __align__(16) uint8_t m[32];
         load_bytes16(m, msgs + 32ull * i, 32);
         G2Jac j;
         hash_to_g2_jac(j, m);
-        G2Affine a;
-        jac_to_affine(a, j);
-        out_h[i] = a;
+        out_h[i] = j;   // stays Jacobian: the Miller loop's addition steps take a projective Q (no inversion here)
     }
 }
 
@@ -197,7 +195,7 @@ __global__ void __launch_bounds__(MILLER_BLOCK) k_miller(const G1Proj3* __restri
 
 // Group g = sets [g*k, (g+1)*k): one thread runs their Miller loops with shared squarings; out_f[g] = the product.
 // The host picks k = ceil(n / resident threads) so that every resident thread gets one group (no partial last wave).
-__global__ void __launch_bounds__(MILLER_BLOCK) k_miller_multi(const G1Proj3* __restrict__ P, const G2Affine* __restrict__ H,
+__global__ void __launch_bounds__(MILLER_BLOCK) k_miller_multi(const G1Proj3* __restrict__ P, const G2Jac* __restrict__ H,
                                                              const uint8_t* __restrict__ status, uint32_t n, uint32_t k,
                                                              uint32_t n_groups, Fp12* __restrict__ out_f) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
@@ -205,7 +203,7 @@ __global__ void __launch_bounds__(MILLER_BLOCK) k_miller_multi(const G1Proj3* __
         int m = 0;
         for (uint32_t j = 0; j < k; j++) {
             const uint32_t i = g * k + j;
-            if (i < n && status[i] == SET_OK && !H[i].inf) idx[m++] = i;
+            if (i < n && status[i] == SET_OK && !jac_is_inf(H[i])) idx[m++] = i;
         }
         Fp12 f;
         if (m == 0) fp12_set_one(f);

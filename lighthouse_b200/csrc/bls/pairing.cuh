@@ -134,14 +134,67 @@ LHB_HD LHB_NOINLINE void miller_loop(Fp12& f, const G1Proj3& P, const G2Affine& 
     fp12_conj(f, f);
 }
 
+// Addition step with Q in JACOBIAN coordinates (X2, Y2, Z2): T <- T + Q (general addition, add-2007-bl) and the line
+// through T and Q.  With lambda = r / Z3 (r = 2(S2 - S1), Z3 = 2 Z1 Z2 H) and x_Q = X2/Z2^2, y_Q = Y2/Z2^3, the line
+// scaled by Z3 Z2^3 (an Fp2 factor, killed by the final exponentiation) is
+//     c0 = r X2 Z2 - Y2 Z3 ,   c1 = -(r Z2^3) x_P ,   c4 = (Z3 Z2^3) y_P          [times pz for a projective P].
+// This lets hash_to_G2 hand its result over without the to-affine inversion (one Fp exponentiation per set).
+LHB_HD LHB_NOINLINE void miller_add_step_jac(G2Jac& T, Fp2& c0, Fp2& c1, Fp2& c4, const G2Jac& Q, const G1Proj3& P) {
+    Fp2 Z1Z1, Z2Z2, Z2c, U1, U2, S1, S2, H, I, J, rr, V, t, Z3, X3;
+    fp2_sqr(Z1Z1, T.Z);
+    fp2_sqr(Z2Z2, Q.Z);
+    fp2_mul(Z2c, Z2Z2, Q.Z);          // Z2^3
+    fp2_mul(U1, T.X, Z2Z2);
+    fp2_mul(U2, Q.X, Z1Z1);
+    fp2_mul(S1, T.Y, Z2c);
+    fp2_mul(S2, Q.Y, T.Z);
+    fp2_mul(S2, S2, Z1Z1);
+    fp2_sub(H, U2, U1);
+    fp2_sub(rr, S2, S1);
+    fp2_add(rr, rr, rr);
+    fp2_add(I, H, H);
+    fp2_sqr(I, I);
+    fp2_mul(J, H, I);
+    fp2_mul(V, U1, I);
+    fp2_add(t, T.Z, Q.Z);
+    fp2_sqr(t, t);
+    fp2_sub(t, t, Z1Z1);
+    fp2_sub(t, t, Z2Z2);
+    fp2_mul(Z3, t, H);
+    fp2_sqr(t, rr);
+    fp2_sub(t, t, J);
+    fp2_sub(t, t, V);
+    fp2_sub(X3, t, V);
+    fp2_sub(t, V, X3);
+    fp2_mul(t, rr, t);
+    fp2_mul(J, S1, J);
+    fp2_add(J, J, J);
+    fp2_sub(T.Y, t, J);
+    T.X = X3;
+    T.Z = Z3;
+    // line
+    fp2_mul(t, Q.X, Q.Z);
+    fp2_mul(c0, rr, t);
+    fp2_mul(t, Q.Y, Z3);
+    fp2_sub(c0, c0, t);
+    fp2_mul(c1, rr, Z2c);
+    fp2_neg(c1, c1);
+    fp2_mul(c4, Z3, Z2c);
+    fp2_mul_fp(c0, c0, P.pz);
+    fp2_mul_fp(c1, c1, P.px);
+    fp2_mul_fp(c4, c4, P.py);
+}
+
 // Multi-pairing Miller loop: prod_j f_{|x|,Q_j}(P_j) for m <= MILLER_KMAX pairs with ONE Fp12 squaring per bit shared by
 // all of them ((prod f_j)^2 prod l_j == prod (f_j^2 l_j) exactly in Fp12) — the shape of blst's miller_loop_n behind
-// verify_multiple_aggregate_signatures (crypto/bls/src/impls/blst.rs:114-118).  P and Q are read in place.
+// verify_multiple_aggregate_signatures (crypto/bls/src/impls/blst.rs:114-118).  P and Q are read in place; Q is
+// Jacobian (what hash_to_G2 produces), so the value equals the affine loop's up to Fp2 factors the final
+// exponentiation kills.
 constexpr int MILLER_KMAX = 4;
-LHB_HD LHB_NOINLINE void miller_loop_multi(Fp12& f, const G1Proj3* P, const G2Affine* Q, const uint32_t* idx, int m) {
+LHB_HD LHB_NOINLINE void miller_loop_multi(Fp12& f, const G1Proj3* P, const G2Jac* Q, const uint32_t* idx, int m) {
     G2Jac T[MILLER_KMAX];
 #pragma unroll 1
-    for (int j = 0; j < m; j++) jac_from_affine(T[j], Q[idx[j]]);
+    for (int j = 0; j < m; j++) T[j] = Q[idx[j]];
     Fp2 c0, c1, c4;
 #pragma unroll 1
     for (int i = 62; i >= 0; i--) {
@@ -159,7 +212,7 @@ LHB_HD LHB_NOINLINE void miller_loop_multi(Fp12& f, const G1Proj3* P, const G2Af
         if ((BLS_X_ABS >> i) & 1) {
 #pragma unroll 1
             for (int j = 0; j < m; j++) {
-                miller_add_step(T[j], c0, c1, c4, Q[idx[j]], P[idx[j]]);
+                miller_add_step_jac(T[j], c0, c1, c4, Q[idx[j]], P[idx[j]]);
                 fp12_mul_by_014(f, f, c0, c1, c4);
             }
         }

@@ -52,7 +52,7 @@ struct lhb200_bls_batch {
     G2Jac* d_sigr = nullptr;      // r_i * sig_i
     G2Jac* d_sig_tmp[2] = {nullptr, nullptr};
     G1Proj3* d_p = nullptr;       // r_i * apk_i (projective evaluation point)
-    G2Affine* d_h = nullptr;      // H(m_i)
+    G2Jac* d_h = nullptr;         // H(m_i), Jacobian
     Fp12* d_f = nullptr;          // Miller loop values
     Fp12* d_f_tmp[2] = {nullptr, nullptr};
     Fp12* d_flast = nullptr;
@@ -134,7 +134,7 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     ALLOC(b->d_sig_tmp[0], n1 * sizeof(G2Jac));
     ALLOC(b->d_sig_tmp[1], n2 * sizeof(G2Jac));
     ALLOC(b->d_p, n * sizeof(G1Proj3));
-    ALLOC(b->d_h, n * sizeof(G2Affine));
+    ALLOC(b->d_h, n * sizeof(G2Jac));
     ALLOC(b->d_f, n * sizeof(Fp12));
     ALLOC(b->d_f_tmp[0], n1 * sizeof(Fp12));
     ALLOC(b->d_f_tmp[1], n2 * sizeof(Fp12));

@@ -135,20 +135,26 @@ EXPORT int hs_pairing(const uint8_t* p96, const uint8_t* q96, int do_final, int 
     fp12_out(out576, f);
     return 0;
 }
-// m pairs (P_j uncompressed G1, Q_j compressed G2): out_multi = miller_loop_multi, out_prod = product of single loops
+// m pairs (P_j uncompressed G1, Q_j compressed G2).  The multi-pairing loop gets Q_j in Jacobian form with Z != 1
+// (tripled and rescaled representative of the same point); out_multi = final_exp(miller_loop_multi),
+// out_prod = final_exp(product of the single affine loops): equal although the raw Miller values differ by Fp2 factors.
 EXPORT int hs_miller_multi(const uint8_t* p96, const uint8_t* q96, int m, uint8_t* out_multi, uint8_t* out_prod) {
-    G1Proj3 P[MILLER_KMAX]; G2Affine Q[MILLER_KMAX]; uint32_t idx[MILLER_KMAX];
+    G1Proj3 P[MILLER_KMAX]; G2Affine Q[MILLER_KMAX]; G2Jac QJ[MILLER_KMAX]; uint32_t idx[MILLER_KMAX];
     if (m < 1 || m > MILLER_KMAX) return -2;
     for (int j = 0; j < m; j++) {
         G1Affine p;
         if (g1_from_uncompressed(p, p96 + 96 * j) != DEC_OK || g2_decompress(Q[j], q96 + 96 * j) != DEC_OK) return -1;
         G1Jac jj; jac_from_affine(jj, p); jac_dbl(jj, jj); g1proj3_from_jac(P[j], jj);
+        // same point, non-trivial Z: (X s^2, Y s^3, s) with s taken from the point's own coordinates
+        Fp2 s = Q[j].x, s2, s3; fp2_add(s, s, Q[j].y); fp2_sqr(s2, s); fp2_mul(s3, s2, s);
+        fp2_mul(QJ[j].X, Q[j].x, s2); fp2_mul(QJ[j].Y, Q[j].y, s3); QJ[j].Z = s;
         idx[j] = (uint32_t)(m - 1 - j);  // permuted on purpose: the index list need not be sorted
     }
     Fp12 f, g, t;
-    miller_loop_multi(f, P, Q, idx, m);
+    miller_loop_multi(f, P, QJ, idx, m);
     miller_loop(g, P[0], Q[0]);
     for (int j = 1; j < m; j++) { miller_loop(t, P[j], Q[j]); fp12_mul(g, g, t); }
+    final_exp(f, f); final_exp(g, g);
     fp12_out(out_multi, f); fp12_out(out_prod, g);
     return 0;
 }

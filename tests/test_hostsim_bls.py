@@ -204,7 +204,8 @@ def test_pairing_and_verify(L):
         assert L.hs_pairing(B.g1_uncompressed(Pt), B.g2_compress(Q), 1, proj, out) == 0
         ref = B.pairing(B.g1_add(Pt, Pt) if proj else Pt, Q)
         assert f12_from(out.raw) == B.f12_mul(B.f12_sqr(ref), ref)
-    # multi-pairing Miller loop with shared squarings == product of the single loops, limb for limb
+    # multi-pairing Miller loop (shared squarings, Jacobian Q with Z != 1) == product of the single affine loops after
+    # the final exponentiation, limb for limb
     for m in (1, 2, 3, 4):
         ps = b"".join(B.g1_uncompressed(B.g1_mul(B.G1_GEN, 1000 + 7 * j)) for j in range(m))
         qs = b"".join(B.g2_compress(B.g2_mul(B.G2_GEN, 55 + 3 * j)) for j in range(m))
