@@ -45,6 +45,13 @@ EXPORT void hs_mont_mul_split(const uint32_t* a, const uint32_t* b, uint32_t* ou
     fp_mulw_inl(w, x, y); fp_redc_inl(o, w);
     for (int i = 0; i < 12; i++) out[i] = o.v[i];
 }
+// dedicated squaring on raw Montgomery limbs
+EXPORT void hs_mont_sqr(const uint32_t* a, uint32_t* out) {
+    Fp x, o;
+    for (int i = 0; i < 12; i++) x.v[i] = a[i];
+    fp_sqr_inl(o, x);
+    for (int i = 0; i < 12; i++) out[i] = o.v[i];
+}
 EXPORT int hs_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     Fp2 x, y, r; fp2_in(x, a); fp2_in(y, b);
     int ok = 1;

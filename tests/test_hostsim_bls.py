@@ -71,6 +71,22 @@ def test_split_multiplier_matches_montgomery_product(L):
         assert got == a * b * Rinv % P, (hex(a), hex(b))
 
 
+def test_dedicated_squaring_matches_product(L):
+    """fp_sqr_inl (66 doubled cross products + 12 squares, then the split reduction) == a a R^-1 mod p on raw limbs."""
+    rnd = random.Random(11)
+    R = 1 << 384
+    Rinv = pow(R, -1, P)
+    vals = [0, 1, 2, P - 1, P - 2, (1 << 383) % P, ((1 << 384) - 1) % P, 0xffffffff, (1 << 352) - 1]
+    vals += [rnd.randrange(P) for _ in range(400)]
+    vals += [int("f" * 95, 16) % P, sum(0xffffffff << (64 * i) for i in range(6)) % P]
+    for a in vals:
+        inp = (C.c_uint32 * 12)(*[(a >> (32 * i)) & 0xffffffff for i in range(12)])
+        out = (C.c_uint32 * 12)()
+        L.hs_mont_sqr(inp, out)
+        got = sum(int(out[i]) << (32 * i) for i in range(12))
+        assert got == a * a * Rinv % P, hex(a)
+
+
 def test_fp2_ops(L):
     rnd = random.Random(2)
     def op(o, a, b=(0, 0)):
