@@ -354,12 +354,18 @@ LHB_HD void fp_mul(Fp& r, const Fp& a, const Fp& b);
 #else
 LHB_HD LHB_NOINLINE void fp_mul(Fp& r, const Fp& a, const Fp& b) { Fp x = a, y = b, o; fp_mul_inl(o, x, y); r = o; }
 #endif
-// Dedicated squaring leaf (fp_sqrw_inl + the split reduction): 234 multiply instructions instead of 300.  The Fp
-// exponentiations of decompression and hash-to-curve (6 per set, 380 squarings each) and the G1 doublings use it.
+// EXPERIMENT (-DLHB_FP_DEDICATED_SQR, not shipped — DESIGN.md §9): a dedicated squaring leaf (fp_sqrw_inl + the split
+// reduction) has 208 multiply instructions instead of 276, but its short, strictly ordered carry chains (rows of
+// 11..1 cross products, the doubling, one 24-limb chain of squares) give ptxas much less to interleave than the fused
+// product rows: a 100 k-set verify went from 91.0 to 94.4 ms with it.
+#ifdef LHB_FP_DEDICATED_SQR
 #ifdef LHB_FP_DECL_ONLY
 LHB_HD void fp_sqr(Fp& r, const Fp& a);
 #else
 LHB_HD LHB_NOINLINE void fp_sqr(Fp& r, const Fp& a) { Fp x = a, o; fp_sqr_inl(o, x); r = o; }
+#endif
+#else
+LHB_HD LHB_INLINE void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
 #endif
 
 LHB_HD LHB_INLINE void fp_to_mont(Fp& r, const Fp& a) { fp_mul(r, a, FP_R2); }
