@@ -7,7 +7,7 @@
 //   k_sig_prepare ...... K10 g2_decompress + K4 subgroup check + K7 r*sig        (blst.rs:73-83, :114)
 //   k_pk_aggregate ..... K5 segmented G1 sum over CSR offsets + K7 r*apk          (blst.rs:86-106, :114)
 //   k_hash_to_g2 ....... K6 hash_to_curve                                         (blst.rs:114, DST :15)
-//   k_miller ........... K8 one Miller loop per set
+//   k_miller_multi ..... K8 Miller loops, k sets per thread sharing the Fp12 squarings
 //   k_fp12_reduce / k_g2_reduce ... product / sum trees
 //   k_final ............ K8 Miller loop for (-g1, sum r*sig) + K9 final exponentiation and == 1
 #pragma once
@@ -31,7 +31,7 @@ constexpr int BLS_BLOCK = 64;
 #ifndef LHB_MILLER_BLOCK
 #define LHB_MILLER_BLOCK 64
 #endif
-constexpr int MILLER_BLOCK = LHB_MILLER_BLOCK;  // k_miller's residency knob (its 3.5 KB/thread stack vs the 126 MB L2)
+constexpr int MILLER_BLOCK = LHB_MILLER_BLOCK;  // k_miller_multi's block size (its 4.5 KB/thread stack vs the 126 MB L2)
 
 __device__ __forceinline__ void load_bytes16(uint8_t* dst, const uint8_t* src, int nbytes) {
     // src is 16-byte aligned; nbytes multiple of 16
@@ -178,21 +178,6 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_hash_to_g2(const uint8_t* __restr
     }
 }
 
-__global__ void __launch_bounds__(MILLER_BLOCK) k_miller(const G1Proj3* __restrict__ P, const G2Affine* __restrict__ H,
-                                                       const uint8_t* __restrict__ status, uint32_t n,
-                                                       Fp12* __restrict__ out_f) {
-    // grid-stride: the host caps resident CTAs per SM so the per-thread stacks stay cache-resident
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Fp12 f;
-        if (status[i] != SET_OK || H[i].inf) {
-            fp12_set_one(f);
-        } else {
-            miller_loop(f, P[i], H[i]);   // operands are read in place (no 352-byte private copies)
-        }
-        out_f[i] = f;
-    }
-}
-
 // Group g = sets [g*k, (g+1)*k): one thread runs their Miller loops with shared squarings; out_f[g] = the product.
 // The host picks k = ceil(n / resident threads) so that every resident thread gets one group (no partial last wave).
 __global__ void __launch_bounds__(MILLER_BLOCK) k_miller_multi(const G1Proj3* __restrict__ P, const G2Jac* __restrict__ H,
@@ -240,7 +225,7 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_g2_reduce(const G2Jac* __restrict
     out[t] = acc;
 }
 
-// f_last = Miller(-g1, S) for the aggregated signature term; runs concurrently with k_miller.
+// f_last = Miller(-g1, S) for the aggregated signature term; runs concurrently with k_miller_multi.
 __global__ void k_last_miller(const G2Jac* __restrict__ sig_sum, Fp12* __restrict__ out_f) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     G2Jac s = *sig_sum;

@@ -64,7 +64,7 @@ struct lhb200_bls_batch {
     cudaStream_t s2 = nullptr, s3 = nullptr;
     cudaEvent_t e_h2c = nullptr, e_sig = nullptr;
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
-    cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller), for the roofline
+    cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller_multi), for the roofline
     uint64_t launches_last = 0;
     // streamed key upload (lhb200_bls_batch_upload_async): the key copy is cut into chunks of whole sets on its own
     // stream; k_pk_aggregate runs per chunk as it lands while the signature / hash-to-curve kernels already compute
@@ -73,7 +73,6 @@ struct lhb200_bls_batch {
     cudaStream_t s_pk[N_PK_STREAMS] = {};    // high priority: chunk c is copied AND aggregated on s_pk[c % 4]
     cudaEvent_t e_pk[N_PK_STREAMS] = {};
     cudaEvent_t e_small = nullptr, e_copy_free = nullptr;
-    cudaEvent_t e_chunk[MAX_CHUNKS] = {};
     uint32_t chunk_lo[MAX_CHUNKS + 1] = {};  // set ranges
     uint64_t chunk_key[MAX_CHUNKS + 1] = {}; // key ranges
     const uint8_t* h_pks = nullptr;          // caller's host keys (valid until result)
@@ -104,8 +103,6 @@ static void batch_free(lhb200_bls_batch* b) {
         if (e) cudaEventDestroy(e);
     if (b->e_small) cudaEventDestroy(b->e_small);
     if (b->e_copy_free) cudaEventDestroy(b->e_copy_free);
-    for (cudaEvent_t e : b->e_chunk)
-        if (e) cudaEventDestroy(e);
     delete b;
 }
 
@@ -158,11 +155,6 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
         batch_free(b);
         return cuda_fail(e, "stream/event create");
     }
-    for (cudaEvent_t& ev : b->e_chunk)
-        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
-            batch_free(b);
-            return cuda_fail(e, "event create");
-        }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the key chunks must not queue behind the 1563-CTA kernels
     for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++)
@@ -468,7 +460,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     } else
         k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
-    LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller reads the status bytes k_sig_prepare may set
+    LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller_multi reads the status bytes k_sig_prepare may set
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
     // Sets per thread: k = ceil(n / resident threads) (<= MILLER_KMAX) share their Fp12 squarings in one thread, so a
     // 100 k batch is ONE wave of 3-set groups instead of three waves of single Miller loops.  LHB_MILLER_K overrides.
@@ -577,7 +569,7 @@ int32_t lhb200_bls_batch_gt(lhb200_bls_batch* b, uint8_t out576[576]) {
 
 uint64_t lhb200_bls_batch_launches(const lhb200_bls_batch* b) { return b ? b->launches_last : 0; }
 
-// Device time (ms, CUDA events on the launching stream) of the dominant kernel k_miller in the last completed
+// Device time (ms, CUDA events on the launching stream) of the dominant kernel k_miller_multi in the last completed
 // enqueue; negative if unavailable.  Call after the stream has been synchronised.
 float lhb200_bls_batch_dominant_kernel_ms(const lhb200_bls_batch* b) {
     float ms = -1.f;
