@@ -24,6 +24,23 @@ def test_header_symbols_exported():
         assert hasattr(lib, s), f"{s} declared in lhb200.h but not exported"
 
 
+def test_python_binding_covers_the_header():
+    """Every entry point of include/lhb200.h has a typed ctypes signature in lighthouse_b200/_ffi.py (the binding the
+    parity tests call through), and every new compute entry point refuses to run without a device."""
+    from lighthouse_b200 import _ffi
+    for s in declared_symbols():
+        f = getattr(_ffi.lib, s)
+        assert f.argtypes is not None, f"{s} has no ctypes signature in _ffi.py"
+    import torch
+    if not torch.cuda.is_available():
+        out = ctypes.create_string_buffer(64)
+        offs = (ctypes.c_uint64 * 2)(0, 84)
+        assert _ffi.lib.lhb200_beacon_block_roots_deneb(b"\0" * 84, ctypes.cast(offs, ctypes.c_void_p), 1, out, None) == _ffi.ENODEV
+        arr = (ctypes.c_uint64 * 4)(0, 1, 2, 3)
+        assert _ffi.lib.lhb200_shuffle_list(ctypes.cast(arr, ctypes.c_void_p), 4, 90, b"\0" * 32, 0,
+                                            ctypes.cast(arr, ctypes.c_void_p)) == _ffi.ENODEV
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
