@@ -144,6 +144,10 @@ LHB200_API int32_t lhb200_verify_merkle_proofs(const uint8_t* leaves, const uint
 LHB200_API int32_t lhb200_beacon_block_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* body_root);
 LHB200_API int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n,
                                                    uint8_t* roots, uint8_t* body_roots);
+/* Same for BlindedBeaconBlockDeneb SSZ (BlindedBeaconBlock, consensus/types/src/beacon_block.rs:80; the body carries
+ * the ExecutionPayloadHeaderDeneb, execution_payload_header.rs:46-87).  The root equals the full block's root. */
+LHB200_API int32_t lhb200_blinded_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n,
+                                                           uint8_t* roots, uint8_t* body_roots);
 
 /* swap_or_not_shuffle::shuffle_list (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79-160):
  * out = shuffle (forwards != 0) or un-shuffle (forwards == 0, the direction the spec uses for committees) of the n

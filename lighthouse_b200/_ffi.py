@@ -118,3 +118,4 @@ _sig("lhb200_bls_batch_upload_async", C.c_int32, vp, vp, vp, vp, vp, vp, C.c_uin
 _sig("lhb200_state_enable_incremental", C.c_int32, vp)
 _sig("lhb200_state_last_root_hashes", C.c_uint64, vp)
 _sig("lhb200_state_patch_batch", C.c_int32, vp, vp, vp, vp, C.c_uint32)
+_sig("lhb200_blinded_beacon_block_roots_deneb", C.c_int32, vp, vp, C.c_uint32, vp, vp)

@@ -1276,6 +1276,7 @@ struct BlockDescriber {
     const uint8_t* s;
     const uint8_t* d;
     bool bad = false;
+    bool blinded = false;   // BlindedBeaconBlock: field 9 of the body is an ExecutionPayloadHeaderDeneb
 
     uint64_t u64(uint64_t off) { return p.literal_bytes(s + off, 8); }
     uint64_t h256(uint64_t off) { return p.literal_bytes(s + off, 32); }
@@ -1365,6 +1366,20 @@ struct BlockDescriber {
         f[15] = u64(off + 512); f[16] = u64(off + 520);
         return p.container(f);
     }
+    // ExecutionPayloadHeaderDeneb (execution_payload_header.rs:46-87): 584-byte fixed part + extra_data
+    uint64_t payload_header(uint64_t off, uint64_t len) {
+        if (len < 584 || len > 584 + 32 || rd32(s + off + 436) != 584) { bad = true; return 0; }
+        std::vector<uint64_t> f(17);
+        f[0] = h256(off); f[1] = addr20(off + 32); f[2] = h256(off + 52); f[3] = h256(off + 84);
+        f[4] = blob(off + 116, 256, 3);
+        f[5] = h256(off + 372); f[6] = u64(off + 404); f[7] = u64(off + 412); f[8] = u64(off + 420); f[9] = u64(off + 428);
+        f[10] = p.bytes_item(d + off + 584, len - 584, 0, true, len - 584);
+        f[11] = h256(off + 440); f[12] = h256(off + 472);
+        f[13] = h256(off + 504);            // transactions_root
+        f[14] = h256(off + 536);            // withdrawals_root
+        f[15] = u64(off + 568); f[16] = u64(off + 576);
+        return p.container(f);
+    }
     uint64_t body(uint64_t off, uint64_t len, uint64_t dst) {
         if (len < 392) { bad = true; return 0; }
         const uint32_t o_ps = rd32(s + off + 200), o_as = rd32(s + off + 204), o_at = rd32(s + off + 208),
@@ -1398,7 +1413,7 @@ struct BlockDescriber {
         f[6] = fixed_list(off + o_dp, o_ex - o_dp, 1240, 4, [&](uint64_t o) { return deposit(o); });
         f[7] = fixed_list(off + o_ex, o_ep - o_ex, 112, 4, [&](uint64_t o) { return voluntary_exit(o); });
         f[8] = p.op_hash(blob(off + 220, 64, 1), sig(off + 284));  // sync_aggregate.rs:38
-        f[9] = payload(off + o_ep, o_bc - o_ep);
+        f[9] = blinded ? payload_header(off + o_ep, o_bc - o_ep) : payload(off + o_ep, o_bc - o_ep);
         f[10] = fixed_list(off + o_bc, o_kz - o_bc, 172, 4, [&](uint64_t o) { return bls_change(o); });
         f[11] = fixed_list(off + o_kz, len - o_kz, 48, 12, [&](uint64_t o) { return pubkey(o); });  // kzg_commitment.rs:51
         if (bad) return 0;
@@ -1415,8 +1430,8 @@ struct BlockDescriber {
 extern "C" {
 
 // n BeaconBlockDeneb SSZ blobs, concatenated; offsets[n+1]; roots n*32; body_roots n*32 or NULL.
-int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
-                                        uint8_t* body_roots) {
+static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
+                                 uint8_t* body_roots, bool blinded) {
     LHB_REQUIRE_READY();
     if (!ssz || !offsets || !roots || n == 0) { set_error("beacon_block_roots: null argument or zero blocks"); return LHB200_EINVAL; }
     for (uint32_t i = 0; i < n; i++)
@@ -1435,6 +1450,7 @@ int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offs
         p.forced_base = reinterpret_cast<uint64_t>(d_roots);
         p.forced_wave.assign(2ull * n, -1);
         BlockDescriber bd{p, ssz + base, d_in};
+        bd.blinded = blinded;
         for (uint32_t i = 0; i < n && !bd.bad; i++)
             bd.block(offsets[i] - base, offsets[i + 1] - offsets[i], reinterpret_cast<uint64_t>(d_roots + 32ull * i),
                      reinterpret_cast<uint64_t>(d_body + 32ull * i));
@@ -1477,9 +1493,18 @@ int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offs
     if (body_roots) memcpy(body_roots, h_out + 32ull * n, 32ull * n);
     return LHB200_OK;
 }
+int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
+                                        uint8_t* body_roots) {
+    return block_roots_deneb(ssz, offsets, n, roots, body_roots, false);
+}
 int32_t lhb200_beacon_block_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* body_root) {
     const uint64_t offs[2] = {0, len};
-    return lhb200_beacon_block_roots_deneb(ssz, offs, 1, out, body_root);
+    return block_roots_deneb(ssz, offs, 1, out, body_root, false);
+}
+// BlindedBeaconBlock (beacon_block.rs:80): the body carries the ExecutionPayloadHeader; the root equals the full block's.
+int32_t lhb200_blinded_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
+                                                uint8_t* body_roots) {
+    return block_roots_deneb(ssz, offsets, n, roots, body_roots, true);
 }
 
 // swap_or_not_shuffle::shuffle_list(input, rounds, seed, forwards) (consensus/swap_or_not_shuffle/src/shuffle_list.rs:79).

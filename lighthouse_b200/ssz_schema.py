@@ -154,3 +154,10 @@ BeaconStateDeneb = C(
     ("current_sync_committee", SyncCommittee), ("next_sync_committee", SyncCommittee),
     ("latest_execution_payload_header", ExecutionPayloadHeaderDeneb), ("next_withdrawal_index", U64),
     ("next_withdrawal_validator_index", U64), ("historical_summaries", ("list", HistoricalSummary, 1 << 24)))
+
+
+# BlindedBeaconBlock (beacon_block.rs:80; payload.rs BlindedPayload): the body carries the payload HEADER
+BlindedBeaconBlockBodyDeneb = C(*[(n, ExecutionPayloadHeaderDeneb) if n == "execution_payload" else (n, t)
+                                 for n, t in BeaconBlockBodyDeneb[1]])
+BlindedBeaconBlockDeneb = C(("slot", U64), ("proposer_index", U64), ("parent_root", B32), ("state_root", B32),
+                            ("body", BlindedBeaconBlockBodyDeneb))

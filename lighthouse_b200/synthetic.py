@@ -242,3 +242,16 @@ def beacon_block_deneb(seed=1, n_attestations=128, n_transactions=150, n_propose
     block = {"slot": u64(), "proposer_index": u64() % 500_000, "parent_root": rb(32), "state_root": rb(32),
              "body": body}
     return block, S.serialize(S.BeaconBlockDeneb, block)
+
+
+def blind_block_deneb(block, transactions_root: bytes, withdrawals_root: bytes):
+    """BlindedBeaconBlockDeneb value + SSZ of `block` (as produced by beacon_block_deneb) given the two list roots
+    of its payload (computed by whoever has a hasher: the CUDA library, the oracle or the spec restatement)."""
+    import copy
+    from . import ssz_schema as S
+    v = copy.deepcopy(block)
+    p = v["body"]["execution_payload"]
+    hdr = {k: p[k] for k in p if k not in ("transactions", "withdrawals")}
+    hdr["transactions_root"], hdr["withdrawals_root"] = transactions_root, withdrawals_root
+    v["body"]["execution_payload"] = {n: hdr[n] for n, _ in S.ExecutionPayloadHeaderDeneb[1]}
+    return v, S.serialize(S.BlindedBeaconBlockDeneb, v)

@@ -116,8 +116,9 @@ def beacon_state_root_deneb(ssz, want_field_roots=False):
     return out.raw
 
 
-def beacon_block_roots_deneb(blocks, want_body_roots=False):
-    """BeaconBlock::canonical_root (beacon_block.rs:158-160) of a batch of BeaconBlockDeneb SSZ blobs in one pass."""
+def beacon_block_roots_deneb(blocks, want_body_roots=False, blinded=False):
+    """BeaconBlock::canonical_root (beacon_block.rs:158-160) of a batch of BeaconBlockDeneb SSZ blobs in one pass
+    (blinded=True: BlindedBeaconBlockDeneb blobs, whose body carries the payload header)."""
     blocks = [bytes(b) for b in blocks]
     n = len(blocks)
     offs = (C.c_uint64 * (n + 1))()
@@ -126,16 +127,17 @@ def beacon_block_roots_deneb(blocks, want_body_roots=False):
     p, keep = buf(b"".join(blocks))
     out = C.create_string_buffer(32 * max(n, 1))
     body = C.create_string_buffer(32 * max(n, 1)) if want_body_roots else None
-    check(lib.lhb200_beacon_block_roots_deneb(p, C.cast(offs, C.c_void_p), n, out, body), "lhb200_beacon_block_roots_deneb")
+    fn = lib.lhb200_blinded_beacon_block_roots_deneb if blinded else lib.lhb200_beacon_block_roots_deneb
+    check(fn(p, C.cast(offs, C.c_void_p), n, out, body), "lhb200_beacon_block_roots_deneb")
     roots = [out.raw[32 * i: 32 * i + 32] for i in range(n)]
     if want_body_roots:
         return roots, [body.raw[32 * i: 32 * i + 32] for i in range(n)]
     return roots
 
 
-def beacon_block_root_deneb(ssz, want_body_root=False):
+def beacon_block_root_deneb(ssz, want_body_root=False, blinded=False):
     """canonical_root of one BeaconBlockDeneb; optionally also hash_tree_root(body) (BeaconBlockHeader.body_root)."""
-    r = beacon_block_roots_deneb([ssz], want_body_root)
+    r = beacon_block_roots_deneb([ssz], want_body_root, blinded)
     return (r[0][0], r[1][0]) if want_body_root else r[0]
 
 

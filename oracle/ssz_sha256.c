@@ -782,7 +782,13 @@ static void proposer_slashing_root(const uint8_t *p, uint8_t out[32]) { /* 416 B
 }
 static void kzg_commitment_root(const uint8_t *p, uint8_t out[32]) { pubkey_root(p, out); } /* 48 B blob (kzg_commitment.rs:51) */
 
+/* blinded != 0: BlindedBeaconBlockBodyDeneb — field 9 is an ExecutionPayloadHeaderDeneb (beacon_block.rs:80,
+ * payload.rs BlindedPayload) instead of the full payload; the body layout is otherwise identical. */
+static int body_root_deneb(const uint8_t *p, uint64_t len, int blinded, uint8_t out[32]);
 EXPORT int orc_beacon_block_body_root_deneb(const uint8_t *p, uint64_t len, uint8_t out[32]) {
+    return body_root_deneb(p, len, 0, out);
+}
+static int body_root_deneb(const uint8_t *p, uint64_t len, int blinded, uint8_t out[32]) {
     ensure_backend();
     if (len < 392) return -1;
     uint32_t o_ps = rd32(p + 200), o_as = rd32(p + 204), o_at = rd32(p + 208), o_dp = rd32(p + 212), o_ex = rd32(p + 216),
@@ -831,7 +837,7 @@ EXPORT int orc_beacon_block_body_root_deneb(const uint8_t *p, uint64_t len, uint
         bytes_root(p + 284, 96, 2, s[1]);
         container_root(s, 2, l[8]);
     }
-    if (payload_root_deneb(p + o_ep, o_bc - o_ep, l[9])) return -1;
+    if (blinded ? exec_header_root(p + o_ep, o_bc - o_ep, l[9]) : payload_root_deneb(p + o_ep, o_bc - o_ep, l[9])) return -1;
     if (fixed_list_root(p + o_bc, o_kz - o_bc, 172, 4, bls_change_root, l[10])) return -1;
     if (fixed_list_root(p + o_kz, len - o_kz, 48, 12, kzg_commitment_root, l[11])) return -1;
     container_root(l, 12, out);
@@ -839,14 +845,22 @@ EXPORT int orc_beacon_block_body_root_deneb(const uint8_t *p, uint64_t len, uint
 }
 
 /* BeaconBlock::canonical_root (beacon_block.rs:158-160).  body_root (32 B) optional. */
+static int block_root_deneb(const uint8_t *p, uint64_t len, int blinded, uint8_t out[32], uint8_t *body_root);
 EXPORT int orc_beacon_block_root_deneb(const uint8_t *p, uint64_t len, uint8_t out[32], uint8_t *body_root) {
+    return block_root_deneb(p, len, 0, out, body_root);
+}
+/* BlindedBeaconBlock::canonical_root: equals the root of the full block it was blinded from. */
+EXPORT int orc_blinded_beacon_block_root_deneb(const uint8_t *p, uint64_t len, uint8_t out[32], uint8_t *body_root) {
+    return block_root_deneb(p, len, 1, out, body_root);
+}
+static int block_root_deneb(const uint8_t *p, uint64_t len, int blinded, uint8_t out[32], uint8_t *body_root) {
     if (len < 84 || rd32(p + 80) != 84) return -1;
     uint8_t l[5][32];
     u64_chunk(p, l[0]);
     u64_chunk(p + 8, l[1]);
     memcpy(l[2], p + 16, 32);
     memcpy(l[3], p + 48, 32);
-    if (orc_beacon_block_body_root_deneb(p + 84, len - 84, l[4])) return -1;
+    if (body_root_deneb(p + 84, len - 84, blinded, l[4])) return -1;
     if (body_root) memcpy(body_root, l[4], 32);
     container_root(l, 5, out);
     return 0;

@@ -145,3 +145,9 @@ def beacon_block_root_deneb(ssz):
     out, body = (C.c_uint8 * 32)(), (C.c_uint8 * 32)()
     rc = L.orc_beacon_block_root_deneb(bytes(ssz), C.c_uint64(len(ssz)), out, body)
     return None if rc else (bytes(out), bytes(body))
+
+
+def blinded_beacon_block_root_deneb(ssz):
+    out, body = (C.c_uint8 * 32)(), (C.c_uint8 * 32)()
+    rc = L.orc_blinded_beacon_block_root_deneb(bytes(ssz), C.c_uint64(len(ssz)), out, body)
+    return None if rc else (bytes(out), bytes(body))

@@ -103,3 +103,33 @@ def test_oracle_block_root_random_shapes():
         assert S.serialize(S.BeaconBlockDeneb, ssz_spec.deserialize(S.BeaconBlockDeneb, ssz)) == ssz
         want = (ssz_spec.hash_tree_root(S.BeaconBlockDeneb, value), ssz_spec.hash_tree_root(S.BeaconBlockBodyDeneb, value["body"]))
         assert O.beacon_block_root_deneb(ssz) == want, kw
+
+
+def _blinded(name):
+    value, ssz = _block(name)
+    payload_t = dict(S.ExecutionPayloadDeneb[1])
+    p = value["body"]["execution_payload"]
+    bv, bssz = synthetic.blind_block_deneb(value, ssz_spec.hash_tree_root(payload_t["transactions"], p["transactions"]),
+                                           ssz_spec.hash_tree_root(payload_t["withdrawals"], p["withdrawals"]))
+    return ssz, bv, bssz
+
+
+@pytest.mark.parametrize("name", ["mainnet_like", "empty_body", "full_operations"])
+def test_oracle_blinded_block_root_equals_full_block_root(name):
+    """BlindedBeaconBlock (beacon_block.rs:80): replacing the payload by its header leaves the root unchanged; the
+    oracle's blinded walk agrees with the full-block walk and with the generic spec merkleization."""
+    ssz, bv, bssz = _blinded(name)
+    full = O.beacon_block_root_deneb(ssz)
+    assert O.blinded_beacon_block_root_deneb(bssz) == full
+    assert ssz_spec.hash_tree_root(S.BlindedBeaconBlockDeneb, bv) == full[0]
+    assert O.blinded_beacon_block_root_deneb(ssz) is None      # a full block is not a valid blinded block
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mainnet_like", "empty_body", "full_operations"])
+def test_gpu_blinded_block_root_matches_oracle(gpu, name):
+    from lighthouse_b200 import tree_hash
+    ssz, _, bssz = _blinded(name)
+    want = O.blinded_beacon_block_root_deneb(bssz)
+    assert tree_hash.beacon_block_root_deneb(bssz, want_body_root=True, blinded=True) == want
+    assert want[0] == tree_hash.beacon_block_root_deneb(ssz)   # == the full block's root on the device as well
