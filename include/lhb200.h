@@ -100,7 +100,9 @@ LHB200_API int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* of
  * (validators, balances, inactivity scores, participation x2, randao mixes, block/state roots, slashings) resident:
  * lhb200_state_patch marks the leaves it touches and lhb200_state_root / _enqueue re-hash only the paths above them
  * plus the tail program.  The first root after enabling is cold (it builds the levels); patches to other lists, or
- * more than 65 536 dirty leaves, fall back to a cold root.  Unsharded handles only.
+ * more than 65 536 dirty leaves, fall back to a cold root.  Unsharded handles only.  With lhb200_state_root_enqueue the
+ * dirty-leaf table is staged through the library's pinned slab: synchronise the stream before the next lhb200_* call
+ * (lhb200_state_root does).
  * lhb200_state_last_root_hashes: hash32_concat units the last root actually computed. */
 LHB200_API int32_t lhb200_state_enable_incremental(lhb200_state* st);
 LHB200_API uint64_t lhb200_state_last_root_hashes(const lhb200_state* st);
