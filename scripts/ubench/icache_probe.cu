@@ -1,5 +1,6 @@
-// icache_probe.cu — where is the instruction-cache cliff of an SM?  K distinct ~8 KB functions (straight-line dependent
-// IMAD chains, no memory traffic) are called round-robin by every warp; the time per executed instruction is flat
+// icache_probe.cu — where is the instruction-cache cliff of an SM?  K distinct ~12.3 KB code bodies (straight-line
+// dependent multiply / rotate-xor chains, no memory traffic; nvcc inlines them into one 300 KB kernel, each guarded by
+// `ID < k`) are executed round-robin by every warp; the time per executed instruction is flat
 // while K x 8 KB fits the instruction cache hierarchy and rises once the hot footprint falls out of it.  Written after
 // round 1 found every code-growing BLS variant (lazy reduction, fused light leaves) losing in the full kernels although
 // it won in isolation: the next round sizes the cooperative Miller loop's hot set against this curve.
@@ -8,13 +9,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-constexpr int BODY = 512;   // IMADs per function (~8 KB of SASS)
+constexpr int BODY = 512;   // instructions per function (~8 KB of SASS): 256 x (IMAD, SHF+LOP3 fused or separate)
 constexpr int KMAX = 24;
 
 template <int ID>
 __device__ __noinline__ uint32_t body(uint32_t x) {
 #pragma unroll
-    for (int i = 0; i < BODY; i++) x = x * (2654435761u + 2u * (uint32_t)(ID * BODY + i)) + (uint32_t)(ID + i);
+    for (int i = 0; i < BODY / 2; i++)   // multiply + rotate-xor: not an affine map, so the chain cannot be folded
+        x = (x * (2654435761u + 2u * (uint32_t)(ID * BODY + i))) ^ __funnelshift_r(x, x, 7 + (i & 15));
     return x;
 }
 template <int ID>
@@ -48,10 +50,10 @@ int main() {
             cudaEventSynchronize(e1);
             float ms = 0;
             cudaEventElapsedTime(&ms, e0, e1);
-            const double insts = (double)iters * k * BODY;                     // per warp
+            const double insts = (double)iters * k * 788.0;                    // per warp: 788 SASS instructions per body (cuobjdump)
             const double cyc = ms * 1e-3 * 1.965e9;
             printf("{\"warps_per_sm\": %d, \"functions\": %d, \"footprint_kb\": %d, \"ms\": %.3f, \"cycles_per_inst_per_warp\": %.3f, \"err\": \"%s\"}\n",
-                   warps_per_sm, k, k * BODY * 16 / 1024, ms, cyc / insts, cudaGetErrorString(cudaGetLastError()));
+                   warps_per_sm, k, (int)(k * 788 * 16 / 1024), ms, cyc / insts, cudaGetErrorString(cudaGetLastError()));
         }
     }
     return 0;
