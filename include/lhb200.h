@@ -227,6 +227,9 @@ LHB200_API int32_t lhb200_g1_decompress_validate(const uint8_t* pk48, uint32_t n
 /* Signature::deserialize, batch form (blst.rs:192-194): 192-byte affine out; status 0 ok, 1 infinity, 2 bad. */
 LHB200_API int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, uint8_t* status);
 
+/* Test hook (no device needed): n blinding scalars from the generator lhb200_verify_signature_sets uses when
+ * `rands == NULL` — a ChaCha20 keystream keyed from getrandom(2), zeros skipped (blst.rs:46-68: rand::thread_rng). */
+LHB200_API int32_t lhb200_debug_rand_scalars(uint64_t* out, uint32_t n);
 
 /* Test hook: run one stage of the BLS pipeline on a single device thread so `pytest -m gpu` can compare every
  * stage with the oracle.  op: 0 expand_message_xmd(32->256), 1 hash_to_g2(32->96), 2 SSWU(u 96 -> x|y 192),

@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(COOP_THREADS) k_final_coop(const Fp12* __restr
         return;
     }
     const int t = threadIdx.x;
-    if (t < 6) m.f.k[t] = coop_tower_coeff(*f_last, t);
+    if (t < 6) {   // f_last == nullptr: the (-g1, sum r sig) pair is already inside prod (cooperative Miller kernel)
+        if (f_last) m.f.k[t] = coop_tower_coeff(*f_last, t);
+        else { fp2_set_zero(m.f.k[t]); if (t == 0) m.f.k[0].c0 = FP_ONE; }
+    }
     __syncthreads();
     for (uint32_t i = 0; i < n_prod; i++) {
         if (t < 6) m.t1.k[t] = coop_tower_coeff(prod[i], t);

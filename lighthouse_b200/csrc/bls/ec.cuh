@@ -367,9 +367,18 @@ LHB_HD LHB_NOINLINE void g2_clear_cofactor(G2Jac& r, const G2Jac& p) {
 enum DecodeStatus : int32_t { DEC_OK = 0, DEC_INFINITY = 1, DEC_BAD = 2 };
 
 // 96-byte uncompressed affine G1 (x || y big-endian), as persisted by validator_pubkey_cache.rs:195-199.
-// No curve/subgroup validation (keys were validated when the cache imported them).
+// Encoding checks as blst's P1 deserialize does for the 96-byte form (blst.rs:142-150): the compression and sort flags
+// must be clear, an infinity encoding must be all zero otherwise.  No curve/subgroup validation here (keys were
+// validated when the cache imported them; k_table_import / lhb200_g1_deserialize_uncompressed add the curve check).
 LHB_HD LHB_INLINE int32_t g1_from_uncompressed(G1Affine& r, const uint8_t* b) {
-    if (b[0] & 0x40) { f_set_zero(r.x); f_set_zero(r.y); r.inf = 1; return DEC_INFINITY; }
+    if (b[0] & 0xa0) return DEC_BAD;
+    if (b[0] & 0x40) {
+        uint32_t nz = b[0] & 0x3f;
+        for (int i = 1; i < 96; i++) nz |= b[i];
+        if (nz) return DEC_BAD;
+        f_set_zero(r.x); f_set_zero(r.y); r.inf = 1;
+        return DEC_INFINITY;
+    }
     Fp cx, cy;
     fp_from_be48(cx, b);
     fp_from_be48(cy, b + 48);

@@ -12,6 +12,7 @@
 //   k_final ............ K8 Miller loop for (-g1, sum r*sig) + K9 final exponentiation and == 1
 #pragma once
 #include "pairing.cuh"
+#include "miller_coop.cuh"
 #include "h2c.cuh"
 
 namespace lhb200 {
@@ -223,6 +224,16 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_g2_reduce(const G2Jac* __restrict
         jac_add(acc, acc, x);
     }
     out[t] = acc;
+}
+
+// The G1 argument of the aggregated-signature pair e(-g1, sum r sig), in the Miller kernels' projective form.
+__global__ void k_init_neg_g1(G1Proj3* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1Proj3 p;
+    p.px = G1_GEN_X;
+    fp_neg(p.py, G1_GEN_Y);
+    p.pz = FP_ONE;
+    *out = p;
 }
 
 // f_last = Miller(-g1, S) for the aggregated signature term; runs concurrently with k_miller_multi.

@@ -9,7 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <random>
+#include <errno.h>
+#include <sys/random.h>
 #include <vector>
 #include "bls/debug.cuh"
 #include "ctx.h"
@@ -66,6 +67,11 @@ struct lhb200_bls_batch {
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller_multi), for the roofline
     uint64_t launches_last = 0;
+    // cooperative Miller kernel (bls/miller_coop.cuh): parking area for T / Q between rounds, the -g1 argument
+    uint32_t* d_mc_scratch = nullptr;
+    size_t mc_scratch_words = 0;
+    G1Proj3* d_neg_g1 = nullptr;
+    const G2Jac* d_sig_sum = nullptr;
     // streamed key upload (lhb200_bls_batch_upload_async): the key copy is cut into chunks of whole sets on its own
     // stream; k_pk_aggregate runs per chunk as it lands while the signature / hash-to-curve kernels already compute
     static constexpr int MAX_CHUNKS = 16;
@@ -85,7 +91,7 @@ static void batch_free(lhb200_bls_batch* b) {
     if (b->d_indices) cudaFree(b->d_indices);
     void* ptrs[] = {b->d_sigs, b->d_msgs, b->d_pks, b->d_offsets, b->d_rands, b->d_sigr, b->d_sig_tmp[0],
                     b->d_sig_tmp[1], b->d_p, b->d_h, b->d_f, b->d_f_tmp[0], b->d_f_tmp[1], b->d_flast, b->d_gt,
-                    b->d_status, b->d_fail, b->d_ok};
+                    b->d_status, b->d_fail, b->d_ok, b->d_mc_scratch, b->d_neg_g1};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (b->h_res) cudaFreeHost(b->h_res);
@@ -140,6 +146,7 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     ALLOC(b->d_status, n);
     ALLOC(b->d_fail, 4);
     ALLOC(b->d_ok, 4);
+    ALLOC(b->d_neg_g1, sizeof(G1Proj3));
 #undef ALLOC
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b->h_res), n + 64 + sizeof(Fp12), cudaHostAllocDefault);
     if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaHostAlloc(result)"); }
@@ -163,6 +170,8 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
             batch_free(b);
             return cuda_fail(e, "stream create");
         }
+    k_init_neg_g1<<<1, 32, 0, ctx().stream>>>(b->d_neg_g1);
+    if ((e = cudaStreamSynchronize(ctx().stream)) != cudaSuccess) { batch_free(b); return cuda_fail(e, "k_init_neg_g1"); }
     *out = b;
     return LHB200_OK;
 }
@@ -173,16 +182,73 @@ int32_t lhb200_bls_batch_destroy(lhb200_bls_batch* b) {
     return LHB200_OK;
 }
 
-static void gen_rands(uint64_t* r, uint32_t n) {
-    // blst.rs:55-67: one nonzero 64-bit scalar per set from a CSPRNG-seeded generator
-    std::random_device rd;
-    std::seed_seq seq{rd(), rd(), rd(), rd(), rd(), rd(), rd(), rd()};
-    std::mt19937_64 g(seq);
-    for (uint32_t i = 0; i < n; i++) {
-        uint64_t v;
-        do v = g(); while (v == 0);
-        r[i] = v;
+// ---- blinding scalars (blst.rs:46-68: `rand::thread_rng()`, a ChaCha CSPRNG seeded from the OS) ----------------
+// Same construction: a ChaCha20 keystream (RFC 8439 block function) keyed with 256 bits from getrandom(2) per thread,
+// re-keyed every 2^20 blocks; every 64-bit word is used as one scalar, zeros are skipped (blst.rs:60-64).
+namespace {
+struct ChaChaRng {
+    uint32_t key[8];
+    uint32_t nonce[3];
+    uint32_t counter = 0;
+    bool keyed = false;
+    uint64_t buf[8];
+    int have = 0;
+    static inline uint32_t rotl(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
+    static inline void qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+        a += b; d ^= a; d = rotl(d, 16);
+        c += d; b ^= c; b = rotl(b, 12);
+        a += b; d ^= a; d = rotl(d, 8);
+        c += d; b ^= c; b = rotl(b, 7);
     }
+    bool rekey() {
+        uint8_t seed[44];
+        size_t got = 0;
+        while (got < sizeof seed) {
+            const ssize_t k = getrandom(seed + got, sizeof seed - got, 0);
+            if (k < 0) { if (errno == EINTR) continue; return false; }
+            got += (size_t)k;
+        }
+        memcpy(key, seed, 32);
+        memcpy(nonce, seed + 32, 12);
+        counter = 0;
+        keyed = true;
+        return true;
+    }
+    bool refill() {
+        if (!keyed || counter >= (1u << 20)) { if (!rekey()) return false; }
+        uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                           key[4], key[5], key[6], key[7], counter, nonce[0], nonce[1], nonce[2]};
+        uint32_t x[16];
+        memcpy(x, st, sizeof x);
+        for (int i = 0; i < 10; i++) {
+            qr(x[0], x[4], x[8], x[12]); qr(x[1], x[5], x[9], x[13]); qr(x[2], x[6], x[10], x[14]); qr(x[3], x[7], x[11], x[15]);
+            qr(x[0], x[5], x[10], x[15]); qr(x[1], x[6], x[11], x[12]); qr(x[2], x[7], x[8], x[13]); qr(x[3], x[4], x[9], x[14]);
+        }
+        for (int i = 0; i < 16; i++) x[i] += st[i];
+        memcpy(buf, x, sizeof buf);
+        counter++;
+        have = 8;
+        return true;
+    }
+    bool next(uint64_t& v) {
+        do {
+            if (have == 0 && !refill()) return false;
+            v = buf[--have];
+        } while (v == 0);
+        return true;
+    }
+};
+}  // namespace
+static bool gen_rands(uint64_t* r, uint32_t n) {
+    static thread_local ChaChaRng rng;
+    for (uint32_t i = 0; i < n; i++)
+        if (!rng.next(r[i])) return false;
+    return true;
+}
+// Test hook: n scalars from the generator above (statistical / distinctness tests without a device).
+extern "C" LHB200_API int32_t lhb200_debug_rand_scalars(uint64_t* out, uint32_t n) {
+    if (!out) return LHB200_EINVAL;
+    return gen_rands(out, n) ? LHB200_OK : LHB200_ECUDA;
 }
 
 // Copy host inputs into the batch's device buffers.  rands == NULL: drawn here.
@@ -203,7 +269,7 @@ int32_t lhb200_bls_batch_upload(lhb200_bls_batch* b, const uint8_t* sigs, const 
     std::vector<uint64_t> rbuf;
     if (!rands) {
         rbuf.resize(n_sets);
-        gen_rands(rbuf.data(), n_sets);
+        if (!gen_rands(rbuf.data(), n_sets)) { set_error("getrandom(2) failed"); return LHB200_ECUDA; }
         rands = rbuf.data();
     } else {
         for (uint32_t i = 0; i < n_sets; i++)
@@ -242,7 +308,7 @@ int32_t lhb200_bls_batch_upload_async(lhb200_bls_batch* b, const uint8_t* sigs, 
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
     if (!rands) {
         b->rbuf.resize(n_sets);
-        gen_rands(b->rbuf.data(), n_sets);
+        if (!gen_rands(b->rbuf.data(), n_sets)) { set_error("getrandom(2) failed"); return LHB200_ECUDA; }
         rands = b->rbuf.data();
     } else {
         for (uint32_t i = 0; i < n_sets; i++)
@@ -351,7 +417,11 @@ int32_t lhb200_bls_batch_upload_indexed(lhb200_bls_batch* b, const lhb200_pubkey
         b->cap_indices = n_keys;
     }
     std::vector<uint64_t> rbuf;
-    if (!rands) { rbuf.resize(n_sets); gen_rands(rbuf.data(), n_sets); rands = rbuf.data(); }
+    if (!rands) {
+        rbuf.resize(n_sets);
+        if (!gen_rands(rbuf.data(), n_sets)) { set_error("getrandom(2) failed"); return LHB200_ECUDA; }
+        rands = rbuf.data();
+    }
     else for (uint32_t i = 0; i < n_sets; i++) if (rands[i] == 0) { set_error("zero random scalar"); return LHB200_EINVAL; }
     LHB_CUDA(cudaMemcpyAsync(b->d_sigs, sigs, (size_t)n_sets * 96, cudaMemcpyHostToDevice, s));
     LHB_CUDA(cudaMemcpyAsync(b->d_msgs, msgs, (size_t)n_sets * 32, cudaMemcpyHostToDevice, s));
@@ -429,8 +499,12 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
             flip ^= 1;
             m = mo;
         }
-        k_last_miller<<<1, 32, 0, b->s2>>>(cur, b->d_flast);
-        launches++;
+        b->d_sig_sum = cur;
+        static const int miller_coop_s2 = [] { const char* e = getenv("LHB_MILLER_COOP"); return e ? atoi(e) : 1; }();
+        if (!miller_coop_s2) {
+            k_last_miller<<<1, 32, 0, b->s2>>>(cur, b->d_flast);
+            launches++;
+        }
         LHB_CUDA(cudaEventRecord(b->e_join, b->s2));
     }
     k_hash_to_g2<<<grid, BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);
@@ -460,7 +534,53 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     } else
         k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
-    LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // k_miller_multi reads the status bytes k_sig_prepare may set
+    LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // the Miller kernel reads the status bytes k_sig_prepare may set
+    static const int miller_coop = [] { const char* e = getenv("LHB_MILLER_COOP"); return e ? atoi(e) : 1; }();
+    const Fp12* cur = b->d_f;
+    uint32_t n_tail = 0;
+    const Fp12* f_last = b->d_flast;
+    if (miller_coop) {
+        // Cooperative shared-memory Miller loop over the n sets AND the (-g1, sum r sig) pair (bls/miller_coop.cuh):
+        // two resident blocks of 96 lanes per SM, every lane runs `rounds` sets, six lanes share one accumulator.
+        constexpr int NT = 96;
+        static const bool attr_ok = [] {
+            return cudaFuncSetAttribute(mc::k_miller_coop<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)mc::smem_bytes<NT>()) == cudaSuccess;
+        }();
+        if (!attr_ok) { set_error("k_miller_coop: cannot reserve %zu B of shared memory", mc::smem_bytes<NT>()); return LHB200_ECUDA; }
+        const uint32_t n_total = n + 1;
+        const uint32_t max_blocks = (uint32_t)n_sm * 2;
+        uint32_t spb = cdiv(n_total, max_blocks);
+        spb = std::max<uint32_t>(spb, NT);
+        const uint32_t mgrid = cdiv(n_total, spb);
+        const uint32_t rounds_cap = cdiv(spb, NT);
+        const size_t need = (size_t)mgrid * rounds_cap * 2 * mc::TWORDS * NT;
+        if (need > b->mc_scratch_words) {
+            LHB_CUDA(cudaStreamSynchronize(s));
+            if (b->d_mc_scratch) cudaFree(b->d_mc_scratch);
+            b->d_mc_scratch = nullptr;
+            LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_mc_scratch), need * 4));
+            b->mc_scratch_words = need;
+        }
+        LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));   // sum r sig (and -g1) ready
+        LHB_CUDA(cudaEventRecord(b->e_k0, s));
+        mc::k_miller_coop<NT><<<mgrid, NT, mc::smem_bytes<NT>(), s>>>(b->d_p, b->d_h, b->d_status, n, b->d_sig_sum, b->d_neg_g1,
+                                                                      spb, b->d_mc_scratch, b->d_f);
+        LHB_CUDA(cudaEventRecord(b->e_k1, s));
+        launches += 1;
+        uint32_t m = mgrid * (NT / 6);
+        int flip = 0;
+        while (m > COOP_TAIL) {
+            const uint32_t mo = cdiv(m, REDUCE_CHUNK);
+            k_fp12_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, s>>>(cur, m, REDUCE_CHUNK, b->d_f_tmp[flip]);
+            launches++;
+            cur = b->d_f_tmp[flip];
+            flip ^= 1;
+            m = mo;
+        }
+        n_tail = m;
+        f_last = nullptr;
+    } else {
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
     // Sets per thread: k = ceil(n / resident threads) (<= MILLER_KMAX) share their Fp12 squarings in one thread, so a
     // 100 k batch is ONE wave of 3-set groups instead of three waves of single Miller loops.  LHB_MILLER_K overrides.
@@ -478,8 +598,6 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         b->d_p, b->d_h, b->d_status, n, mk, n_groups, b->d_f);
     LHB_CUDA(cudaEventRecord(b->e_k1, s));
     launches += 3;
-    const Fp12* cur = b->d_f;
-    uint32_t n_tail = n_groups;
     {
         uint32_t m = n_groups;
         int flip = 0;
@@ -494,7 +612,8 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         n_tail = m;
     }
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));
-    k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, n_tail, b->d_flast, b->d_fail, b->d_ok, b->d_gt);
+    }
+    k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, n_tail, f_last, b->d_fail, b->d_ok, b->d_gt);
     launches++;
     LHB_CUDA(cudaGetLastError());
     count_launch(launches);

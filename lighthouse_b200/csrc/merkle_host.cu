@@ -1519,7 +1519,8 @@ int32_t lhb200_shuffle_list(const uint64_t* input, uint64_t n, uint8_t rounds, c
     Ctx& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
     const uint32_t n_blocks = (uint32_t)ceil_div(n, 256);
-    const size_t b_in = align_up(n * 8, 256), b_src = align_up((size_t)rounds * n_blocks * 32, 256), b_piv = 1024;
+    const size_t b_in = align_up(n * 8, 256), b_src = align_up((size_t)rounds * n_blocks * 32, 256),
+                 b_piv = 2048 + 256;   // 255 rounds x 8-byte pivots (2040 B), then the seed in its own slot
     uint8_t* d = static_cast<uint8_t*>(dev_scratch(2 * b_in + b_src + b_piv + 256));
     uint8_t* h = static_cast<uint8_t*>(pinned_scratch(2 * b_in + 64));
     if (!d || !h) return LHB200_ENOMEM;
@@ -1527,7 +1528,7 @@ int32_t lhb200_shuffle_list(const uint64_t* input, uint64_t n, uint8_t rounds, c
     uint64_t* d_out = reinterpret_cast<uint64_t*>(d + b_in);
     uint8_t* d_src = d + 2 * b_in;
     uint64_t* d_piv = reinterpret_cast<uint64_t*>(d_src + b_src);
-    uint8_t* d_seed = reinterpret_cast<uint8_t*>(d_piv) + 768;
+    uint8_t* d_seed = reinterpret_cast<uint8_t*>(d_piv) + 2048;
     memcpy(h, input, n * 8);
     memcpy(h + b_in, seed, 32);
     LHB_CUDA(cudaMemcpyAsync(d_in, h, n * 8, cudaMemcpyHostToDevice, c.stream));

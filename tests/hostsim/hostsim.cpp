@@ -8,6 +8,8 @@
 #include "../../lighthouse_b200/csrc/bls/ec.cuh"
 #include "../../lighthouse_b200/csrc/bls/h2c.cuh"
 #include "../../lighthouse_b200/csrc/bls/pairing.cuh"
+#include "../../lighthouse_b200/csrc/bls/miller_coop.cuh"
+#include <vector>
 
 using namespace lhb200::bls;
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -192,4 +194,94 @@ EXPORT int hs_g1_mul_u64(const uint8_t* p96, uint64_t r, uint8_t* out96) {
     G1Jac j, o; jac_from_affine(j, a); jac_dbl(j, j);   // Jacobian base with Z != 1 (2P)
     jac_mul_u64(o, j, r);
     G1Affine ar; jac_to_affine(ar, o); g1_to_uncompressed(out96, ar); return 0;
+}
+
+// ---- fused sum-of-products Montgomery (bls/sop.cuh) on raw limbs: outA = sum_q xa_q ya_q / R, outB likewise (K = k <= 8).
+// x operands as given (may be unreduced within the documented bounds); y operands streamed from a strided array.
+template <int K>
+static void hs_sop2_k(const uint32_t* xa, const uint32_t* ya, const uint32_t* xb, const uint32_t* yb, uint32_t* oa, uint32_t* ob) {
+    const int stride = 3;   // deliberately not 1
+    std::vector<uint32_t> ma(K * 12 * stride), mb(K * 12 * stride);
+    SopX<K> XA, XB; SopY<K> YA, YB;
+    YA.stride = stride; YB.stride = stride;
+    for (int q = 0; q < K; q++) {
+        for (int i = 0; i < 12; i++) {
+            XA.x[q].v[i] = xa[12 * q + i]; XB.x[q].v[i] = xb[12 * q + i];
+            ma[(q * 12 + i) * stride] = ya[12 * q + i]; mb[(q * 12 + i) * stride] = yb[12 * q + i];
+        }
+        YA.base[q] = &ma[q * 12 * stride]; YB.base[q] = &mb[q * 12 * stride];
+    }
+    Fp ra, rb;
+    fp_sop2<K>(ra, rb, XA, YA, XB, YB);
+    Fp r1;
+    fp_sop1<K>(r1, XA, YA);
+    for (int i = 0; i < 12; i++) { oa[i] = ra.v[i]; ob[i] = rb.v[i]; if (r1.v[i] != ra.v[i]) oa[i] = ~oa[i]; }
+}
+EXPORT int hs_sop2(int k, const uint32_t* xa, const uint32_t* ya, const uint32_t* xb, const uint32_t* yb, uint32_t* oa, uint32_t* ob) {
+    switch (k) {
+        case 1: hs_sop2_k<1>(xa, ya, xb, yb, oa, ob); return 0;
+        case 2: hs_sop2_k<2>(xa, ya, xb, yb, oa, ob); return 0;
+        case 4: hs_sop2_k<4>(xa, ya, xb, yb, oa, ob); return 0;
+        case 6: hs_sop2_k<6>(xa, ya, xb, yb, oa, ob); return 0;
+        case 8: hs_sop2_k<8>(xa, ya, xb, yb, oa, ob); return 0;
+    }
+    return -1;
+}
+
+// ---- the cooperative Miller program (bls/miller_coop.cuh) run lane by lane: NT = 12 lanes = 2 groups per "block".
+// n pairs (P_j uncompressed G1 given as 2 P_j in projective form, Q_j compressed G2 handed over in Jacobian form with
+// Z != 1); status[j] != 0 marks a set as skipped; with_extra appends (-g1, Q_extra).  Blocks of `spb` sets.
+// out = final_exp(product of all group products) (576 bytes).
+template <int NT>
+struct ExecHost {
+    std::vector<mc::Lane<NT>> lanes;
+};
+EXPORT int hs_miller_coop(const uint8_t* p96, const uint8_t* q96, const uint8_t* status, int n, const uint8_t* extra_q96,
+                          int spb, uint8_t* out576) {
+    constexpr int NT = 12;
+    std::vector<G1Proj3> P(n); std::vector<G2Jac> H(n);
+    for (int j = 0; j < n; j++) {
+        G1Affine p; G2Affine q;
+        if (g1_from_uncompressed(p, p96 + 96 * j) != DEC_OK) return -1;
+        const int rc = g2_decompress(q, q96 + 96 * j);
+        if (rc == DEC_BAD) return -1;
+        G1Jac jj; jac_from_affine(jj, p); jac_dbl(jj, jj); g1proj3_from_jac(P[j], jj);
+        if (rc == DEC_INFINITY) { jac_set_inf(H[j]); continue; }
+        Fp2 s = q.x, s2, s3; fp2_add(s, s, q.y); fp2_sqr(s2, s); fp2_mul(s3, s2, s);
+        fp2_mul(H[j].X, q.x, s2); fp2_mul(H[j].Y, q.y, s3); H[j].Z = s;
+    }
+    G2Jac extra; bool have_extra = extra_q96 != nullptr;
+    if (have_extra) {
+        G2Affine q; const int rc = g2_decompress(q, extra_q96);
+        if (rc == DEC_BAD) return -1;
+        if (rc == DEC_INFINITY) jac_set_inf(extra); else jac_from_affine(extra, q);
+        G2Jac d; if (rc == DEC_OK) { jac_dbl(d, extra); jac_add(extra, d, extra); jac_neg(d, d); jac_add(extra, extra, d); }  // same point, Z != 1
+    }
+    const uint32_t n_total = n + (have_extra ? 1 : 0);
+    const uint32_t n_blocks = (n_total + spb - 1) / spb;
+    const uint32_t rounds_cap = (spb + NT - 1) / NT;
+    std::vector<Fp12> outs(n_blocks * (NT / 6));
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        std::vector<uint32_t> smem(mc::NSLOT * NL * NT + NT, 0xdeadbeefu);
+        std::vector<uint32_t> scratch((size_t)rounds_cap * 2 * mc::TWORDS * NT, 0xabababab);
+        ExecHost<NT> ex;
+        ex.lanes.resize(NT);
+        for (int t = 0; t < NT; t++) {
+            mc::Lane<NT>& L = ex.lanes[t];
+            L.tid = t; L.t = t % 6; L.c = Col<NT>::make(smem.data(), t);
+            L.act = reinterpret_cast<uint8_t*>(smem.data() + mc::NSLOT * NL * NT);
+            L.active = false; L.extra = false; L.set = 0;
+        }
+        mc::Args a;
+        G1Proj3 neg_g1; neg_g1.px = G1_GEN_X; fp_neg(neg_g1.py, G1_GEN_Y); neg_g1.pz = FP_ONE;
+        a.P = P.data(); a.H = H.data(); a.status = status; a.n = n; a.extra_q = have_extra ? &extra : nullptr; a.extra_p = &neg_g1;
+        a.lo = b * spb; a.hi = std::min<uint32_t>(n_total, a.lo + spb);
+        a.scratch = scratch.data(); a.out = &outs[b * (NT / 6)];
+        mc::miller_program<NT>(ex, a);
+    }
+    Fp12 f = outs[0];
+    for (size_t i = 1; i < outs.size(); i++) fp12_mul(f, f, outs[i]);
+    final_exp(f, f);
+    fp12_out(out576, f);
+    return 0;
 }

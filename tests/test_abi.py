@@ -75,3 +75,23 @@ def test_cpp_host_layer_builds_and_fails_loudly_without_gpu():
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "/dev/null"], capture_output=True, text=True)
         assert r.returncode == 2 and "no device" in r.stderr
+
+
+def test_blinding_scalars_come_from_a_csprng_stream():
+    """blst.rs:46-68: nonzero 64-bit scalars from a CSPRNG.  The library draws them from a getrandom(2)-keyed ChaCha20
+    stream; two draws must differ, no value may be zero, and the bits must be balanced (a broken generator that
+    repeats a block or returns a counter fails this)."""
+    import ctypes as C
+    import numpy as np
+    from lighthouse_b200 import _ffi
+    n = 1 << 16
+    a = np.zeros(n, dtype=np.uint64)
+    b = np.zeros(n, dtype=np.uint64)
+    assert _ffi.lib.lhb200_debug_rand_scalars(C.c_void_p(a.ctypes.data), n) == 0
+    assert _ffi.lib.lhb200_debug_rand_scalars(C.c_void_p(b.ctypes.data), n) == 0
+    assert (a != 0).all() and (b != 0).all()
+    assert len(np.unique(np.concatenate([a, b]))) == 2 * n
+    bits = np.unpackbits(a.view(np.uint8))
+    assert abs(bits.mean() - 0.5) < 0.005
+    per_bit = np.unpackbits(a.view(np.uint8).reshape(n, 8), axis=1).mean(axis=0)
+    assert (abs(per_bit - 0.5) < 0.02).all()

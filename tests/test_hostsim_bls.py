@@ -236,3 +236,66 @@ def test_pairing_and_verify(L):
     sig = bytes.fromhex(d["signature"])
     assert L.hs_verify(pk, m, sig) == 1
     assert L.hs_verify(pk, bytes(32), sig) == 0
+
+
+def test_fused_sum_of_products_matches_big_integers(L):
+    """bls/sop.cuh: fp_sop2<K> / fp_sop1<K> == (sum_q x_q y_q) R^-1 mod p on raw limbs, at the operand bounds the call
+    sites use (x < X p with K X <= 8; y < p), streaming y from a strided array."""
+    rnd = random.Random(21)
+    R = 1 << 384
+    Rinv = pow(R, -1, P)
+
+    def arr(vals):
+        return (C.c_uint32 * (12 * len(vals)))(*[(v >> (32 * i)) & 0xffffffff for v in vals for i in range(12)])
+
+    for k, xmax in ((1, 2 * P), (2, P + 1), (2, 2 * P), (4, 2 * P), (6, P + 1), (8, P + 1)):
+        for trial in range(40):
+            if trial == 0:
+                xa = [xmax - 1] * k; ya = [P - 1] * k; xb = [xmax - 1] * k; yb = [P - 1] * k
+            elif trial == 1:
+                xa = [0] * k; ya = [0] * k; xb = [1] * k; yb = [1] * k
+            else:
+                xa = [rnd.randrange(xmax) for _ in range(k)]; ya = [rnd.randrange(P) for _ in range(k)]
+                xb = [rnd.randrange(xmax) for _ in range(k)]; yb = [rnd.randrange(P) for _ in range(k)]
+            oa, ob = (C.c_uint32 * 12)(), (C.c_uint32 * 12)()
+            assert L.hs_sop2(k, arr(xa), arr(ya), arr(xb), arr(yb), oa, ob) == 0
+            ga = sum(int(oa[i]) << (32 * i) for i in range(12))
+            gb = sum(int(ob[i]) << (32 * i) for i in range(12))
+            assert ga == sum(x * y for x, y in zip(xa, ya)) * Rinv % P, (k, trial)
+            assert gb == sum(x * y for x, y in zip(xb, yb)) * Rinv % P, (k, trial)
+
+
+def test_cooperative_miller_program_matches_oracle(L):
+    """bls/miller_coop.cuh run lane by lane (two groups of six per block): product of pairings, after the final
+    exponentiation, == cube of the oracle's GT value — for ragged set counts, several rounds per lane, skipped sets, an
+    infinite Q and the appended (-g1, Q_extra) pair."""
+    def pts(n, seed):
+        ps = [B.g1_mul(B.G1_GEN, 1000 + 7 * j + seed) for j in range(n)]
+        qs = [B.g2_mul(B.G2_GEN, 55 + 3 * j + seed) for j in range(n)]
+        return ps, qs
+
+    def ref_cube(pairs):
+        f = None
+        for p, q in pairs:
+            if q is None:
+                continue
+            m = B.miller_loop(p, q)
+            f = m if f is None else B.f12_mul(f, m)
+        g = B.final_exp(f)
+        return B.f12_mul(B.f12_sqr(g), g)
+
+    for n, spb, skip, with_extra, inf_at in ((1, 12, (), False, None), (7, 12, (), False, None), (13, 12, (3,), True, None),
+                                             (29, 36, (0, 17), True, 5), (6, 12, (), True, None)):
+        ps, qs = pts(n, n)
+        if inf_at is not None:
+            qs[inf_at] = None
+        status = bytes(1 if j in skip else 0 for j in range(n))
+        extra = B.g2_mul(B.G2_GEN, 424242) if with_extra else None
+        out = C.create_string_buffer(576)
+        rc = L.hs_miller_coop(b"".join(B.g1_uncompressed(p) for p in ps), b"".join(B.g2_compress(q) for q in qs), status, n,
+                              B.g2_compress(extra) if with_extra else None, spb, out)
+        assert rc == 0
+        pairs = [(B.g1_add(p, p), q) for j, (p, q) in enumerate(zip(ps, qs)) if j not in skip]
+        if with_extra:
+            pairs.append((B.g1_neg(B.G1_GEN), extra))
+        assert f12_from(out.raw) == ref_cube(pairs), (n, spb)

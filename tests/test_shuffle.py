@@ -44,7 +44,7 @@ def test_gpu_shuffle_matches_oracle(gpu, n):
     seed = hashlib.sha256(b"gpu-seed-%d" % n).digest()
     rng = np.random.default_rng(n)
     inp = rng.integers(0, 1 << 40, size=n, dtype=np.uint64).tolist()
-    for rounds in ((1, 90) if n < 100_000 else (90,)):
+    for rounds in ((1, 90, 97, 161, 255) if n < 100_000 else (90,)):   # > 96 rounds: pivot table / seed slot sizing
         for forwards in (False, True):
             assert shuffle_list(inp, rounds, seed, forwards) == O.shuffle_list(inp, rounds, seed, forwards)
     assert shuffle_list(shuffle_list(inp, 90, seed, True), 90, seed, False) == inp
