@@ -227,6 +227,25 @@ LHB200_API int32_t lhb200_g1_decompress_validate(const uint8_t* pk48, uint32_t n
 /* Signature::deserialize, batch form (blst.rs:192-194): 192-byte affine out; status 0 ok, 1 infinity, 2 bad. */
 LHB200_API int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, uint8_t* status);
 
+/* ---- aggregation surface of a crypto/bls backend (crypto/bls/src/impls/blst.rs) ----
+ * TAggregateSignature::add_assign / add_assign_aggregate (blst.rs:230-237): out = sum of n compressed signatures; no
+ * subgroup check (the trait's contract), infinity encodings are the identity, n == 0 -> the infinity signature;
+ * LHB200_EDECODE if an encoding is malformed. */
+LHB200_API int32_t lhb200_g2_aggregate(const uint8_t* sigs96, uint32_t n, uint8_t out96[96]);
+/* TAggregatePublicKey::aggregate (blst.rs:178-184; generic_aggregate_public_key.rs:9-15): sum of n uncompressed keys
+ * (already validated, per the trait's contract), compressed and/or uncompressed result (either may be NULL).
+ * n == 0 -> LHB200_EINVAL; malformed / off-curve key -> LHB200_EDECODE. */
+LHB200_API int32_t lhb200_g1_aggregate(const uint8_t* pks96, uint32_t n, uint8_t* out48, uint8_t* out96);
+/* TPublicKey::deserialize_uncompressed (blst.rs:142-150), batch form: flag bits and on-curve check, no subgroup check.
+ * status[i]: 0 ok, 1 infinity, 2 bad encoding / not on the curve; pk48 (optional) receives the compressed keys.
+ * NOTE: lhb200_verify_signature_sets does not repeat the curve check on its explicit `pks` (blst.rs:115
+ * pks_validate = false): keys must come from this call, lhb200_g1_decompress_validate or a pubkey table. */
+LHB200_API int32_t lhb200_g1_deserialize_uncompressed(const uint8_t* pks96, uint32_t n, uint8_t* pk48, uint8_t* status);
+/* TAggregateSignature::aggregate_verify (blst.rs:263-273): *ok = 1 iff e(g1, sig) == prod_i e(pk_i, H(m_i)) and sig is
+ * in G2.  n == 0 -> *ok = 0 (generic_aggregate_signature.rs:214-216). */
+LHB200_API int32_t lhb200_aggregate_verify(const uint8_t sig96[96], const uint8_t* msgs, const uint8_t* pks96, uint32_t n,
+                                           uint8_t* ok);
+
 /* Test hook (no device needed): n blinding scalars from the generator lhb200_verify_signature_sets uses when
  * `rands == NULL` — a ChaCha20 keystream keyed from getrandom(2), zeros skipped (blst.rs:46-68: rand::thread_rng). */
 LHB200_API int32_t lhb200_debug_rand_scalars(uint64_t* out, uint32_t n);

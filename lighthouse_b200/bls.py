@@ -81,6 +81,23 @@ class PublicKey:
             raise BlstError(f"key_validate status {int(st[0])}")
         return cls(bytes(b), unc)
 
+    @classmethod
+    def deserialize_uncompressed(cls, b: bytes) -> "PublicKey":
+        """TPublicKey::deserialize_uncompressed (blst.rs:142-150; generic_public_key.rs:97-102): encoding + curve
+        check, no subgroup check; infinity is rejected like `deserialize`."""
+        if len(b) != PUBLIC_KEY_UNCOMPRESSED_BYTES_LEN:
+            raise InvalidByteLength(f"got {len(b)}, expected {PUBLIC_KEY_UNCOMPRESSED_BYTES_LEN}")
+        c48 = np.zeros(48, dtype=np.uint8)
+        st = np.zeros(1, dtype=np.uint8)
+        p, k = buf(b)
+        check(lib.lhb200_g1_deserialize_uncompressed(p, 1, c48.ctypes.data, st.ctypes.data),
+              "lhb200_g1_deserialize_uncompressed")
+        if st[0] == 1:
+            raise InvalidInfinityPublicKey()
+        if st[0] != 0:
+            raise BlstError("bad uncompressed G1 encoding")
+        return cls(c48.tobytes(), bytes(b))
+
     def serialize(self) -> bytes:
         return self.compressed
 
@@ -135,14 +152,82 @@ class Signature:
         return SignatureSet.single_pubkey(self, pubkey, msg).verify()
 
 
+def aggregate_signatures(sigs96: bytes) -> bytes:
+    """Sum of n compressed signatures (lhb200_g2_aggregate; TAggregateSignature::add_assign, blst.rs:230-237)."""
+    n = len(sigs96) // 96
+    out = C.create_string_buffer(96)
+    p, k = buf(sigs96 if n else b"\0")
+    rc = lib.lhb200_g2_aggregate(p, n, out)
+    if rc == _ffi.EDECODE:
+        raise BlstError("bad G2 encoding")
+    check(rc, "lhb200_g2_aggregate")
+    return out.raw
+
+
+class AggregatePublicKey:
+    """GenericAggregatePublicKey (generic_aggregate_public_key.rs:9-15, impls/blst.rs:160-184)."""
+    __slots__ = ("pk",)
+
+    def __init__(self, pk: PublicKey):
+        self.pk = pk
+
+    @classmethod
+    def aggregate(cls, pubkeys) -> "AggregatePublicKey":
+        pubkeys = list(pubkeys)
+        if not pubkeys:
+            raise BlstError("aggregate of no keys")   # blst: BLST_AGGR_TYPE_MISMATCH
+        o48, o96 = C.create_string_buffer(48), C.create_string_buffer(96)
+        p, k = buf(b"".join(x.serialize_uncompressed() for x in pubkeys))
+        rc = lib.lhb200_g1_aggregate(p, len(pubkeys), o48, o96)
+        if rc == _ffi.EDECODE:
+            raise BlstError("bad G1 key")
+        check(rc, "lhb200_g1_aggregate")
+        return cls(PublicKey(o48.raw, o96.raw))
+
+    def to_public_key(self) -> PublicKey:
+        return self.pk
+
+
 class AggregateSignature(Signature):
-    """GenericAggregateSignature.  Aggregation of already-aggregated signatures is host-side bookkeeping only
-    in this mirror (signatures arrive pre-aggregated on the hot path); verification is on the device."""
+    """GenericAggregateSignature (generic_aggregate_signature.rs:60-235): the point is kept as its canonical bytes;
+    `add_assign*` and every verification run on the device."""
 
     @classmethod
     def deserialize(cls, b: bytes) -> "AggregateSignature":
         s = Signature.deserialize(b)
         return cls(s.bytes_)
+
+    def add_assign(self, other: Signature):
+        """generic_aggregate_signature.rs:124-136: an empty `other` is ignored; an empty `self` starts from infinity."""
+        if other.is_empty:
+            return
+        base = INFINITY_SIGNATURE if self.is_empty else self.bytes_
+        self.bytes_ = aggregate_signatures(base + other.bytes_)
+        self.is_empty = False
+
+    def add_assign_aggregate(self, other: "AggregateSignature"):
+        self.add_assign(other)
+
+    @classmethod
+    def aggregate(cls, signatures) -> "AggregateSignature":
+        """All signatures in one device pass (what repeated add_assign computes)."""
+        agg = cls.infinity()
+        sigs = [s.bytes_ for s in signatures if not s.is_empty]
+        if sigs:
+            agg.bytes_ = aggregate_signatures(b"".join(sigs))
+        return agg
+
+    def aggregate_verify(self, msgs, pubkeys) -> bool:
+        """generic_aggregate_signature.rs:213-222 -> blst.rs:263-273."""
+        msgs, pubkeys = list(msgs), list(pubkeys)
+        if not msgs or len(msgs) != len(pubkeys) or self.is_empty:
+            return False
+        ok = C.create_string_buffer(1)
+        ps, k1 = buf(self.bytes_)
+        pm, k2 = buf(b"".join(msgs))
+        pp, k3 = buf(b"".join(k.serialize_uncompressed() for k in pubkeys))
+        check(lib.lhb200_aggregate_verify(ps, pm, pp, len(msgs), ok), "lhb200_aggregate_verify")
+        return ok.raw[0] == 1
 
     def fast_aggregate_verify(self, msg: bytes, pubkeys) -> bool:
         """generic_aggregate_signature.rs:187-196: empty key list -> False."""

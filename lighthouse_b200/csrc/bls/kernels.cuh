@@ -313,6 +313,79 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_sign(const uint8_t* __restrict__ 
     for (int t = 0; t < 96; t++) sig96[96ull * i + t] = b[t];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Aggregation surface of a crypto/bls backend (TAggregateSignature::add_assign / add_assign_aggregate
+// blst.rs:230-237, TAggregatePublicKey::aggregate blst.rs:178-184, deserialize_uncompressed blst.rs:142-150).
+// sum tree over G1 points (k_g2_reduce's twin)
+__global__ void __launch_bounds__(BLS_BLOCK) k_g1_reduce(const G1Jac* __restrict__ in, uint32_t n, uint32_t chunk,
+                                                          G1Jac* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t lo = (uint64_t)t * chunk;
+    if (lo >= n) return;
+    const uint32_t hi = (uint32_t)min((uint64_t)n, lo + chunk);
+    G1Jac acc = in[lo];
+    for (uint32_t j = (uint32_t)lo + 1; j < hi; j++) {
+        G1Jac x = in[j];
+        jac_add(acc, acc, x);
+    }
+    out[t] = acc;
+}
+// compressed signatures -> Jacobian points (infinity = identity); any malformed encoding raises *n_bad
+__global__ void __launch_bounds__(BLS_BLOCK) k_g2_load_points(const uint8_t* __restrict__ sig96, uint32_t n,
+                                                               G2Jac* __restrict__ out, uint32_t* __restrict__ n_bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[96];
+    for (int t = 0; t < 96; t++) b[t] = sig96[96ull * i + t];
+    G2Affine a;
+    G2Jac j;
+    jac_set_inf(j);
+    const int32_t rc = g2_decompress(a, b);
+    if (rc == DEC_BAD) atomicAdd(n_bad, 1u);
+    else if (rc == DEC_OK) jac_from_affine(j, a);
+    out[i] = j;
+}
+__global__ void k_g2_store_point(const G2Jac* __restrict__ in, uint8_t* __restrict__ out96) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G2Jac j = *in;
+    G2Affine a;
+    jac_to_affine(a, j);
+    uint8_t b[96];
+    g2_compress(b, a);
+    for (int t = 0; t < 96; t++) out96[t] = b[t];
+}
+// uncompressed keys -> Jacobian points; status as lhb200_g1_deserialize_uncompressed (0 ok, 1 infinity, 2 bad)
+__global__ void __launch_bounds__(BLS_BLOCK) k_g1_load_points(const uint8_t* __restrict__ pk96, uint32_t n,
+                                                               G1Jac* __restrict__ out, uint8_t* __restrict__ pk48,
+                                                               uint8_t* __restrict__ st, uint32_t* __restrict__ n_bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __align__(16) uint8_t b[96];
+    for (int t = 0; t < 96; t++) b[t] = pk96[96ull * i + t];
+    G1Affine a;
+    int32_t rc = g1_from_uncompressed(a, b);
+    if (rc == DEC_OK && !g1_on_curve(a)) rc = DEC_BAD;
+    if (rc == DEC_BAD) { atomicAdd(n_bad, 1u); a.inf = 1; }
+    if (out) { G1Jac j; jac_from_affine(j, a); out[i] = j; }
+    if (st) st[i] = (uint8_t)rc;
+    if (pk48) {
+        uint8_t c[48];
+        if (rc == DEC_OK) g1_compress(c, a);
+        else for (int t = 0; t < 48; t++) c[t] = 0;
+        for (int t = 0; t < 48; t++) pk48[48ull * i + t] = c[t];
+    }
+}
+__global__ void k_g1_store_point(const G1Jac* __restrict__ in, uint8_t* __restrict__ out48, uint8_t* __restrict__ out96) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1Jac j = *in;
+    G1Affine a;
+    jac_to_affine(a, j);
+    uint8_t b[96];
+    if (out48) { g1_compress(b, a); for (int t = 0; t < 48; t++) out48[t] = b[t]; }
+    if (out96) { g1_to_uncompressed(b, a); for (int t = 0; t < 96; t++) out96[t] = b[t]; }
+}
+
 // PublicKey::deserialize + key_validate (blst.rs:130-140): decompress, reject infinity, subgroup check.
 // status: 0 ok, 1 infinity, 2 bad encoding / not on curve, 3 not in subgroup.
 __global__ void __launch_bounds__(BLS_BLOCK) k_g1_decompress_validate(const uint8_t* __restrict__ pk48, uint32_t n,

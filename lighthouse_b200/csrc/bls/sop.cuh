@@ -90,34 +90,26 @@ LHB_HD LHB_INLINE void sop_row(uint32_t* even, uint32_t* odd, const SopX<K>& x, 
 }
 
 // Two fused sums of K products each (see the header comment).  The row loop is rolled (6 iterations of two rows per
-// window); the y limbs of the next row pair are fetched while the current pair computes.
+// window).  The y limbs of a row pair are fetched at the top of its iteration: ~30 cycles of shared-memory latency per
+// ~2000 cycles of multiply work; an explicit double buffer cost 4 K register copies per iteration and 4 K registers.
 template <int K>
 LHB_HD LHB_INLINE void fp_sop2(Fp& ra, Fp& rb, const SopX<K>& xa, const SopY<K>& ya, const SopX<K>& xb,
                                const SopY<K>& yb) {
     uint32_t ea[NL], oa[NL], eb[NL], ob[NL];
 #pragma unroll
     for (int i = 0; i < NL; i++) { ea[i] = 0; oa[i] = 0; eb[i] = 0; ob[i] = 0; }
-    uint32_t sa[2][K], sb[2][K];
-#pragma unroll
-    for (int q = 0; q < K; q++) {
-        sa[0][q] = ya.limb(q, 0); sa[1][q] = ya.limb(q, 1);
-        sb[0][q] = yb.limb(q, 0); sb[1][q] = yb.limb(q, 1);
-    }
 #pragma unroll 1
     for (int jp = 0; jp < NL; jp += 2) {
-        uint32_t na[2][K], nb[2][K];
-        const int jn = (jp + 2 < NL) ? jp + 2 : 0;   // (the last prefetch re-reads row 0: harmless)
+        uint32_t sa0[K], sa1[K], sb0[K], sb1[K];
 #pragma unroll
         for (int q = 0; q < K; q++) {
-            na[0][q] = ya.limb(q, jn); na[1][q] = ya.limb(q, jn + 1);
-            nb[0][q] = yb.limb(q, jn); nb[1][q] = yb.limb(q, jn + 1);
+            sa0[q] = ya.limb(q, jp); sa1[q] = ya.limb(q, jp + 1);
+            sb0[q] = yb.limb(q, jp); sb1[q] = yb.limb(q, jp + 1);
         }
-        sop_row<K>(ea, oa, xa, sa[0]);
-        sop_row<K>(eb, ob, xb, sb[0]);
-        sop_row<K>(oa, ea, xa, sa[1]);
-        sop_row<K>(ob, eb, xb, sb[1]);
-#pragma unroll
-        for (int q = 0; q < K; q++) { sa[0][q] = na[0][q]; sa[1][q] = na[1][q]; sb[0][q] = nb[0][q]; sb[1][q] = nb[1][q]; }
+        sop_row<K>(ea, oa, xa, sa0);
+        sop_row<K>(eb, ob, xb, sb0);
+        sop_row<K>(oa, ea, xa, sa1);
+        sop_row<K>(ob, eb, xb, sb1);
     }
     sop_finish(ra, ea, oa);
     sop_finish(rb, eb, ob);
@@ -168,8 +160,9 @@ LHB_HD LHB_INLINE void fp_half(Fp& r, const Fp& a) {
 }
 
 // ------------------------------------------------------------------------------------------------ columns
-// A "column" is one thread's private strip of a word-interleaved shared-memory array: Fp slot s, limb w of thread t is
-// word (s * 12 + w) * NT + t, so a warp's access to the same limb of the same slot is one conflict-free row.
+// A "column" is one lane's private strip of a word-interleaved shared-memory array of NT lanes (one warp's region on the
+// device: NT = 32): Fp slot s, limb w of lane t is word (s * 12 + w) * NT + t, so a warp's access to the same limb of
+// the same slot is one conflict-free row, and so is any permutation of lanes (a lane reading a neighbour's column).
 // On the device a column is a 32-bit word offset into the kernel's dynamic shared memory, so that the out-of-line
 // operations below address it with LDS/STS (a generic pointer argument would turn every access into LD/ST).
 #if !defined(LHB_HOSTSIM)
@@ -185,7 +178,7 @@ struct Col {
 #else
     uint32_t off;
     LHB_HD LHB_INLINE uint32_t* base() const { return lhb_dyn_smem + off; }
-    static LHB_HD LHB_INLINE Col make(uint32_t*, int tid) { return Col{(uint32_t)tid}; }
+    static LHB_HD LHB_INLINE Col make(uint32_t* region, int lane) { return Col{(uint32_t)(region - lhb_dyn_smem) + (uint32_t)lane}; }
     LHB_HD LHB_INLINE Col lane(int delta) const { return Col{off + (uint32_t)delta}; }
 #endif
     LHB_HD LHB_INLINE const uint32_t* at(int slot) const { return base() + slot * NL * NT; }

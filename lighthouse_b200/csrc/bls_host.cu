@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <errno.h>
 #include <sys/random.h>
 #include <vector>
@@ -22,7 +23,7 @@ using namespace bls;
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 int32_t bls_init() { return LHB200_OK; }
-void bls_shutdown() {}
+void bls_shutdown();
 
 }  // namespace lhb200
 
@@ -62,6 +63,7 @@ struct lhb200_bls_batch {
     uint32_t* d_fail = nullptr;
     uint8_t* d_ok = nullptr;
     uint8_t* h_res = nullptr;     // pinned: ok + status
+    cudaStream_t s_main = nullptr;   // the stream lhb200_verify_signature_sets drives this handle on (one per handle)
     cudaStream_t s2 = nullptr, s3 = nullptr;
     cudaEvent_t e_h2c = nullptr, e_sig = nullptr;
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
@@ -95,6 +97,7 @@ static void batch_free(lhb200_bls_batch* b) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (b->h_res) cudaFreeHost(b->h_res);
+    if (b->s_main) cudaStreamDestroy(b->s_main);
     if (b->s2) cudaStreamDestroy(b->s2);
     if (b->s3) cudaStreamDestroy(b->s3);
     if (b->e_h2c) cudaEventDestroy(b->e_h2c);
@@ -114,6 +117,52 @@ static void batch_free(lhb200_bls_batch* b) {
 
 constexpr uint32_t REDUCE_CHUNK = 8;
 
+// ---- pool of batch handles behind lhb200_verify_signature_sets -------------------------------------------------
+namespace {
+std::mutex g_pool_mu;
+std::vector<lhb200_bls_batch*> g_pool_free;
+constexpr size_t POOL_MAX_IDLE = 16;
+
+lhb200_bls_batch* pool_acquire(uint32_t n_sets, uint64_t n_keys) {
+    lhb200_bls_batch* b = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        // best fit: the smallest idle handle that is large enough
+        size_t best = SIZE_MAX;
+        for (size_t i = 0; i < g_pool_free.size(); i++) {
+            lhb200_bls_batch* c = g_pool_free[i];
+            if (c->cap_sets >= n_sets && c->cap_keys >= n_keys &&
+                (best == SIZE_MAX || c->cap_keys < g_pool_free[best]->cap_keys)) best = i;
+        }
+        if (best != SIZE_MAX) {
+            b = g_pool_free[best];
+            g_pool_free.erase(g_pool_free.begin() + best);
+        } else if (g_pool_free.size() >= POOL_MAX_IDLE) {   // recycle the oldest handle's slot
+            lhb200_bls_batch* victim = g_pool_free.front();
+            g_pool_free.erase(g_pool_free.begin());
+            cudaStreamSynchronize(victim->s_main);
+            batch_free(victim);
+        }
+    }
+    if (b) return b;
+    const uint32_t cap_sets = std::max<uint32_t>(n_sets + n_sets / 4, 256);
+    const uint64_t cap_keys = std::max<uint64_t>(n_keys + n_keys / 4, 4096);
+    if (lhb200_bls_batch_create(cap_sets, cap_keys, &b) != LHB200_OK) return nullptr;
+    return b;
+}
+void pool_release(lhb200_bls_batch* b) {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    g_pool_free.push_back(b);
+}
+}  // namespace
+namespace lhb200 {
+void bls_shutdown() {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (lhb200_bls_batch* b : g_pool_free) batch_free(b);
+    g_pool_free.clear();
+}
+}  // namespace lhb200
+
 extern "C" {
 
 int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls_batch** out) {
@@ -123,6 +172,9 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     b->cap_sets = max_sets;
     b->cap_keys = max_keys;
     const uint64_t n = max_sets, n1 = cdiv(n, REDUCE_CHUNK) + 1, n2 = cdiv(n1, REDUCE_CHUNK) + 1;
+    // Miller values: one per set (old kernels) or 5 per warp of the cooperative kernel (<= ceil((n+1)/6) + 40 warps)
+    const uint64_t nf = std::max<uint64_t>(n, (cdiv(n + 1, 6) + 48) * 5), nf1 = cdiv(nf, REDUCE_CHUNK) + 1,
+                   nf2 = cdiv(nf1, REDUCE_CHUNK) + 1;
 #define ALLOC(p, bytes)                                                         \
     do {                                                                        \
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&(p)), (bytes));    \
@@ -138,9 +190,9 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     ALLOC(b->d_sig_tmp[1], n2 * sizeof(G2Jac));
     ALLOC(b->d_p, n * sizeof(G1Proj3));
     ALLOC(b->d_h, n * sizeof(G2Jac));
-    ALLOC(b->d_f, n * sizeof(Fp12));
-    ALLOC(b->d_f_tmp[0], n1 * sizeof(Fp12));
-    ALLOC(b->d_f_tmp[1], n2 * sizeof(Fp12));
+    ALLOC(b->d_f, nf * sizeof(Fp12));
+    ALLOC(b->d_f_tmp[0], nf1 * sizeof(Fp12));
+    ALLOC(b->d_f_tmp[1], nf2 * sizeof(Fp12));
     ALLOC(b->d_flast, sizeof(Fp12));
     ALLOC(b->d_gt, sizeof(Fp12));
     ALLOC(b->d_status, n);
@@ -150,7 +202,8 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
 #undef ALLOC
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b->h_res), n + 64 + sizeof(Fp12), cudaHostAllocDefault);
     if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaHostAlloc(result)"); }
-    if ((e = cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking)) != cudaSuccess ||
+    if ((e = cudaStreamCreateWithFlags(&b->s_main, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&b->s3, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_h2c, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_sig, cudaEventDisableTiming)) != cudaSuccess ||
@@ -170,8 +223,8 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
             batch_free(b);
             return cuda_fail(e, "stream create");
         }
-    k_init_neg_g1<<<1, 32, 0, ctx().stream>>>(b->d_neg_g1);
-    if ((e = cudaStreamSynchronize(ctx().stream)) != cudaSuccess) { batch_free(b); return cuda_fail(e, "k_init_neg_g1"); }
+    k_init_neg_g1<<<1, 32, 0, b->s_main>>>(b->d_neg_g1);
+    if ((e = cudaStreamSynchronize(b->s_main)) != cudaSuccess) { batch_free(b); return cuda_fail(e, "k_init_neg_g1"); }
     *out = b;
     return LHB200_OK;
 }
@@ -541,20 +594,24 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     const Fp12* f_last = b->d_flast;
     if (miller_coop) {
         // Cooperative shared-memory Miller loop over the n sets AND the (-g1, sum r sig) pair (bls/miller_coop.cuh):
-        // two resident blocks of 96 lanes per SM, every lane runs `rounds` sets, six lanes share one accumulator.
-        constexpr int NT = 96;
+        // one block of 8 independent warps per SM, 30 working lanes per warp, every lane runs `rounds` sets, six lanes
+        // share one accumulator.  Small batches spread over more, emptier warps (latency), large ones fill 8 x n_sm.
         static const bool attr_ok = [] {
-            return cudaFuncSetAttribute(mc::k_miller_coop<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)mc::smem_bytes<NT>()) == cudaSuccess;
+            return cudaFuncSetAttribute(mc::k_miller_coop, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)mc::mc_smem_bytes()) == cudaSuccess;
         }();
-        if (!attr_ok) { set_error("k_miller_coop: cannot reserve %zu B of shared memory", mc::smem_bytes<NT>()); return LHB200_ECUDA; }
+        if (!attr_ok) { set_error("k_miller_coop: cannot reserve %zu B of shared memory", mc::mc_smem_bytes()); return LHB200_ECUDA; }
+        constexpr uint32_t LU = 30;
         const uint32_t n_total = n + 1;
-        const uint32_t max_blocks = (uint32_t)n_sm * 2;
-        uint32_t spb = cdiv(n_total, max_blocks);
-        spb = std::max<uint32_t>(spb, NT);
-        const uint32_t mgrid = cdiv(n_total, spb);
-        const uint32_t rounds_cap = cdiv(spb, NT);
-        const size_t need = (size_t)mgrid * rounds_cap * 2 * mc::TWORDS * NT;
+        const uint32_t max_warps = (uint32_t)n_sm * mc::MC_WARPS;
+        uint32_t spw = cdiv(n_total, max_warps);             // sets per warp
+        spw = cdiv(spw, LU) * LU;                            // whole rounds
+        spw = std::max<uint32_t>(spw, 6);
+        if (n_total <= max_warps * 6) spw = 6;               // tiny batches: one group per warp, as many SMs as possible
+        const uint32_t n_warps = cdiv(n_total, spw);
+        const uint32_t mgrid = cdiv(n_warps, mc::MC_WARPS);
+        const uint32_t rounds_cap = cdiv(spw, LU);
+        const size_t need = (size_t)mgrid * mc::MC_WARPS * rounds_cap * 2 * mc::TWORDS * 32;
         if (need > b->mc_scratch_words) {
             LHB_CUDA(cudaStreamSynchronize(s));
             if (b->d_mc_scratch) cudaFree(b->d_mc_scratch);
@@ -564,11 +621,11 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         }
         LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));   // sum r sig (and -g1) ready
         LHB_CUDA(cudaEventRecord(b->e_k0, s));
-        mc::k_miller_coop<NT><<<mgrid, NT, mc::smem_bytes<NT>(), s>>>(b->d_p, b->d_h, b->d_status, n, b->d_sig_sum, b->d_neg_g1,
-                                                                      spb, b->d_mc_scratch, b->d_f);
+        mc::k_miller_coop<<<mgrid, 32 * mc::MC_WARPS, mc::mc_smem_bytes(), s>>>(b->d_p, b->d_h, b->d_status, n, b->d_sig_sum,
+                                                                                b->d_neg_g1, spw, b->d_mc_scratch, b->d_f);
         LHB_CUDA(cudaEventRecord(b->e_k1, s));
         launches += 1;
-        uint32_t m = mgrid * (NT / 6);
+        uint32_t m = mgrid * mc::MC_WARPS * mc::MC_GROUPS_PER_WARP;
         int flip = 0;
         while (m > COOP_TAIL) {
             const uint32_t mo = cdiv(m, REDUCE_CHUNK);
@@ -707,29 +764,19 @@ int32_t lhb200_verify_signature_sets(const uint8_t* sigs, const uint8_t* msgs, c
     *ok = 0;
     if (n_sets == 0) return LHB200_OK;
     if (!pk_offsets) { set_error("verify_signature_sets: null offsets"); return LHB200_EINVAL; }
-    Ctx& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    // One cached batch (device buffers, streams, events) is reused across calls and grown on demand: a 64-set gossip
-    // batch must not pay 18 cudaMalloc/cudaFree per call.
-    static lhb200_bls_batch* cached = nullptr;
+    // Re-entrant: Lighthouse calls this from up to num_cpus blocking workers with <= 64-set gossip batches
+    // (beacon_processor/src/lib.rs:202-203,256).  Every call borrows a batch handle (device buffers, streams, events —
+    // no cudaMalloc on the steady path) from a pool and drives it on the handle's own stream, so concurrent calls
+    // overlap on the device instead of queueing behind one mutex.
     const uint64_t n_keys = pk_offsets[n_sets];
-    if (cached && (cached->cap_sets < n_sets || cached->cap_keys < n_keys)) {
-        cudaDeviceSynchronize();
-        batch_free(cached);
-        cached = nullptr;
-    }
-    if (!cached) {
-        const uint32_t cap_sets = std::max<uint32_t>(n_sets + n_sets / 4, 256);
-        const uint64_t cap_keys = std::max<uint64_t>(n_keys + n_keys / 4, 4096);
-        int32_t rc0 = lhb200_bls_batch_create(cap_sets, cap_keys, &cached);
-        if (rc0) { cached = nullptr; return rc0; }
-    }
-    lhb200_bls_batch* b = cached;
-    int32_t rc = lhb200_bls_batch_upload_async(b, sigs, msgs, pks, pk_offsets, rands, n_sets, c.stream);
-    if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, c.stream);
-    if (!rc) rc = lhb200_bls_batch_result(b, c.stream, ok, set_status);
+    lhb200_bls_batch* b = pool_acquire(n_sets, n_keys);
+    if (!b) return LHB200_ENOMEM;
+    int32_t rc = lhb200_bls_batch_upload_async(b, sigs, msgs, pks, pk_offsets, rands, n_sets, b->s_main);
+    if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, b->s_main);
+    if (!rc) rc = lhb200_bls_batch_result(b, b->s_main, ok, set_status);
     cudaStreamSynchronize(b->s2);
     cudaStreamSynchronize(b->s3);
+    pool_release(b);
     return rc;
 }
 
@@ -815,6 +862,143 @@ int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, 
     LHB_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, c.stream));
     LHB_CUDA(cudaStreamSynchronize(c.stream));
     return LHB200_OK;
+}
+
+
+// ---- aggregation surface of a crypto/bls backend --------------------------------------------------------------
+// TAggregateSignature::add_assign / add_assign_aggregate (blst.rs:230-237) and AggregateSignature aggregation in
+// general: out = sum of n compressed signatures.  No subgroup check (blst.rs:231: "signature has already been subgroup
+// checked"); infinity encodings are the identity; n == 0 gives the infinity signature.  LHB200_EDECODE if any encoding
+// is malformed.
+int32_t lhb200_g2_aggregate(const uint8_t* sigs96, uint32_t n, uint8_t out96[96]) {
+    LHB_REQUIRE_READY();
+    if (!out96 || (n && !sigs96)) return LHB200_EINVAL;
+    if (n == 0) { memset(out96, 0, 96); out96[0] = 0xc0; return LHB200_OK; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const uint64_t n1 = cdiv(n, REDUCE_CHUNK) + 1;
+    const size_t b_in = ((size_t)n * 96 + 255) / 256 * 256, b_pts = (size_t)n * sizeof(G2Jac), b_t = (size_t)n1 * sizeof(G2Jac);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(b_in + b_pts + 2 * b_t + 512));
+    if (!d) return LHB200_ENOMEM;
+    G2Jac* pts = reinterpret_cast<G2Jac*>(d + b_in);
+    G2Jac* tmp[2] = {reinterpret_cast<G2Jac*>(d + b_in + b_pts), reinterpret_cast<G2Jac*>(d + b_in + b_pts + b_t)};
+    uint8_t* d_out = d + b_in + b_pts + 2 * b_t;
+    uint32_t* d_bad = reinterpret_cast<uint32_t*>(d_out + 128);
+    LHB_CUDA(cudaMemcpyAsync(d, sigs96, (size_t)n * 96, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    k_g2_load_points<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, n, pts, d_bad);
+    uint64_t launches = 2;
+    const G2Jac* cur = pts;
+    uint32_t m = n;
+    int flip = 0;
+    while (m > 1) {
+        const uint32_t mo = cdiv(m, REDUCE_CHUNK);
+        k_g2_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(cur, m, REDUCE_CHUNK, tmp[flip]);
+        launches++;
+        cur = tmp[flip];
+        flip ^= 1;
+        m = mo;
+    }
+    k_g2_store_point<<<1, 32, 0, c.stream>>>(cur, d_out);
+    count_launch(launches);
+    LHB_CUDA(cudaGetLastError());
+    uint8_t h[96];
+    uint32_t bad = 0;
+    LHB_CUDA(cudaMemcpyAsync(h, d_out, 96, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    if (bad) { set_error("g2_aggregate: %u malformed signature encodings", bad); return LHB200_EDECODE; }
+    memcpy(out96, h, 96);
+    return LHB200_OK;
+}
+
+// TAggregatePublicKey::aggregate (blst.rs:178-184): sum of n uncompressed keys ("already checked for subgroup and
+// infinity"), both serialisations out (either may be NULL).  n == 0 -> LHB200_EINVAL (blst: AGGR_TYPE_MISMATCH).
+// Malformed / off-curve key -> LHB200_EDECODE.
+int32_t lhb200_g1_aggregate(const uint8_t* pks96, uint32_t n, uint8_t* out48, uint8_t* out96) {
+    LHB_REQUIRE_READY();
+    if (!pks96 || n == 0 || (!out48 && !out96)) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const uint64_t n1 = cdiv(n, REDUCE_CHUNK) + 1;
+    const size_t b_in = ((size_t)n * 96 + 255) / 256 * 256, b_pts = (size_t)n * sizeof(G1Jac), b_t = (size_t)n1 * sizeof(G1Jac);
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(b_in + b_pts + 2 * b_t + 512));
+    if (!d) return LHB200_ENOMEM;
+    G1Jac* pts = reinterpret_cast<G1Jac*>(d + b_in);
+    G1Jac* tmp[2] = {reinterpret_cast<G1Jac*>(d + b_in + b_pts), reinterpret_cast<G1Jac*>(d + b_in + b_pts + b_t)};
+    uint8_t* d_out = d + b_in + b_pts + 2 * b_t;
+    uint32_t* d_bad = reinterpret_cast<uint32_t*>(d_out + 256);
+    LHB_CUDA(cudaMemcpyAsync(d, pks96, (size_t)n * 96, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    k_g1_load_points<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, n, pts, nullptr, nullptr, d_bad);
+    uint64_t launches = 2;
+    const G1Jac* cur = pts;
+    uint32_t m = n;
+    int flip = 0;
+    while (m > 1) {
+        const uint32_t mo = cdiv(m, REDUCE_CHUNK);
+        k_g1_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(cur, m, REDUCE_CHUNK, tmp[flip]);
+        launches++;
+        cur = tmp[flip];
+        flip ^= 1;
+        m = mo;
+    }
+    k_g1_store_point<<<1, 32, 0, c.stream>>>(cur, d_out, d_out + 64);
+    count_launch(launches);
+    LHB_CUDA(cudaGetLastError());
+    uint8_t h[160];
+    uint32_t bad = 0;
+    LHB_CUDA(cudaMemcpyAsync(h, d_out, 160, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    if (bad) { set_error("g1_aggregate: %u malformed or off-curve keys", bad); return LHB200_EDECODE; }
+    if (out48) memcpy(out48, h, 48);
+    if (out96) memcpy(out96, h + 64, 96);
+    return LHB200_OK;
+}
+
+// TPublicKey::deserialize_uncompressed (blst.rs:142-150), batch form: encoding and on-curve checks, NO subgroup check
+// (blst's P1 deserialize does none).  status[i]: 0 ok, 1 infinity, 2 bad encoding / not on the curve.  pk48 (optional):
+// the compressed form of every accepted key (zeros otherwise).
+int32_t lhb200_g1_deserialize_uncompressed(const uint8_t* pks96, uint32_t n, uint8_t* pk48, uint8_t* status) {
+    LHB_REQUIRE_READY();
+    if (n == 0) return LHB200_OK;
+    if (!pks96 || !status) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const size_t b_in = ((size_t)n * 96 + 255) / 256 * 256, b_48 = ((size_t)n * 48 + 255) / 256 * 256;
+    uint8_t* d = static_cast<uint8_t*>(dev_scratch(b_in + b_48 + n + 512));
+    if (!d) return LHB200_ENOMEM;
+    uint8_t *d48 = d + b_in, *dst = d48 + b_48;
+    uint32_t* d_bad = reinterpret_cast<uint32_t*>(dst + (n + 255) / 256 * 256);
+    LHB_CUDA(cudaMemcpyAsync(d, pks96, (size_t)n * 96, cudaMemcpyHostToDevice, c.stream));
+    LHB_CUDA(cudaMemsetAsync(d_bad, 0, 4, c.stream));
+    k_g1_load_points<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, c.stream>>>(d, n, nullptr, pk48 ? d48 : nullptr, dst, d_bad);
+    count_launch();
+    LHB_CUDA(cudaGetLastError());
+    if (pk48) LHB_CUDA(cudaMemcpyAsync(pk48, d48, (size_t)n * 48, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaStreamSynchronize(c.stream));
+    return LHB200_OK;
+}
+
+// TAggregateSignature::aggregate_verify (blst.rs:263-273; generic_aggregate_signature.rs:213-222):
+// e(g1, sig) == prod_i e(pk_i, H(m_i)) with the signature subgroup-checked.  n == 0 -> *ok = 0.
+// Runs on the batch pipeline: set 0 carries `sig`, the other sets the infinity signature, all blinding scalars are 1,
+// so prod_i e(pk_i, H(m_i)) * e(-g1, sig) == 1 is exactly the check.
+int32_t lhb200_aggregate_verify(const uint8_t sig96[96], const uint8_t* msgs, const uint8_t* pks96, uint32_t n, uint8_t* ok) {
+    LHB_REQUIRE_READY();
+    if (!ok) return LHB200_EINVAL;
+    *ok = 0;
+    if (n == 0) return LHB200_OK;
+    if (!sig96 || !msgs || !pks96) return LHB200_EINVAL;
+    std::vector<uint8_t> sigs((size_t)n * 96, 0);
+    std::vector<uint32_t> offs(n + 1);
+    std::vector<uint64_t> ones(n, 1);
+    memcpy(sigs.data(), sig96, 96);
+    for (uint32_t i = 1; i < n; i++) sigs[(size_t)i * 96] = 0xc0;
+    for (uint32_t i = 0; i <= n; i++) offs[i] = i;
+    return lhb200_verify_signature_sets(sigs.data(), msgs, pks96, offs.data(), ones.data(), n, ok, nullptr);
 }
 
 // Test hook: run one pipeline stage on a single device thread (op codes in bls/debug.cuh).

@@ -65,6 +65,7 @@ void* pinned_scratch(size_t nbytes) {
 }
 
 int32_t merkle_init();  // merkle_host.cu
+void merkle_shutdown();
 int32_t bls_init();     // bls_host.cu
 void bls_shutdown();
 
@@ -115,7 +116,8 @@ void lhb200_shutdown(void) {
     std::lock_guard<std::recursive_mutex> g(c.mu);
     if (!c.ready) return;
     cudaStreamSynchronize(c.stream);
-    bls_shutdown();
+    bls_shutdown();     // idle batch handles (device buffers, streams, events of the old context)
+    merkle_shutdown();  // the recycled state arena
     if (c.d_scratch) cudaFree(c.d_scratch);
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
     c.d_scratch = nullptr; c.d_scratch_bytes = 0;

@@ -457,6 +457,15 @@ struct ShardedList {
 
 static uint8_t* g_spare_arena = nullptr;  // guarded by ctx().mu
 static size_t g_spare_bytes = 0;
+// lhb200_shutdown: the recycled arena belongs to the context that is going away
+namespace lhb200 {
+void merkle_shutdown();
+}
+void lhb200::merkle_shutdown() {
+    if (g_spare_arena) cudaFree(g_spare_arena);
+    g_spare_arena = nullptr;
+    g_spare_bytes = 0;
+}
 
 struct lhb200_state {
     uint8_t* arena = nullptr;

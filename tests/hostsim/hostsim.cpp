@@ -228,7 +228,7 @@ EXPORT int hs_sop2(int k, const uint32_t* xa, const uint32_t* ya, const uint32_t
     return -1;
 }
 
-// ---- the cooperative Miller program (bls/miller_coop.cuh) run lane by lane: NT = 12 lanes = 2 groups per "block".
+// ---- the cooperative Miller program (bls/miller_coop.cuh) run lane by lane: NT = 14 lanes = 2 groups + 2 idle lanes per "warp".
 // n pairs (P_j uncompressed G1 given as 2 P_j in projective form, Q_j compressed G2 handed over in Jacobian form with
 // Z != 1); status[j] != 0 marks a set as skipped; with_extra appends (-g1, Q_extra).  Blocks of `spb` sets.
 // out = final_exp(product of all group products) (576 bytes).
@@ -238,7 +238,7 @@ struct ExecHost {
 };
 EXPORT int hs_miller_coop(const uint8_t* p96, const uint8_t* q96, const uint8_t* status, int n, const uint8_t* extra_q96,
                           int spb, uint8_t* out576) {
-    constexpr int NT = 12;
+    constexpr int NT = 14;   // two working groups + two idle lanes (the device has 30 + 2)
     std::vector<G1Proj3> P(n); std::vector<G2Jac> H(n);
     for (int j = 0; j < n; j++) {
         G1Affine p; G2Affine q;
@@ -258,22 +258,22 @@ EXPORT int hs_miller_coop(const uint8_t* p96, const uint8_t* q96, const uint8_t*
         G2Jac d; if (rc == DEC_OK) { jac_dbl(d, extra); jac_add(extra, d, extra); jac_neg(d, d); jac_add(extra, extra, d); }  // same point, Z != 1
     }
     const uint32_t n_total = n + (have_extra ? 1 : 0);
-    const uint32_t n_blocks = (n_total + spb - 1) / spb;
+    const uint32_t n_blocks = (n_total + spb - 1) / spb;          // "warps" of NT lanes
     const uint32_t rounds_cap = (spb + NT - 1) / NT;
     std::vector<Fp12> outs(n_blocks * (NT / 6));
+    G1Proj3 neg_g1; neg_g1.px = G1_GEN_X; fp_neg(neg_g1.py, G1_GEN_Y); neg_g1.pz = FP_ONE;
     for (uint32_t b = 0; b < n_blocks; b++) {
-        std::vector<uint32_t> smem(mc::NSLOT * NL * NT + NT, 0xdeadbeefu);
+        std::vector<uint32_t> smem(mc::region_words<NT>(), 0xdeadbeefu);
         std::vector<uint32_t> scratch((size_t)rounds_cap * 2 * mc::TWORDS * NT, 0xabababab);
         ExecHost<NT> ex;
         ex.lanes.resize(NT);
         for (int t = 0; t < NT; t++) {
             mc::Lane<NT>& L = ex.lanes[t];
-            L.tid = t; L.t = t % 6; L.c = Col<NT>::make(smem.data(), t);
+            L.lane = t; L.t = t % 6; L.idle = t >= mc::lanes_used<NT>(); L.c = Col<NT>::make(smem.data(), t);
             L.act = reinterpret_cast<uint8_t*>(smem.data() + mc::NSLOT * NL * NT);
             L.active = false; L.extra = false; L.set = 0;
         }
         mc::Args a;
-        G1Proj3 neg_g1; neg_g1.px = G1_GEN_X; fp_neg(neg_g1.py, G1_GEN_Y); neg_g1.pz = FP_ONE;
         a.P = P.data(); a.H = H.data(); a.status = status; a.n = n; a.extra_q = have_extra ? &extra : nullptr; a.extra_p = &neg_g1;
         a.lo = b * spb; a.hi = std::min<uint32_t>(n_total, a.lo + spb);
         a.scratch = scratch.data(); a.out = &outs[b * (NT / 6)];

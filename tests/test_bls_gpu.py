@@ -405,3 +405,124 @@ def test_cpp_host_layer_on_golden_vectors(gpu, tmp_path):
     r = subprocess.run([os.path.join(O.ROOT, "tests", "cpp", "host_mirror_test"), str(p)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "OK 22 sets" in r.stdout
+
+
+def test_aggregate_signature_add_assign_matches_oracle(bls):
+    """TAggregateSignature::add_assign / add_assign_aggregate (blst.rs:230-237) built the way
+    crypto/bls/tests/tests.rs:170-188 builds its aggregates: infinity, then add_assign every signer's signature.
+    The aggregate's bytes must equal the oracle's G2 sum, and verify like tests.rs:248-342 expects."""
+    msg = (42).to_bytes(32, "big")                                   # Hash256::from_low_u64_be(42)
+    for n in (1, 2, 5, 33):
+        sks = [bls.SecretKey.deserialize(secret_from_u64(i)) for i in range(n)]
+        agg = bls.AggregateSignature.infinity()
+        for sk in sks:
+            agg.add_assign(sk.sign(msg))
+        acc = None
+        h = B.hash_to_g2(msg)
+        for i in range(n):
+            acc = B.g2_add(acc, B.g2_mul(h, i + 1))
+        assert agg.serialize() == B.g2_compress(acc)
+        assert bls.AggregateSignature.aggregate([sk.sign(msg) for sk in sks]).serialize() == B.g2_compress(acc)
+        keys = [sk.public_key() for sk in sks]
+        assert agg.fast_aggregate_verify(msg, keys)
+        assert agg.aggregate_verify([msg] * n, keys)                 # tests.rs:232-240
+        assert not agg.aggregate_verify([msg] * n, keys[::-1][:n - 1] + keys[:1]) if n > 2 else True
+    # tests.rs:196-220 builder cases
+    keys = [bls.SecretKey.deserialize(secret_from_u64(i)).public_key() for i in range(2)]
+    agg = bls.AggregateSignature.infinity()
+    for i in range(2):
+        agg.add_assign(bls.SecretKey.deserialize(secret_from_u64(i)).sign(msg))
+    before = agg.serialize()
+    agg.add_assign(bls.Signature.empty())                            # aggregate_empty_sig: unchanged
+    agg.add_assign_aggregate(bls.AggregateSignature.empty())         # aggregate_empty_agg_sig: unchanged
+    agg.add_assign(bls.Signature.deserialize(bls.INFINITY_SIGNATURE))  # aggregate_infinity_sig: unchanged
+    assert agg.serialize() == before and agg.fast_aggregate_verify(msg, keys)
+    e = bls.AggregateSignature.empty()
+    e.add_assign(bls.SecretKey.deserialize(secret_from_u64(0)).sign(msg))   # empty + sig = infinity + sig
+    assert e.fast_aggregate_verify(msg, keys[:1])
+    assert not bls.AggregateSignature.empty().aggregate_verify([msg], keys[:1])
+    assert not bls.AggregateSignature.infinity().aggregate_verify([msg], keys[:1])
+    assert not agg.aggregate_verify([], [])                          # generic_aggregate_signature.rs:214-216
+    with pytest.raises(bls.BlstError):
+        bls.aggregate_signatures(before + bytes([0x80]) + bytes(95))  # not a valid G2 encoding
+
+
+def test_aggregate_verify_distinct_messages(bls):
+    """blst.rs:263-273: one aggregate signature over different messages (the EF aggregate_verify shape)."""
+    n = 7
+    msgs = [hashlib.sha256(b"agv%d" % i).digest() for i in range(n)]
+    sks = [bls.SecretKey.deserialize(secret_from_u64(i)) for i in range(n)]
+    agg = bls.AggregateSignature.aggregate([sk.sign(m) for sk, m in zip(sks, msgs)])
+    keys = [sk.public_key() for sk in sks]
+    assert agg.aggregate_verify(msgs, keys)
+    assert not agg.aggregate_verify(msgs[::-1], keys)
+    assert not agg.aggregate_verify(msgs[:-1], keys[:-1])
+    assert B.multi_pairing_is_one([(B.g1_neg(B.G1_GEN), B.g2_decompress(agg.serialize()))] +
+                                  [(B.g1_decompress(k.serialize()), B.hash_to_g2(m)) for k, m in zip(keys, msgs)])
+
+
+def test_aggregate_public_key_and_uncompressed_deserialize(bls):
+    """TAggregatePublicKey::aggregate (blst.rs:178-184) and TPublicKey::deserialize_uncompressed (blst.rs:142-150)."""
+    n = 9
+    keys = [bls.SecretKey.deserialize(secret_from_u64(i)).public_key() for i in range(n)]
+    apk = bls.AggregatePublicKey.aggregate(keys).to_public_key()
+    ref = B.g1_mul(B.G1_GEN, sum(range(1, n + 1)))
+    assert apk.serialize() == B.g1_compress(ref) and apk.serialize_uncompressed() == B.g1_uncompressed(ref)
+    with pytest.raises(bls.BlstError):
+        bls.AggregatePublicKey.aggregate([])
+    pk = bls.PublicKey.deserialize_uncompressed(keys[3].serialize_uncompressed())
+    assert pk == keys[3] and pk.serialize() == keys[3].serialize()
+    u = bytearray(keys[3].serialize_uncompressed())
+    with pytest.raises(bls.BlstError):
+        bls.PublicKey.deserialize_uncompressed(bytes([u[0] | 0x80]) + bytes(u[1:]))    # compression flag set
+    with pytest.raises(bls.BlstError):
+        bls.PublicKey.deserialize_uncompressed(bytes([u[0] | 0x20]) + bytes(u[1:]))    # sort flag set
+    u[95] ^= 1
+    with pytest.raises(bls.BlstError):
+        bls.PublicKey.deserialize_uncompressed(bytes(u))                               # not on the curve
+    with pytest.raises(bls.InvalidInfinityPublicKey):
+        bls.PublicKey.deserialize_uncompressed(bytes([0x40]) + bytes(95))
+    with pytest.raises(bls.BlstError):
+        bls.PublicKey.deserialize_uncompressed(bytes([0x40]) + bytes(94) + b"\x01")    # infinity flag with payload
+    with pytest.raises(bls.InvalidByteLength):
+        bls.PublicKey.deserialize_uncompressed(bytes(48))
+
+
+def test_concurrent_callers_overlap_on_the_device(bls):
+    """Lighthouse calls verify_signature_sets from up to num_cpus blocking workers with <= 64-set gossip batches
+    (beacon_processor/src/lib.rs:202-203,256).  Eight threads hammer lhb200_verify_signature_sets with their own 64-set
+    batches (one of them carrying a bad set): every verdict must be right, and the eight callers together must finish
+    far sooner than eight times a lone caller (each call borrows its own batch handle and stream)."""
+    import threading
+    import time
+    from lighthouse_b200.synthetic import attestation_batch
+    n_thr, n_sets, reps = 8, 64, 6
+    batches = []
+    for t in range(n_thr):
+        ab = attestation_batch(n_sets, keys_per_set=16, n_validators=1024, seed=700 + t)
+        sigs = bytearray(ab.sigs)
+        if t == 3:
+            sigs[96 * 17:96 * 18] = ab.sigs[96 * 18:96 * 19]     # set 17 carries set 18's signature
+        batches.append((bytes(sigs), ab.msgs, ab.pks, ab.offsets, t != 3))
+    for b in batches:                                              # warm the handle pool / caches
+        assert bls.verify_signature_sets_raw(*b[:4]) == b[4]
+
+    def worker(b, out, k):
+        for _ in range(reps):
+            out[k] = out[k] and (bls.verify_signature_sets_raw(*b[:4]) == b[4])
+
+    res = [True] * n_thr
+    t0 = time.perf_counter()
+    worker(batches[0], res, 0)
+    t_one = time.perf_counter() - t0
+    ths = [threading.Thread(target=worker, args=(batches[k], res, k)) for k in range(n_thr)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    t_all = time.perf_counter() - t0
+    assert all(res)
+    speedup = n_thr * t_one / t_all
+    print(f"1 caller: {reps * n_sets / t_one:.0f} sets/s; {n_thr} callers: {n_thr * reps * n_sets / t_all:.0f} sets/s ({speedup:.2f}x)")
+    assert speedup > 2.5, (t_one, t_all)
