@@ -119,6 +119,9 @@ LHB200_API int32_t lhb200_state_stage_deneb_shard(const uint8_t* ssz, uint64_t l
                                                   lhb200_state** out);
 LHB200_API int32_t lhb200_state_shard_roots(lhb200_state* st, uint8_t* out, uint32_t* n_lists);
 LHB200_API int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t out[32]);
+/* Steps 2-4 in one call over the library's communicator (lhb200_comm_init): subtree roots stay on the device, one
+ * ncclAllGather, every rank folds the top; only the 32-byte root crosses the host link. */
+LHB200_API int32_t lhb200_state_root_sharded(lhb200_state* st, uint8_t out[32]);
 LHB200_API int32_t lhb200_state_release(lhb200_state* st);
 /* Algorithmic work of the last root computed on this handle: number of hash32_concat units. */
 LHB200_API uint64_t lhb200_state_hash_units(const lhb200_state* st);
@@ -226,6 +229,23 @@ LHB200_API int32_t lhb200_sign(const uint8_t* sk32, const uint8_t* msg32, uint32
 LHB200_API int32_t lhb200_g1_decompress_validate(const uint8_t* pk48, uint32_t n, uint8_t* pk96, uint8_t* status);
 /* Signature::deserialize, batch form (blst.rs:192-194): 192-byte affine out; status 0 ok, 1 infinity, 2 bad. */
 LHB200_API int32_t lhb200_g2_decompress(const uint8_t* sig96, uint32_t n, uint8_t* out192, uint8_t* status);
+
+/* ---- multi-GPU: the library's own NCCL communicator (one process per GPU) ----
+ * Rank 0 obtains the 128-byte id (ncclGetUniqueId) and ships it to the other ranks by any means; every rank then calls
+ * lhb200_comm_init (collective).  NCCL is dlopen'ed on first use (libnccl.so.2); single-GPU users never load it.
+ * The collectives below run on DEVICE buffers on the library's streams — no host hop, no torch. */
+LHB200_API int32_t lhb200_comm_unique_id(uint8_t id[128]);
+LHB200_API int32_t lhb200_comm_init(int32_t rank, int32_t world, const uint8_t id[128]);
+LHB200_API int32_t lhb200_comm_destroy(void);
+LHB200_API int32_t lhb200_comm_info(int32_t* rank, int32_t* world);
+/* bls::verify_signature_sets sharded over the communicator: each rank passes its contiguous shard of the sets (an empty
+ * shard is allowed); per-rank batch check + ONE ncclAllReduce(min) of the device verdicts; *ok = verdict of the whole
+ * batch on every rank.  Shard with equal key counts (lighthouse_b200/parallel.py::shard_ranges_by_keys). */
+LHB200_API int32_t lhb200_verify_signature_sets_collective(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks,
+                                                           const uint32_t* pk_offsets, const uint64_t* rands,
+                                                           uint32_t n_sets, uint8_t* ok);
+/* Staged form: ncclAllReduce(min) of a batch's device verdict, enqueued on `stream` behind verify_enqueue. */
+LHB200_API int32_t lhb200_bls_batch_allreduce_verdict(lhb200_bls_batch* b, void* stream);
 
 /* ---- aggregation surface of a crypto/bls backend (crypto/bls/src/impls/blst.rs) ----
  * TAggregateSignature::add_assign / add_assign_aggregate (blst.rs:230-237): out = sum of n compressed signatures; no

@@ -124,3 +124,10 @@ _sig("lhb200_g2_aggregate", C.c_int32, vp, C.c_uint32, vp)
 _sig("lhb200_g1_aggregate", C.c_int32, vp, C.c_uint32, vp, vp)
 _sig("lhb200_g1_deserialize_uncompressed", C.c_int32, vp, C.c_uint32, vp, vp)
 _sig("lhb200_aggregate_verify", C.c_int32, vp, vp, vp, C.c_uint32, vp)
+_sig("lhb200_comm_unique_id", C.c_int32, vp)
+_sig("lhb200_comm_init", C.c_int32, C.c_int32, C.c_int32, vp)
+_sig("lhb200_comm_destroy", C.c_int32)
+_sig("lhb200_comm_info", C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
+_sig("lhb200_verify_signature_sets_collective", C.c_int32, vp, vp, vp, vp, vp, C.c_uint32, vp)
+_sig("lhb200_bls_batch_allreduce_verdict", C.c_int32, vp, vp)
+_sig("lhb200_state_root_sharded", C.c_int32, vp, vp)

@@ -5,8 +5,8 @@
 // that spilled 74 GB per 100 k-set launch to DRAM.  Here
 //   * a GROUP of six lanes shares one Fp12 accumulator f = sum a_k w^k (Fp12 = Fp2[w]/(w^6 - xi)); lane t owns the Fp2
 //     coefficient a_t.  f^2 and the sparse products f * l are SCHOOLBOOK in the w-basis: lane t computes its own
-//     output coefficient as one fused sum of Fp2 products (sop.cuh: lazy reduction, no Karatsuba glue, uniform code
-//     across the six lanes);
+//     output coefficient as fused sums of products (sop.cuh: one reduction per sum, Karatsuba inside Fp2 on reduced
+//     values only — no double-width glue; uniform code across the six lanes);
 //   * every lane owns one SignatureSet per round: its point T (homogeneous projective, Costello-Lange-Naehrig doubling:
 //     3 M + 6 S in Fp2), the line through it and the temporaries live in the lane's private shared-memory column —
 //     18 Fp slots = 864 B per lane: 3 for the coefficient of f, 1 scratch, and SEVEN Fp2 slots whose roles (X, Y, Z of
@@ -33,7 +33,7 @@ namespace lhb200 {
 namespace bls {
 namespace mc {
 
-constexpr int S_F0 = 0, S_F1 = 1, S_NF1 = 2;     // own coefficient of f: (re, im, p - im)
+constexpr int S_F0 = 0, S_F1 = 1, S_FS = 2;      // own coefficient of f: (re, im, re + im)
 constexpr int S_SCR = 3;
 constexpr int S_W = 4;                            // seven Fp2 slots: S_W + 2 k
 constexpr int NSLOT = 18;
@@ -223,13 +223,34 @@ LHB_HD LHB_INLINE void roles_after_add(Roles& r) {
     r = n;
 }
 
-// ---- f <- f^2: lane t's coefficient.  K = 8 (four Fp2 terms), X = Y = 1
+// The f-updates are sums of Fp2 products  sum_q u_q * a_q  computed Karatsuba-style WITHOUT double-width values:
+//     S0 = sum u_q.0 a_q.0,   S1 = sum u_q.1 a_q.1,   S2 = sum (u_q.0 + u_q.1)(a_q.0 + a_q.1)      (three fused sums)
+//     re = S0 - S1,   im = S2 - S0 - S1
+// 3 K products + 3 reductions instead of the schoolbook 4 K + 2; the coefficient is stored as (re, im, re + im) so the
+// y operand of the third sum streams from shared memory like the others.  S0 and S1 run as two interleaved windows,
+// S2 as a single one (all three at once would need 3 K x-operands + 72 window registers).
+template <int K, int NT>
+LHB_HD LHB_INLINE void sum_fp2_products(Lane<NT>& L, const SopX<K>& x0, const SopX<K>& x1, const Col<NT>* ycol) {
+    SopY<K> y0, y1, ys;
+    y0.stride = NT; y1.stride = NT; ys.stride = NT;
+#pragma unroll
+    for (int q = 0; q < K; q++) { y0.base[q] = ycol[q].at(S_F0); y1.base[q] = ycol[q].at(S_F1); ys.base[q] = ycol[q].at(S_FS); }
+    Fp s0, s1, s2;
+    fp_sop2<K>(s0, s1, x0, y0, x1, y1);                      // X = Y = 1
+    SopX<K> xs;
+#pragma unroll
+    for (int q = 0; q < K; q++) fp_add_nr(xs.x[q], x0.x[q], x1.x[q]);   // < 2p: X = 2, Y = 1, K X <= 8
+    fp_sop1<K>(s2, xs, ys);
+    fp_sub_inl(L.ra, s0, s1);
+    fp_sub_inl(s2, s2, s0);
+    fp_sub_inl(L.rb, s2, s1);
+}
+// ---- f <- f^2: lane t's coefficient (four Fp2 terms, schedule SQR_TERMS)
 template <int NT>
 LHB_HD LHB_INLINE void phase_sqr_compute(Lane<NT>& L) {
     const Col<NT> g = L.c.lane(-L.t);   // column of the group's lane 0
-    SopX<8> x;
-    SopY<8> ya, yb;
-    ya.stride = NT; yb.stride = NT;
+    SopX<4> x0, x1;
+    Col<NT> yc[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t e = SQR_TERMS[L.t][k];
@@ -240,14 +261,12 @@ LHB_HD LHB_INLINE void phase_sqr_compute(Lane<NT>& L) {
         if (e & 0x40) { fp_add_inl(u.c0, u.c0, u.c0); fp_add_inl(u.c1, u.c1, u.c1); }
         if (e & 0x80) fp2_mul_xi_inl(u, u);
         if (!valid) { fp_set_zero(u.c0); fp_set_zero(u.c1); }
-        x.x[2 * k] = u.c0; x.x[2 * k + 1] = u.c1;
-        const Col<NT> cj = g.lane(j);
-        ya.base[2 * k] = cj.at(S_F0); ya.base[2 * k + 1] = cj.at(S_NF1);   // u0 a0 + u1 (-a1)
-        yb.base[2 * k] = cj.at(S_F1); yb.base[2 * k + 1] = cj.at(S_F0);    // u0 a1 + u1 a0
+        x0.x[k] = u.c0; x1.x[k] = u.c1;
+        yc[k] = g.lane(j);
     }
-    fp_sop2<8>(L.ra, L.rb, x, ya, x, yb);
+    sum_fp2_products<4>(L, x0, x1, yc);
 }
-// ---- f <- f * l(owner): lane t's coefficient  a_t c0 + xi^[t<2] a_{t-2} c1 + xi^[t<3] a_{t-3} c4.  K = 6
+// ---- f <- f * l(owner): lane t's coefficient  a_t c0 + xi^[t<2] a_{t-2} c1 + xi^[t<3] a_{t-3} c4
 template <int NT>
 LHB_HD LHB_INLINE void phase_sparse_compute(Lane<NT>& L, const Roles& r, int owner) {
     const Col<NT> g = L.c.lane(-L.t);
@@ -257,23 +276,18 @@ LHB_HD LHB_INLINE void phase_sparse_compute(Lane<NT>& L, const Roles& r, int own
     oc.ld2(l0, r.l0); oc.ld2(l1, r.l1); oc.ld2(l4, r.l4);
     if (L.t < 2) fp2_mul_xi_inl(l1, l1);
     if (L.t < 3) fp2_mul_xi_inl(l4, l4);
-    SopX<6> x;
-    x.x[0] = l0.c0; x.x[1] = l0.c1; x.x[2] = l1.c0; x.x[3] = l1.c1; x.x[4] = l4.c0; x.x[5] = l4.c1;
+    SopX<3> x0, x1;
+    x0.x[0] = l0.c0; x0.x[1] = l1.c0; x0.x[2] = l4.c0;
+    x1.x[0] = l0.c1; x1.x[1] = l1.c1; x1.x[2] = l4.c1;
     const int i1 = L.t >= 2 ? L.t - 2 : L.t + 4, i2 = L.t >= 3 ? L.t - 3 : L.t + 3;
-    const Col<NT> c0 = L.c, c1 = g.lane(i1), c2 = g.lane(i2);
-    SopY<6> ya, yb;
-    ya.stride = NT; yb.stride = NT;
-    ya.base[0] = c0.at(S_F0); ya.base[1] = c0.at(S_NF1); ya.base[2] = c1.at(S_F0); ya.base[3] = c1.at(S_NF1);
-    ya.base[4] = c2.at(S_F0); ya.base[5] = c2.at(S_NF1);
-    yb.base[0] = c0.at(S_F1); yb.base[1] = c0.at(S_F0); yb.base[2] = c1.at(S_F1); yb.base[3] = c1.at(S_F0);
-    yb.base[4] = c2.at(S_F1); yb.base[5] = c2.at(S_F0);
-    fp_sop2<6>(L.ra, L.rb, x, ya, x, yb);
+    const Col<NT> yc[3] = {L.c, g.lane(i1), g.lane(i2)};
+    sum_fp2_products<3>(L, x0, x1, yc);
 }
 template <int NT>
 LHB_HD LHB_INLINE void phase_store_f(Lane<NT>& L) {
-    Fp n;
-    fp_neg(n, L.rb);
-    L.c.st(S_F0, L.ra); L.c.st(S_F1, L.rb); L.c.st(S_NF1, n);
+    Fp s;
+    fp_add_inl(s, L.ra, L.rb);
+    L.c.st(S_F0, L.ra); L.c.st(S_F1, L.rb); L.c.st(S_FS, s);
 }
 template <int NT>
 LHB_HD LHB_INLINE void phase_store_f_if(Lane<NT>& L, int owner) {
@@ -295,7 +309,7 @@ LHB_HD LHB_INLINE void miller_program(Exec& ex, const Args& a) {
     Roles R = roles_init();
     // f = 1; points
     MC_PHASE(Fp z; fp_set_zero(z); Fp one = FP_ONE;
-             L.c.st(S_F0, L.t == 0 ? one : z); L.c.st(S_F1, z); L.c.st(S_NF1, z));
+             L.c.st(S_F0, L.t == 0 ? one : z); L.c.st(S_F1, z); L.c.st(S_FS, L.t == 0 ? one : z));
     for (uint32_t r = 0; r < rounds; r++)
         MC_PHASE(lane_select(L, a, r);
                  phase_init_point(L, a, R, park_q(L, a, r));

@@ -678,6 +678,16 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     return LHB200_OK;
 }
 
+// ncclAllReduce(min) of the batch's device verdict over the library's communicator (lhb200_comm_init), enqueued on
+// `stream` right behind lhb200_bls_batch_verify_enqueue: the one collective of the sharded BLS path,
+// on the device buffer, no host hop.  A no-op without a communicator.
+int32_t lhb200_bls_batch_allreduce_verdict(lhb200_bls_batch* b, void* stream) {
+    LHB_REQUIRE_READY();
+    if (!b) return LHB200_EINVAL;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
+    return comm_allreduce_min_u8(b->d_ok, 1, s);
+}
+
 int32_t lhb200_bls_batch_result(lhb200_bls_batch* b, void* stream, uint8_t* ok, uint8_t* set_status) {
     LHB_REQUIRE_READY();
     if (!b || !ok) return LHB200_EINVAL;
@@ -774,6 +784,40 @@ int32_t lhb200_verify_signature_sets(const uint8_t* sigs, const uint8_t* msgs, c
     int32_t rc = lhb200_bls_batch_upload_async(b, sigs, msgs, pks, pk_offsets, rands, n_sets, b->s_main);
     if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, b->s_main);
     if (!rc) rc = lhb200_bls_batch_result(b, b->s_main, ok, set_status);
+    cudaStreamSynchronize(b->s2);
+    cudaStreamSynchronize(b->s3);
+    pool_release(b);
+    return rc;
+}
+
+// verify_signature_sets over the ranks of the library's communicator: every rank passes ITS shard of the sets (possibly
+// empty: an empty shard contributes `true`), runs the batch check on it with its own blinding scalars and final
+// exponentiation, and the verdicts are combined by one ncclAllReduce(min) on the device (SURVEY.md §8e option (a)).
+// *ok is the verdict of the WHOLE batch on every rank.  Without a communicator this is lhb200_verify_signature_sets
+// (except that n_sets == 0 yields *ok = 1: "this shard has nothing to object to").
+int32_t lhb200_verify_signature_sets_collective(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks,
+                                                const uint32_t* pk_offsets, const uint64_t* rands, uint32_t n_sets,
+                                                uint8_t* ok) {
+    LHB_REQUIRE_READY();
+    if (!ok) return LHB200_EINVAL;
+    *ok = 0;
+    if (n_sets && !pk_offsets) return LHB200_EINVAL;
+    const uint64_t n_keys = n_sets ? pk_offsets[n_sets] : 0;
+    lhb200_bls_batch* b = pool_acquire(std::max<uint32_t>(n_sets, 1), n_keys);
+    if (!b) return LHB200_ENOMEM;
+    int32_t rc = LHB200_OK;
+    if (n_sets) {
+        rc = lhb200_bls_batch_upload_async(b, sigs, msgs, pks, pk_offsets, rands, n_sets, b->s_main);
+        if (!rc) rc = lhb200_bls_batch_verify_enqueue(b, b->s_main);
+    } else {
+        const uint8_t one = 1;
+        cudaError_t e = cudaMemcpyAsync(b->d_ok, &one, 1, cudaMemcpyHostToDevice, b->s_main);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->s_main);   // `one` is a stack variable
+        if (e != cudaSuccess) rc = cuda_fail(e, "empty shard verdict");
+        b->n = 0;
+    }
+    if (!rc) rc = comm_allreduce_min_u8(b->d_ok, 1, b->s_main);
+    if (!rc) rc = lhb200_bls_batch_result(b, b->s_main, ok, nullptr);
     cudaStreamSynchronize(b->s2);
     cudaStreamSynchronize(b->s3);
     pool_release(b);

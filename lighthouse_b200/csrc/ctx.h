@@ -46,6 +46,13 @@ void* pinned_scratch(size_t nbytes);
         }                                                                            \
     } while (0)
 
+// the library's NCCL communicator (comm.cu); no-ops / local copies when no communicator is initialised
+bool comm_active();
+int comm_world();
+int comm_rank();
+int32_t comm_allreduce_min_u8(void* d_buf, size_t n, cudaStream_t s);
+int32_t comm_allgather_bytes(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s);
+
 inline void count_launch(uint64_t n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace lhb200

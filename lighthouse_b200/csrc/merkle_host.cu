@@ -354,7 +354,7 @@ static int32_t plan_upload(Plan& pl, cudaStream_t s, std::vector<HashOp>& ops_so
 // Generic runner for "one input blob -> one root" host entry points.
 //   stage(plan, d_in) describes the work given the device copy of the input.
 template <class F>
-static int32_t run_simple(const uint8_t* h_in, size_t in_bytes, uint8_t out[32], F&& describe) {
+static int32_t run_simple(const uint8_t* h_in, size_t in_bytes, uint8_t out[32], F&& describe, bool in_on_device = false) {
     Ctx& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
     // pass 1: dry run to size
@@ -383,7 +383,9 @@ static int32_t run_simple(const uint8_t* h_in, size_t in_bytes, uint8_t out[32],
     if (rc) return rc;
     // H2D input (zero the padding tail so packed lists see zero-filled last chunks)
     LHB_CUDA(cudaMemsetAsync(d_in + in_bytes / 256 * 256, 0, in_pad - in_bytes / 256 * 256, c.stream));
-    if (in_bytes) {
+    if (in_bytes && in_on_device) {
+        LHB_CUDA(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyDeviceToDevice, c.stream));
+    } else if (in_bytes) {
         cudaPointerAttributes at;
         bool pinned = cudaPointerGetAttributes(&at, h_in) == cudaSuccess && at.type == cudaMemoryTypeHost;
         cudaGetLastError();
@@ -477,6 +479,7 @@ struct lhb200_state {
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around k_validator_roots
     lhb200::ShardCfg shard;
     std::vector<lhb200::ShardedList> sharded;
+    uint8_t* d_coll = nullptr;              // lhb200_state_root_sharded: gather ops | own subtree roots | all ranks' roots
     std::vector<lhb200::StageCopy> copies;  // SSZ ranges resident in the arena (for lhb200_state_patch)
     // warm path (lhb200_state_enable_incremental): full level arrays per big list + dirty leaves since the last root
     struct Tree { lhb200::TreeDev dev; uint64_t src_off, src_bytes; uint32_t item_bytes; std::vector<uint32_t> dirty; };
@@ -882,8 +885,7 @@ int32_t lhb200_state_shard_roots(lhb200_state* st, uint8_t* out, uint32_t* n_lis
 
 // Fold the all-gathered subtree roots (rank-major: gathered[(g * n_lists + l) * 32]) into the state root.
 // Must be called after lhb200_state_shard_roots on the same handle (the unsharded field roots live in its arena).
-int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t out[32]) {
-    LHB_REQUIRE_READY();
+static int32_t state_combine_impl(lhb200_state* st, const uint8_t* gathered, uint8_t out[32], bool on_device) {
     if (!st || !gathered || !out) return LHB200_EINVAL;
     const uint32_t n = (uint32_t)st->sharded.size(), world = st->shard.world;
     uint32_t lg = 0;
@@ -901,7 +903,45 @@ int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t 
             f[L.field] = r;
         }
         return p.container(f);
-    });
+    }, on_device);
+}
+int32_t lhb200_state_combine(lhb200_state* st, const uint8_t* gathered, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    return state_combine_impl(st, gathered, out, false);
+}
+
+// One BeaconState root over the ranks of the library's communicator (lhb200_comm_init), on a handle staged with
+// lhb200_state_stage_deneb_shard(rank, world): the shard's subtree roots stay on the device, one ncclAllGather of
+// n_lists x 32 B per rank, then every rank folds the top (log2(world) levels, zero ladders, length mix-ins, container)
+// — all on the library's stream; the only host transfer is the 32-byte root (SURVEY.md §8e "Tree hash").
+int32_t lhb200_state_root_sharded(lhb200_state* st, uint8_t out[32]) {
+    LHB_REQUIRE_READY();
+    if (!st || !out) return LHB200_EINVAL;
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const uint32_t n = (uint32_t)st->sharded.size(), world = st->shard.world;
+    if ((int)world != comm_world() && world != 1) { set_error("state sharded %u ways but the communicator has %d ranks", world, comm_world()); return LHB200_EINVAL; }
+    int32_t rc = lhb200_state_root_enqueue(st, c.stream, nullptr);
+    if (rc) return rc;
+    if (n == 0) { set_error("handle is not sharded"); return LHB200_EINVAL; }
+    std::vector<HashOp> gath(n);
+    for (uint32_t i = 0; i < n; i++) gath[i] = {0, st->sharded[i].local_op, 0};
+    if (!st->d_coll) {   // [gather ops | my roots | all roots], owned by the handle (dev_scratch is reused by the combine)
+        LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->d_coll), 4096 + (size_t)(world + 1) * n * 32 + 512));
+    }
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(n * sizeof(HashOp) + 512));
+    if (!h) return LHB200_ENOMEM;
+    memcpy(h, gath.data(), n * sizeof(HashOp));
+    uint8_t* d_ops = st->d_coll;
+    uint8_t* d_mine = st->d_coll + 4096;
+    uint8_t* d_all = d_mine + ((n * 32 + 255) / 256) * 256;
+    if (n * sizeof(HashOp) > 4096) return LHB200_EINVAL;
+    LHB_CUDA(cudaMemcpyAsync(d_ops, h, n * sizeof(HashOp), cudaMemcpyHostToDevice, c.stream));
+    k_gather_nodes<<<1, 32, 0, c.stream>>>(reinterpret_cast<const HashOp*>(d_ops), (int)n, d_mine);
+    count_launch();
+    rc = comm_allgather_bytes(d_mine, d_all, (size_t)n * 32, c.stream);
+    if (rc) return rc;
+    return state_combine_impl(st, d_all, out, true);
 }
 
 // Apply same-length mutations to a staged state (the resident analogue of BeaconState::apply_pending_mutations,
@@ -1153,6 +1193,7 @@ int32_t lhb200_state_release(lhb200_state* st) {
     if (st->d_levels) cudaFree(st->d_levels);
     if (st->d_trees) cudaFree(st->d_trees);
     if (st->d_dirty) cudaFree(st->d_dirty);
+    if (st->d_coll) cudaFree(st->d_coll);
     delete st;
     return LHB200_OK;
 }

@@ -141,37 +141,97 @@ class AttestationBatch:
         return len(self.sigs) + len(self.msgs) + len(self.pks) + 8 * self.n_sets
 
 
-def attestation_batch(n_sets, keys_per_set=128, n_validators=16384, seed=0x11570000, epoch=100):
-    """n_sets aggregate attestations, each signed by `keys_per_set` distinct validators.  Needs lhb200.init()."""
-    from . import bls
-    assert n_validators & (n_validators - 1) == 0 and keys_per_set <= n_validators
+def sets_workload(key_counts, n_validators=16384, seed=0x11570000, epoch=100, first_index=0):
+    """The DEFINITION of a synthetic batch of SignatureSets, without any curve arithmetic (numpy + hashlib only, so the
+    CPU reference arm of bench.py builds the very same workload without loading the CUDA library):
+    set j (global index first_index + j) is signed by key_counts[j] distinct validators perm[(a_j + t b_j) mod V]
+    (b_j odd, V a power of two) over the attestation signing root of its global index.
+    -> dict(committees uint32[K], offsets uint32[n+1], agg_sk list[int] (sum of the signers' interop keys mod r),
+            msgs bytes n*32, n_validators)"""
+    key_counts = np.asarray(key_counts, dtype=np.int64)
+    n_sets = len(key_counts)
+    V = n_validators
+    assert V & (V - 1) == 0 and int(key_counts.max(initial=0)) <= V
     rng = np.random.default_rng(seed)
-    sks = interop_secret_keys(n_validators)
-    sk_bytes = b"".join(s.to_bytes(32, "big") for s in sks)
-    _, pk96 = bls.sk_to_pk(sk_bytes)
-    pk_tab = np.frombuffer(pk96, dtype=np.uint8).reshape(n_validators, 96)
-    # committee j = perm[(a_j + t*b_j) mod V], b_j odd  (distinct because V is a power of two)
-    perm = rng.permutation(n_validators)
-    a = rng.integers(0, n_validators, size=n_sets)
-    b = rng.integers(0, n_validators // 2, size=n_sets) * 2 + 1
-    t = np.arange(keys_per_set)
-    committees = perm[(a[:, None] + t[None, :] * b[:, None]) % n_validators]
-    # aggregate secret keys: limb-wise sums (8 x 32-bit words held in uint64), recombined with Python ints
+    perm = rng.permutation(V)
+    # a_j, b_j are functions of the GLOBAL set index, so a shard [first_index, first_index + n) of a larger batch is
+    # generated exactly as the same range of the whole batch
+    gidx = np.arange(first_index, first_index + n_sets, dtype=np.uint64)
+    mix = (gidx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    a = (mix >> np.uint64(7)) % np.uint64(V)
+    b = ((mix >> np.uint64(29)) % np.uint64(V // 2)) * np.uint64(2) + np.uint64(1)
+    offsets = np.zeros(n_sets + 1, dtype=np.uint64)
+    np.cumsum(key_counts, out=offsets[1:])
+    K = int(offsets[-1])
+    set_of_key = np.repeat(np.arange(n_sets), key_counts)
+    t = np.arange(K, dtype=np.uint64) - offsets[:-1][set_of_key]
+    committees = perm[((a[set_of_key] + t * b[set_of_key]) % np.uint64(V)).astype(np.int64)].astype(np.uint32)
+    sks = interop_secret_keys(V)
     words = np.array([[(s >> (32 * w)) & 0xFFFFFFFF for w in range(8)] for s in sks], dtype=np.uint64)
     agg = []
-    for lo in range(0, n_sets, 8192):
-        ws = words[committees[lo:lo + 8192]].sum(axis=1)  # [chunk, 8]
-        for row in ws:
-            v = 0
-            for w in range(8):
-                v += int(row[w]) << (32 * w)
-            agg.append(v % CURVE_ORDER)
+    CH = 1 << 20
+    sums = np.zeros((n_sets, 8), dtype=np.uint64)
+    # limb-wise sums (8 x 32-bit words held in uint64), recombined with Python ints
+    if n_sets and np.all(key_counts == key_counts[0]) and key_counts[0] > 0:
+        k = int(key_counts[0])
+        rows = max(1, CH // k)
+        for lo in range(0, n_sets, rows):
+            hi = min(n_sets, lo + rows)
+            sums[lo:hi] = words[committees[lo * k:hi * k].reshape(hi - lo, k)].sum(axis=1)
+    else:
+        for lo in range(0, K, CH):
+            hi = min(K, lo + CH)
+            np.add.at(sums, set_of_key[lo:hi], words[committees[lo:hi]])
+    for row in sums:
+        v = 0
+        for w in range(8):
+            v += int(row[w]) << (32 * w)
+        agg.append(v % CURVE_ORDER)
     domain = attester_domain()
-    msgs = b"".join(attestation_signing_root(j, epoch, domain) for j in range(n_sets))
-    sigs = bls.sign(b"".join(v.to_bytes(32, "big") for v in agg), msgs)
-    pks = pk_tab[committees.reshape(-1)].tobytes()
-    offsets = (np.arange(n_sets + 1, dtype=np.uint64) * keys_per_set).astype(np.uint32)
-    return AttestationBatch(sigs, msgs, pks, offsets, committees, pk_tab)
+    msgs = b"".join(attestation_signing_root(first_index + j, epoch, domain) for j in range(n_sets))
+    return {"committees": committees, "offsets": offsets.astype(np.uint32), "agg_sk": agg, "msgs": msgs,
+            "n_validators": V, "sks": sks}
+
+
+def materialize_sets(work, pk_table96, sign_fn):
+    """Attach keys and signatures to a sets_workload(): pk_table96 = uint8[V, 96] uncompressed keys of the interop
+    validators, sign_fn(sk_bytes n*32, msgs n*32) -> n*96 compressed signatures (the CUDA library's lhb200_sign for the
+    GPU arm, the CPU oracle for the reference arm)."""
+    sigs = sign_fn(b"".join(v.to_bytes(32, "big") for v in work["agg_sk"]), work["msgs"])
+    pks = pk_table96[work["committees"]].tobytes()
+    n = len(work["offsets"]) - 1
+    offs = work["offsets"]
+    comm = work["committees"]
+    if n and np.all(np.diff(offs) == np.diff(offs)[0]):
+        comm = comm.reshape(n, -1)
+    return AttestationBatch(sigs, work["msgs"], pks, offs, comm, pk_table96)
+
+
+def interop_pubkey_table(n_validators):
+    """uint8[V, 96]: uncompressed interop public keys, produced by the CUDA library's sk_to_pk kernel."""
+    from . import bls
+    sk_bytes = b"".join(s.to_bytes(32, "big") for s in interop_secret_keys(n_validators))
+    _, pk96 = bls.sk_to_pk(sk_bytes)
+    return np.frombuffer(pk96, dtype=np.uint8).reshape(n_validators, 96)
+
+
+def attestation_batch(n_sets, keys_per_set=128, n_validators=16384, seed=0x11570000, epoch=100, first_index=0,
+                      pk_table=None):
+    """n_sets aggregate attestations, each signed by `keys_per_set` distinct validators.  Needs lhb200.init()."""
+    from . import bls
+    work = sets_workload(np.full(n_sets, keys_per_set), n_validators, seed, epoch, first_index)
+    if pk_table is None:
+        pk_table = interop_pubkey_table(n_validators)
+    return materialize_sets(work, pk_table, bls.sign)
+
+
+def block_signature_key_counts(n_blocks=32, n_validators=524288):
+    """Key counts of the SignatureSets a full Deneb block contributes to BlockSignatureVerifier
+    (block_signature_verifier.rs:141-171): proposal, randao, 128 attestations (committee =
+    V / 32 / 64 keys), the sync aggregate (512 keys), 16 exits, 16 BLS-to-execution changes."""
+    committee = max(1, n_validators // 32 // 64)
+    per_block = [1, 1] + [committee] * 128 + [512] + [1] * 16 + [1] * 16
+    return np.array(per_block * n_blocks, dtype=np.int64)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -163,6 +163,12 @@ class ShardedState:
         check(lib.lhb200_state_combine(self._h, p, out), "lhb200_state_combine")
         return out.raw
 
+    def root_collective(self, stream=None) -> bytes:
+        """lhb200_state_root_sharded: shard roots -> ncclAllGather (library communicator) -> combine, all on the device."""
+        out = C.create_string_buffer(32)
+        check(lib.lhb200_state_root_sharded(self._h, out), "lhb200_state_root_sharded")
+        return out.raw
+
     def release(self):
         if self._h:
             lib.lhb200_state_release(self._h)
