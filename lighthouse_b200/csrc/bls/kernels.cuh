@@ -110,6 +110,144 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate(const uint8_t* __res
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pk_aggregate_tma — the same per-set aggregation with the key ingest STAGED THROUGH SHARED MEMORY BY THE TMA UNIT
+// (north_star: "pubkey batches staged through shared memory via TMA with coalesced HBM loads"; replaces the loop at
+// blst.rs:86-106).  One thread still owns one set (the additions of a set are a serial chain), but it never touches
+// global memory for keys: every thread issues bulk async copies (cp.async.bulk, SASS UBLKCP) of PK_TMA_KEYS consecutive
+// keys of ITS set — whole 32-byte sectors, 192 B per request — into its slot of a PK_TMA_STAGES-deep ring, tracked by
+// one mbarrier per stage (64 arrivals + the stage's byte count), and adds keys from shared memory while the next
+// stages are in flight.  Ragged sets are natural: a thread copies min(PK_TMA_KEYS, keys left) and, once its set is
+// exhausted, keeps arriving with zero bytes until the block's longest set is done.
+constexpr int PK_TMA_KEYS = 2;
+constexpr int PK_TMA_STAGES = 3;
+constexpr int PK_TMA_SLOT = PK_TMA_KEYS * 96;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 96-byte uncompressed key held as 24 aligned little-endian words (shared memory): same checks as g1_from_uncompressed
+__device__ __forceinline__ int32_t g1_from_uncompressed_words(G1Affine& r, const uint32_t* w) {
+    uint32_t v[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) v[i] = w[i];
+    const uint32_t b0 = v[0] & 0xffu;
+    if (b0 & 0xa0) return DEC_BAD;
+    if (b0 & 0x40) {
+        uint32_t nz = v[0] & 0xffffff3fu;
+#pragma unroll
+        for (int i = 1; i < 24; i++) nz |= v[i];
+        if (nz) return DEC_BAD;
+        f_set_zero(r.x); f_set_zero(r.y); r.inf = 1;
+        return DEC_INFINITY;
+    }
+    Fp cx, cy;
+#pragma unroll
+    for (int i = 0; i < NL; i++) {   // limb i = big-endian bytes 4 (11 - i) .. +3
+        cx.v[i] = __byte_perm(v[NL - 1 - i], 0, 0x0123);
+        cy.v[i] = __byte_perm(v[2 * NL - 1 - i], 0, 0x0123);
+    }
+    if (!fp_canon_lt_p(cx) || !fp_canon_lt_p(cy)) return DEC_BAD;
+    fp_to_mont(r.x, cx);
+    fp_to_mont(r.y, cy);
+    r.inf = 0;
+    return DEC_OK;
+}
+
+__global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate_tma(const uint8_t* __restrict__ pks,
+                                                                 const uint32_t* __restrict__ offsets,
+                                                                 const uint64_t* __restrict__ rands, uint32_t n,
+                                                                 G1Proj3* __restrict__ out_p, uint8_t* __restrict__ status,
+                                                                 uint32_t* __restrict__ fail) {
+    __shared__ __align__(128) uint8_t ring[PK_TMA_STAGES][BLS_BLOCK][PK_TMA_SLOT];
+    __shared__ __align__(8) uint64_t bars[PK_TMA_STAGES];
+    __shared__ uint32_t max_chunks;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < n;
+    const uint32_t lo = have ? offsets[i] : 0, hi = have ? offsets[i + 1] : 0;
+    const uint32_t nk = hi > lo ? hi - lo : 0;
+    const uint32_t my_chunks = (nk + PK_TMA_KEYS - 1) / PK_TMA_KEYS;
+    if (threadIdx.x == 0) {
+        max_chunks = 0;
+        for (int s = 0; s < PK_TMA_STAGES; s++) mbar_init(&bars[s], BLS_BLOCK);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    atomicMax(&max_chunks, my_chunks);
+    __syncthreads();
+    const uint32_t n_chunks = max_chunks;
+    auto issue = [&](uint32_t c) {   // chunk c of my set -> my slot of stage c % STAGES
+        const int s = c % PK_TMA_STAGES;
+        if (c < my_chunks) {
+            const uint32_t k0 = lo + c * PK_TMA_KEYS, cnt = min((uint32_t)PK_TMA_KEYS, hi - k0);
+            mbar_arrive_expect_tx(&bars[s], cnt * 96);
+            bulk_g2s(ring[s][threadIdx.x], pks + 96ull * k0, cnt * 96, &bars[s]);
+        } else {
+            mbar_arrive(&bars[s]);
+        }
+    };
+    for (uint32_t c = 0; c < (uint32_t)PK_TMA_STAGES && c < n_chunks; c++) issue(c);
+    uint8_t st = SET_OK;
+    G1Jac acc;
+    jac_set_inf(acc);
+    if (have && nk == 0) st = SET_NO_KEYS;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const int s = c % PK_TMA_STAGES;
+        mbar_wait(&bars[s], (c / PK_TMA_STAGES) & 1);
+        if (c < my_chunks && st == SET_OK) {
+            const uint32_t cnt = min((uint32_t)PK_TMA_KEYS, nk - c * PK_TMA_KEYS);
+            for (uint32_t k = 0; k < cnt; k++) {
+                G1Affine a;
+                if (g1_from_uncompressed_words(a, reinterpret_cast<const uint32_t*>(ring[s][threadIdx.x] + 96 * k)) == DEC_BAD) {
+                    st = SET_PK_DECODE;
+                    break;
+                }
+                jac_add_affine(acc, acc, a);
+            }
+        }
+        if (c + PK_TMA_STAGES < n_chunks) {   // my slot of this stage is free again: order my reads before the refill
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c + PK_TMA_STAGES);
+        }
+    }
+    if (!have) return;
+    if (st == SET_OK && jac_is_inf(acc)) st = SET_APK_INFINITY;
+    G1Proj3 P;
+    if (st == SET_OK) {
+        G1Jac ra;
+        jac_mul_u64(ra, acc, rands[i]);
+        g1proj3_from_jac(P, ra);
+    } else {
+        P.px = FP_ONE; P.py = FP_ONE; P.pz = FP_ONE;
+    }
+    out_p[i] = P;
+    if (st != SET_OK) { status[i] = st; atomicOr(fail, 1u); }
+}
+
 // Device-resident pubkey table (mirror of ValidatorPubkeyCache, beacon_chain/src/validator_pubkey_cache.rs:20-25):
 // entries are affine G1 in Montgomery form, converted once at import, so per-set aggregation needs no decoding.
 struct G1Mont {

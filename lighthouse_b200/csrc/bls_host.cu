@@ -527,6 +527,9 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         grid = cdiv(n, (uint64_t)per_thread * BLS_BLOCK);
     }
     uint64_t launches = 0;
+    // key ingest through the TMA unit (bulk async copies into a shared-memory ring); needs 16-byte aligned keys
+    static const int pk_tma_env = [] { const char* e = getenv("LHB_PK_TMA"); return e ? atoi(e) : 1; }();
+    const bool pk_tma = pk_tma_env && b->in_pks && ((uintptr_t)b->in_pks & 15) == 0;
     if (b->n_chunks) LHB_CUDA(cudaStreamWaitEvent(s, b->e_small, 0));  // streamed upload: small arrays first
     LHB_CUDA(cudaMemsetAsync(b->d_status, 0, n, s));
     LHB_CUDA(cudaMemsetAsync(b->d_fail, 0, 4, s));
@@ -575,8 +578,12 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
                 LHB_CUDA(cudaMemcpyAsync(b->d_pks + k0 * 96, b->h_pks + k0 * 96, (k1 - k0) * 96, cudaMemcpyHostToDevice,
                                          b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]));
             if (cnt == 0) continue;
-            k_pk_aggregate<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]>>>(
-                b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
+            if (pk_tma)
+                k_pk_aggregate_tma<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]>>>(
+                    b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
+            else
+                k_pk_aggregate<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]>>>(
+                    b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
             launches++;
         }
         for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++) {
@@ -584,7 +591,10 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
             LHB_CUDA(cudaStreamWaitEvent(s, b->e_pk[j], 0));
         }
         launches--;  // (the single-launch form below counts one)
-    } else
+    } else if (pk_tma)
+        k_pk_aggregate_tma<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status,
+                                                                    b->d_fail);
+    else
         k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // the Miller kernel reads the status bytes k_sig_prepare may set

@@ -481,6 +481,9 @@ struct lhb200_state {
     std::vector<lhb200::ShardedList> sharded;
     uint8_t* d_coll = nullptr;              // lhb200_state_root_sharded: gather ops | own subtree roots | all ranks' roots
     std::vector<lhb200::StageCopy> copies;  // SSZ ranges resident in the arena (for lhb200_state_patch)
+    std::vector<uint32_t> copy_order, lit_order;   // offset-sorted indices into copies / plan.lit_src (patch lookups)
+    std::vector<int32_t> copy_tree;         // copies[k] -> index of its resident tree (warm path), -1 if none
+    size_t copy_tree_trees = 0;
     // warm path (lhb200_state_enable_incremental): full level arrays per big list + dirty leaves since the last root
     struct Tree { lhb200::TreeDev dev; uint64_t src_off, src_bytes; uint32_t item_bytes; std::vector<uint32_t> dirty; };
     bool incremental = false, need_full = false;
@@ -965,28 +968,87 @@ int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* offsets, cons
     Plan& pl = st->plan;
     uint64_t blob_off = 0;
     uint32_t lit_lo = ~0u, lit_hi = 0;
+    // Range lookups by binary search over offset-sorted indices (built once per handle): O(log fields) per edit, so a
+    // slot's worth of mutations (tens of thousands of 8-byte edits) costs the host well under a millisecond.
+    if (st->copy_order.empty() && !st->copies.empty()) {
+        st->copy_order.resize(st->copies.size());
+        for (size_t k = 0; k < st->copies.size(); k++) st->copy_order[k] = (uint32_t)k;
+        std::sort(st->copy_order.begin(), st->copy_order.end(),
+                  [&](uint32_t a, uint32_t b) { return st->copies[a].src_off < st->copies[b].src_off; });
+        st->copy_tree.assign(st->copies.size(), -1);
+        for (size_t k = 0; k < st->copies.size(); k++)
+            for (size_t t = 0; t < st->trees.size(); t++)
+                if (st->trees[t].src_off == st->copies[k].src_off) st->copy_tree[k] = (int32_t)t;
+        st->lit_order.resize(pl.lit_src.size());
+        for (size_t k = 0; k < pl.lit_src.size(); k++) st->lit_order[k] = (uint32_t)k;
+        std::sort(st->lit_order.begin(), st->lit_order.end(),
+                  [&](uint32_t a, uint32_t b) { return pl.lit_src[a].src_off < pl.lit_src[b].src_off; });
+    }
+    if (st->incremental && st->copy_tree_trees != st->trees.size()) {   // trees appear with enable_incremental
+        for (size_t k = 0; k < st->copies.size(); k++) {
+            st->copy_tree[k] = -1;
+            for (size_t t = 0; t < st->trees.size(); t++)
+                if (st->trees[t].src_off == st->copies[k].src_off) st->copy_tree[k] = (int32_t)t;
+        }
+        st->copy_tree_trees = st->trees.size();
+    }
+    // pass 1: every edit must hit resident bytes — validated BEFORE anything is modified, so a rejected batch leaves the
+    // handle (host literals, dirty lists, device copy) exactly as it was
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t lo = offsets[i], hi = lo + lens[i];
+        if (lens[i] == 0) continue;
+        bool touched = false;
+        size_t k = std::partition_point(st->copy_order.begin(), st->copy_order.end(), [&](uint32_t ci) {
+                       const StageCopy& cp = st->copies[ci];
+                       return cp.src_off + cp.nbytes <= lo;
+                   }) - st->copy_order.begin();
+        if (k < st->copy_order.size() && st->copies[st->copy_order[k]].src_off < hi) touched = true;
+        if (!touched) {
+            size_t m = std::partition_point(st->lit_order.begin(), st->lit_order.end(), [&](uint32_t li) {
+                           const Plan::LitSrc& ls = pl.lit_src[li];
+                           return ls.src_off + ls.n <= lo;
+                       }) - st->lit_order.begin();
+            if (m < st->lit_order.size() && pl.lit_src[st->lit_order[m]].src_off < hi) touched = true;
+        }
+        if (!touched) {
+            set_error("state_patch: range [%llu, %llu) is not resident on this handle (offset table or another rank's shard)",
+                      (unsigned long long)lo, (unsigned long long)hi);
+            return LHB200_EINVAL;
+        }
+    }
     for (uint32_t i = 0; i < n; i++) {
         const uint64_t lo = offsets[i], hi = lo + lens[i];
         const uint8_t* src = data + blob_off;
         bool touched = lens[i] == 0;
-        for (const StageCopy& cp : st->copies) {
+        // first resident range whose end lies beyond lo
+        size_t k = std::partition_point(st->copy_order.begin(), st->copy_order.end(), [&](uint32_t ci) {
+                       const StageCopy& cp = st->copies[ci];
+                       return cp.src_off + cp.nbytes <= lo;
+                   }) - st->copy_order.begin();
+        for (; k < st->copy_order.size(); k++) {
+            const uint32_t ci = st->copy_order[k];
+            const StageCopy& cp = st->copies[ci];
+            if (cp.src_off >= hi) break;
             const uint64_t a = std::max<uint64_t>(lo, cp.src_off), b = std::min<uint64_t>(hi, cp.src_off + cp.nbytes);
             if (a >= b) continue;
             ops.push_back({cp.dst + (a - cp.src_off), (uint32_t)(b - a), (uint32_t)(blob_off + (a - lo))});
             touched = true;
             if (st->incremental && !st->need_full) {   // warm path: which leaves of which tree does this touch?
-                bool found = false;
-                for (lhb200_state::Tree& t : st->trees) {
-                    if (t.src_off != cp.src_off) continue;
-                    found = true;
-                    const uint64_t i0 = (a - t.src_off) / t.item_bytes, i1 = (b - 1 - t.src_off) / t.item_bytes;
-                    if (t.dirty.size() + (i1 - i0 + 1) > lhb200_state::DIRTY_CAP) { st->need_full = true; break; }
-                    for (uint64_t k = i0; k <= i1; k++) t.dirty.push_back((uint32_t)k);
-                }
-                if (!found) st->need_full = true;      // a list without a resident tree (votes, summaries, committees)
+                const int32_t ti = st->copy_tree[ci];
+                if (ti < 0) { st->need_full = true; continue; }   // a list without a resident tree (votes, summaries, ...)
+                lhb200_state::Tree& t = st->trees[ti];
+                const uint64_t i0 = (a - t.src_off) / t.item_bytes, i1 = (b - 1 - t.src_off) / t.item_bytes;
+                if (t.dirty.size() + (i1 - i0 + 1) > lhb200_state::DIRTY_CAP) { st->need_full = true; continue; }
+                for (uint64_t q = i0; q <= i1; q++) t.dirty.push_back((uint32_t)q);
             }
         }
-        for (const Plan::LitSrc& ls : pl.lit_src) {      // small fixed fields live in host-packed literal chunks
+        size_t m = std::partition_point(st->lit_order.begin(), st->lit_order.end(), [&](uint32_t li) {
+                       const Plan::LitSrc& ls = pl.lit_src[li];
+                       return ls.src_off + ls.n <= lo;
+                   }) - st->lit_order.begin();
+        for (; m < st->lit_order.size(); m++) {          // small fixed fields live in host-packed literal chunks
+            const Plan::LitSrc& ls = pl.lit_src[st->lit_order[m]];
+            if (ls.src_off >= hi) break;
             const uint64_t a = std::max<uint64_t>(lo, ls.src_off), b = std::min<uint64_t>(hi, ls.src_off + ls.n);
             if (a >= b) continue;
             memcpy(&pl.lit[(size_t)ls.lit_index * 32] + (a - ls.src_off), src + (a - lo), b - a);

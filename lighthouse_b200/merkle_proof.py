@@ -11,44 +11,158 @@ class MerkleTreeError(Exception):
     pass
 
 
-class MerkleTree:
-    """Right-sparse fixed-depth tree over `leaves` (list of 32-byte values)."""
+def _hash_pairs(pairs: bytes) -> bytes:
+    """n x 64 bytes -> n x 32 bytes on the device (lhb200_hash_pairs)."""
+    n = len(pairs) // 64
+    if n == 0:
+        return b""
+    out = C.create_string_buffer(32 * n)
+    p, keep = buf(pairs)
+    check(lib.lhb200_hash_pairs(p, out, n), "lhb200_hash_pairs")
+    return out.raw
 
-    def __init__(self, leaves, depth):
-        if depth > MAX_TREE_DEPTH or len(leaves) > (1 << depth):
-            raise MerkleTreeError("DepthTooSmall" if len(leaves) > (1 << depth) else "Invalid")
-        self.leaves = list(leaves)
+
+def _zero_hash(level: int) -> bytes:
+    out = C.create_string_buffer(32)
+    check(lib.lhb200_zero_hash(level, out), "lhb200_zero_hash")
+    return out.raw
+
+
+class MerkleTree:
+    """Right-sparse fixed-depth tree (consensus/merkle_proof/src/lib.rs:27-45) with a FINALIZED prefix:
+    the first `finalized_count` leaves are represented only by the hashes of their maximal aligned subtrees
+    (`MerkleTree::Finalized` nodes, one per set bit of the count, left to right), the rest are explicit leaves.
+    All hashing runs on the device."""
+
+    def __init__(self, leaves, depth, finalized=None, finalized_count=0):
+        if depth > MAX_TREE_DEPTH or finalized_count + len(leaves) > (1 << depth):
+            raise MerkleTreeError("DepthTooSmall" if finalized_count + len(leaves) > (1 << depth) else "Invalid")
+        self.leaves = list(leaves)          # explicit leaves, indices finalized_count ...
         self.depth = depth
+        self.finalized = list(finalized or [])
+        self.finalized_count = finalized_count
 
     @classmethod
     def create(cls, leaves, depth):
         return cls(leaves, depth)
 
+    def __len__(self):
+        return self.finalized_count + len(self.leaves)
+
     def push_leaf(self, elem, depth=None):
         if self.depth == 0:
             raise MerkleTreeError("DepthTooSmall")
-        if len(self.leaves) >= (1 << self.depth):
+        if len(self) >= (1 << self.depth):
             raise MerkleTreeError("MerkleTreeFull")
         self.leaves.append(elem)
 
+    # ---- level arrays: level l holds the nodes with index >= start_l (start_l even, or 0), the first one being the
+    # finalized maximal subtree of that level when bit l of the finalized count is set
+    def _levels(self):
+        F, depth = self.finalized_count, self.depth
+        fin = {}
+        hashes = list(self.finalized)
+        for l in range(depth, -1, -1):          # left to right = descending levels of the set bits of F
+            if (F >> l) & 1:
+                fin[l] = hashes.pop(0)
+        levels = []
+        nodes, start = list(self.leaves), F
+        for l in range(depth + 1):
+            if l in fin and l < depth:
+                nodes, start = [fin[l]] + nodes, start - 1
+            elif l in fin:                       # F == 2^depth: the root itself is finalized
+                nodes, start = [fin[l]], 0
+            levels.append((start, nodes))
+            if l == depth:
+                break
+            if len(nodes) % 2:
+                nodes = nodes + [_zero_hash(l)]
+            out = _hash_pairs(b"".join(nodes))
+            nodes, start = [out[32 * i:32 * i + 32] for i in range(len(nodes) // 2)], start // 2
+        return levels
+
     def _proof(self, index):
-        root = C.create_string_buffer(32)
-        branch = C.create_string_buffer(max(32 * self.depth, 1))
-        p, keep = buf(b"".join(self.leaves))
-        check(lib.lhb200_merkle_tree_proof(p, len(self.leaves), self.depth, index, root, branch),
-              "lhb200_merkle_tree_proof")
-        return root.raw, [branch.raw[32 * i: 32 * i + 32] for i in range(self.depth)]
+        if not self.finalized_count:             # no finalized prefix: one fused device pass
+            root = C.create_string_buffer(32)
+            branch = C.create_string_buffer(max(32 * self.depth, 1))
+            p, keep = buf(b"".join(self.leaves))
+            check(lib.lhb200_merkle_tree_proof(p, len(self.leaves), self.depth, index, root, branch),
+                  "lhb200_merkle_tree_proof")
+            return root.raw, [branch.raw[32 * i: 32 * i + 32] for i in range(self.depth)]
+        levels = self._levels()
+        start, top = levels[self.depth]
+        root = top[0] if top else _zero_hash(self.depth)
+        branch = []
+        idx = index
+        for l in range(self.depth):
+            start, nodes = levels[l]
+            sib = (idx ^ 1) - start
+            branch.append(nodes[sib] if 0 <= sib < len(nodes) else _zero_hash(l))
+            idx >>= 1
+        return root, branch
 
     def hash(self):
-        return self._proof(0)[0]
+        if not self.finalized_count:
+            return self._proof(0)[0]
+        top = self._levels()[self.depth][1]
+        return top[0] if top else _zero_hash(self.depth)
 
     def generate_proof(self, index, depth=None):
-        """-> (leaf, branch bottom-up).  Leaf beyond the populated range is the zero chunk."""
+        """-> (leaf, branch bottom-up).  Leaf beyond the populated range is the zero chunk; a leaf inside the finalized
+        prefix raises ProofEncounteredFinalizedNode (lib.rs:300-302)."""
         if index >= (1 << self.depth):
             raise MerkleTreeError("Invalid")
+        if index < self.finalized_count:
+            raise MerkleTreeError("ProofEncounteredFinalizedNode")
         _, branch = self._proof(index)
-        leaf = self.leaves[index] if index < len(self.leaves) else b"\0" * 32
+        k = index - self.finalized_count
+        leaf = self.leaves[k] if k < len(self.leaves) else b"\0" * 32
         return leaf, branch
+
+    def finalize_deposits(self, deposits_to_finalize, level=None):
+        """lib.rs:185-219: every subtree entirely inside the first `deposits_to_finalize` leaves becomes a Finalized
+        node.  Descending into an unpopulated (Zero) subtree is the error ZeroNodeFinalized; a count of 0 still
+        finalizes leaf 0 (the reference's Leaf arm has no count check)."""
+        n = max(int(deposits_to_finalize), 1)
+        if n > len(self):
+            raise MerkleTreeError("ZeroNodeFinalized")
+        if n <= self.finalized_count:
+            return
+        levels = self._levels()
+        hashes, pos = [], 0
+        for l in range(self.depth, -1, -1):
+            if (n >> l) & 1:
+                start, nodes = levels[l]
+                hashes.append(nodes[(pos >> l) - start])
+                pos += 1 << l
+        self.leaves = self.leaves[n - self.finalized_count:]
+        self.finalized, self.finalized_count = hashes, n
+
+    def get_finalized_hashes(self):
+        """lib.rs:232-236"""
+        return list(self.finalized)
+
+    @classmethod
+    def from_finalized_snapshot(cls, finalized_branch, deposit_count, level):
+        """lib.rs:238-288: rebuild a tree whose first `deposit_count` leaves are finalized."""
+        branch = list(finalized_branch)
+
+        def walk(br, count, lvl):                # returns the hashes the reference's recursion actually consumes
+            if not br:
+                if count == 0:
+                    return []
+                raise MerkleTreeError(f"InvalidSnapshot(EmptyBranchWithNonZeroDeposits({count}))")
+            if count == (1 << lvl):
+                return [br[0]]
+            if lvl == 0:
+                raise MerkleTreeError("InvalidSnapshot(EndOfTree)")
+            half = 1 << (lvl - 1)
+            if count >= half:
+                return [br[0]] + walk(br[1:], count - half, lvl - 1)
+            return walk(br, count, lvl - 1)
+
+        used = walk(branch, deposit_count, level)
+        return cls([], level, finalized=used, finalized_count=deposit_count if used else 0)
 
 
 def verify_merkle_proofs(leaves, branches, depth, indices, roots):
