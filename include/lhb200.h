@@ -81,6 +81,17 @@ LHB200_API int32_t lhb200_validator_roots(const uint8_t* ssz, uint64_t n, uint8_
  * nodes) — consensus/types/src/beacon_state.rs:2031-2038, fields :343-484.  `ssz` is the SSZ encoding of
  * BeaconStateDeneb.  field_roots (28*32 bytes) is optional (NULL to skip). */
 LHB200_API int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* field_roots);
+/* The other post-Altair variants of the BeaconState superstruct (consensus/types/src/beacon_state.rs:224-571) through
+ * the same kernels; `fork` is one of LHB200_FORK_*.  Altair has 24 fields, Bellatrix 25 (+ a 14-field execution payload
+ * header), Capella 28 (15-field header, withdrawal indices, historical_summaries), Deneb 28 (17-field header).
+ * field_roots (optional, 28 x 32 B): entries beyond the fork's field count are zero chunks. */
+#define LHB200_FORK_ALTAIR 1
+#define LHB200_FORK_BELLATRIX 2
+#define LHB200_FORK_CAPELLA 3
+#define LHB200_FORK_DENEB 4
+LHB200_API int32_t lhb200_beacon_state_root(const uint8_t* ssz, uint64_t len, int32_t fork, uint8_t out[32],
+                                            uint8_t* field_roots);
+LHB200_API int32_t lhb200_state_stage(const uint8_t* ssz, uint64_t len, int32_t fork, struct lhb200_state** out);
 
 /* Device-resident variant: stage once (H2D into the library's aligned HBM layout), then hash
  * as often as wanted without touching the host link.  The handle owns device memory until released. */

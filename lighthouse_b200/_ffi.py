@@ -131,3 +131,5 @@ _sig("lhb200_comm_info", C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
 _sig("lhb200_verify_signature_sets_collective", C.c_int32, vp, vp, vp, vp, vp, C.c_uint32, vp)
 _sig("lhb200_bls_batch_allreduce_verdict", C.c_int32, vp, vp)
 _sig("lhb200_state_root_sharded", C.c_int32, vp, vp)
+_sig("lhb200_beacon_state_root", C.c_int32, vp, C.c_uint64, C.c_int32, vp, vp)
+_sig("lhb200_state_stage", C.c_int32, vp, C.c_uint64, C.c_int32, C.POINTER(vp))

@@ -446,6 +446,7 @@ struct StageCopy {
 
 struct ShardCfg {
     uint32_t rank = 0, world = 1;
+    int32_t fork = LHB200_FORK_DENEB;   // which BeaconState variant the SSZ is (fork_spec)
 };
 struct ShardedList {
     int field;            // index in the 28-field container
@@ -499,26 +500,56 @@ namespace lhb200 {
 
 // Describe the whole Deneb state.  `s` = host SSZ (read for offsets and small literal fields only).
 // Big fields are placed in the arena by `place(src_off, nbytes)` which records an H2D copy.
+// The post-Altair BeaconState variants (consensus/types/src/beacon_state.rs:224-571) share the first 24 fields and
+// their fixed-part offsets; later forks APPEND fields and widen the execution payload header:
+//   Altair     24 fields                                                        fixed part 2 736 629 B
+//   Bellatrix  + latest_execution_payload_header (14 fields, 536 B fixed)       2 736 633 B
+//   Capella    header + withdrawals_root (15 fields, 568 B); + next_withdrawal_index, next_withdrawal_validator_index,
+//              historical_summaries                                             2 736 653 B
+//   Deneb      header + blob_gas_used, excess_blob_gas (17 fields, 584 B)       2 736 653 B
+// so one describer covers them all; the kernels are fork-agnostic.
+struct ForkSpec {
+    int n_fields;        // 24 / 25 / 28 / 28
+    uint32_t fixed;      // bytes of the fixed part
+    uint32_t hdr_fixed;  // fixed part of the execution payload header (0: no header)
+    int hdr_fields;
+};
+static bool fork_spec(int32_t fork, ForkSpec* f) {
+    switch (fork) {
+        case LHB200_FORK_ALTAIR: *f = {24, 2736629, 0, 0}; return true;
+        case LHB200_FORK_BELLATRIX: *f = {25, 2736633, 536, 14}; return true;
+        case LHB200_FORK_CAPELLA: *f = {28, 2736653, 568, 15}; return true;
+        case LHB200_FORK_DENEB: *f = {28, 2736653, 584, 17}; return true;
+    }
+    return false;
+}
+
 static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vector<StageCopy>* copies,
                               uint64_t field_ops[28], uint64_t* root_op, ShardCfg sh = ShardCfg(),
                               std::vector<ShardedList>* sharded = nullptr) {
     using namespace deneb;
-    if (len < FIXED) { set_error("BeaconStateDeneb SSZ shorter than its fixed part"); return LHB200_EINVAL; }
+    ForkSpec fk;
+    if (!fork_spec(sh.fork, &fk)) { set_error("unknown fork id %d", sh.fork); return LHB200_EINVAL; }
+    const uint32_t FIXED = fk.fixed;
+    if (len < FIXED) { set_error("BeaconState SSZ shorter than its fixed part"); return LHB200_EINVAL; }
     const uint32_t o_hist = rd32(s + O_HIST_OFF), o_votes = rd32(s + O_VOTES_OFF), o_val = rd32(s + O_VAL_OFF),
                    o_bal = rd32(s + O_BAL_OFF), o_pp = rd32(s + O_PP_OFF), o_cp = rd32(s + O_CP_OFF),
-                   o_inact = rd32(s + O_INACT_OFF), o_leph = rd32(s + O_LEPH_OFF), o_hs = rd32(s + O_HS_OFF);
+                   o_inact = rd32(s + O_INACT_OFF);
+    const uint32_t o_leph = fk.hdr_fields ? rd32(s + O_LEPH_OFF) : (uint32_t)len;
+    const uint32_t o_hs = fk.n_fields == 28 ? rd32(s + O_HS_OFF) : (uint32_t)len;
     if (o_hist != FIXED || !(o_hist <= o_votes && o_votes <= o_val && o_val <= o_bal && o_bal <= o_pp &&
                              o_pp <= o_cp && o_cp <= o_inact && o_inact <= o_leph && o_leph <= o_hs && o_hs <= len)) {
-        set_error("BeaconStateDeneb SSZ: inconsistent variable-part offsets");
+        set_error("BeaconState SSZ: inconsistent variable-part offsets");
         return LHB200_EINVAL;
     }
     const uint64_t n_hist = (o_votes - o_hist) / 32, n_votes = (o_val - o_votes) / 72, n_val = (o_bal - o_val) / 121,
                    n_bal = (o_pp - o_bal) / 8, n_pp = o_cp - o_pp, n_cp = o_inact - o_cp,
                    n_inact = (o_leph - o_inact) / 8, leph_len = o_hs - o_leph, n_hs = (len - o_hs) / 64;
     if ((o_votes - o_hist) % 32 || (o_val - o_votes) % 72 || (o_bal - o_val) % 121 || (o_pp - o_bal) % 8 ||
-        (o_leph - o_inact) % 8 || (len - o_hs) % 64 || leph_len < 584 || leph_len > 584 + 32 ||
-        rd32(s + o_leph + 436) != 584 || n_votes > 2048 || n_hist > (1u << 24) || n_hs > (1u << 24)) {
-        set_error("BeaconStateDeneb SSZ: malformed variable part");
+        (o_leph - o_inact) % 8 || (len - o_hs) % 64 ||
+        (fk.hdr_fields && (leph_len < fk.hdr_fixed || leph_len > fk.hdr_fixed + 32 || rd32(s + o_leph + 436) != fk.hdr_fixed)) ||
+        n_votes > 2048 || n_hist > (1u << 24) || n_hs > (1u << 24)) {
+        set_error("BeaconState SSZ: malformed variable part");
         return LHB200_EINVAL;
     }
     p.ssz_base = s;
@@ -605,22 +636,27 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
         uint8_t* roots = p.leaf_kernel(1, place(k ? O_NSC : O_CSC, SYNC_COMMITTEE_BYTES), 513);
         f[22 + k] = p.container({p.merkle_list(roots, 512, 9), reinterpret_cast<uint64_t>(roots + 512 * 32)});
     }
-    {
+    if (fk.hdr_fields) {
         const uint8_t* h = s + o_leph;
         std::vector<uint64_t> bloom;
         for (int i = 0; i < 8; i++) bloom.push_back(p.literal(h + 116 + 32 * i));
-        const uint64_t extra_len = leph_len - 584;
-        f[24] = p.container({p.literal(h), p.literal_bytes(h + 32, 20), p.literal(h + 52), p.literal(h + 84),
-                             p.small_tree(bloom, 3), p.literal(h + 372), p.literal_bytes(h + 404, 8),
-                             p.literal_bytes(h + 412, 8), p.literal_bytes(h + 420, 8), p.literal_bytes(h + 428, 8),
-                             p.mix_in_length(p.literal_bytes(h + 584, extra_len), extra_len), p.literal(h + 440),
-                             p.literal(h + 472), p.literal(h + 504), p.literal(h + 536),
-                             p.literal_bytes(h + 568, 8), p.literal_bytes(h + 576, 8)});
+        const uint64_t extra_len = leph_len - fk.hdr_fixed;
+        std::vector<uint64_t> hf = {p.literal(h), p.literal_bytes(h + 32, 20), p.literal(h + 52), p.literal(h + 84),
+                                    p.small_tree(bloom, 3), p.literal(h + 372), p.literal_bytes(h + 404, 8),
+                                    p.literal_bytes(h + 412, 8), p.literal_bytes(h + 420, 8), p.literal_bytes(h + 428, 8),
+                                    p.mix_in_length(p.literal_bytes(h + fk.hdr_fixed, extra_len), extra_len),
+                                    p.literal(h + 440), p.literal(h + 472), p.literal(h + 504)};
+        if (fk.hdr_fields >= 15) hf.push_back(p.literal(h + 536));                       // withdrawals_root (Capella)
+        if (fk.hdr_fields >= 17) { hf.push_back(p.literal_bytes(h + 568, 8)); hf.push_back(p.literal_bytes(h + 576, 8)); }
+        f[24] = p.container(hf);
     }
-    f[25] = p.literal_bytes(s + O_NWI, 8);
-    f[26] = p.literal_bytes(s + O_NWVI, 8);
-    f[27] = p.mix_in_length(p.merkle_list(p.leaf_kernel(3, place(o_hs, n_hs * 64), n_hs), n_hs, 24), n_hs);
-    *root_op = p.container(std::vector<uint64_t>(f, f + 28));
+    if (fk.n_fields == 28) {
+        f[25] = p.literal_bytes(s + O_NWI, 8);
+        f[26] = p.literal_bytes(s + O_NWVI, 8);
+        f[27] = p.mix_in_length(p.merkle_list(p.leaf_kernel(3, place(o_hs, n_hs * 64), n_hs), n_hs, 24), n_hs);
+    }
+    for (int k = fk.n_fields; k < 28; k++) f[k] = Plan::zero_op(0);   // absent in this fork (not part of its container)
+    *root_op = p.container(std::vector<uint64_t>(f, f + fk.n_fields));
     return LHB200_OK;
 }
 
@@ -848,6 +884,12 @@ static int32_t stage_deneb(const uint8_t* ssz, uint64_t len, ShardCfg sh, lhb200
 
 int32_t lhb200_state_stage_deneb(const uint8_t* ssz, uint64_t len, lhb200_state** out) {
     return stage_deneb(ssz, len, ShardCfg(), out);
+}
+// Same for any post-Altair fork (LHB200_FORK_*): the describer is table-driven, the kernels are shared.
+int32_t lhb200_state_stage(const uint8_t* ssz, uint64_t len, int32_t fork, lhb200_state** out) {
+    ShardCfg sh;
+    sh.fork = fork;
+    return stage_deneb(ssz, len, sh, out);
 }
 
 int32_t lhb200_state_stage_deneb_shard(const uint8_t* ssz, uint64_t len, uint32_t rank, uint32_t world,
@@ -1269,9 +1311,14 @@ float lhb200_state_dominant_kernel_ms(const lhb200_state* st) {
 }
 
 int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* field_roots) {
+    return lhb200_beacon_state_root(ssz, len, LHB200_FORK_DENEB, out, field_roots);
+}
+// BeaconState::update_tree_hash_cache for any post-Altair variant of the superstruct (beacon_state.rs:224-571).
+// field_roots (optional): 28 x 32 bytes; entries beyond the fork's field count are the zero chunk.
+int32_t lhb200_beacon_state_root(const uint8_t* ssz, uint64_t len, int32_t fork, uint8_t out[32], uint8_t* field_roots) {
     LHB_REQUIRE_READY();
     lhb200_state* st = nullptr;
-    int32_t rc = lhb200_state_stage_deneb(ssz, len, &st);
+    int32_t rc = lhb200_state_stage(ssz, len, fork, &st);
     if (rc) return rc;
     rc = lhb200_state_root(st, out, field_roots);
     lhb200_state_release(st);

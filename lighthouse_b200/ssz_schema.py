@@ -156,6 +156,18 @@ BeaconStateDeneb = C(
     ("next_withdrawal_validator_index", U64), ("historical_summaries", ("list", HistoricalSummary, 1 << 24)))
 
 
+# ---- the earlier post-Altair variants of the superstruct (beacon_state.rs:224-571): prefixes of the Deneb field list
+# with narrower execution payload headers
+ExecutionPayloadHeaderBellatrix = C(*ExecutionPayloadHeaderDeneb[1][:14])
+ExecutionPayloadHeaderCapella = C(*ExecutionPayloadHeaderDeneb[1][:15])
+_f = BeaconStateDeneb[1]
+BeaconStateAltair = C(*_f[:24])
+BeaconStateBellatrix = C(*(_f[:24] + [("latest_execution_payload_header", ExecutionPayloadHeaderBellatrix)]))
+BeaconStateCapella = C(*(_f[:24] + [("latest_execution_payload_header", ExecutionPayloadHeaderCapella)] + _f[25:]))
+BEACON_STATE_BY_FORK = {"altair": BeaconStateAltair, "bellatrix": BeaconStateBellatrix, "capella": BeaconStateCapella,
+                        "deneb": BeaconStateDeneb}
+
+
 # BlindedBeaconBlock (beacon_block.rs:80; payload.rs BlindedPayload): the body carries the payload HEADER
 BlindedBeaconBlockBodyDeneb = C(*[(n, ExecutionPayloadHeaderDeneb) if n == "execution_payload" else (n, t)
                                  for n, t in BeaconBlockBodyDeneb[1]])

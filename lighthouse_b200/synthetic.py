@@ -25,9 +25,12 @@ def validators_ssz(n, rng, pubkeys=None):
 
 
 def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots=758, n_votes=1024,
-                           n_summaries=600, extra_data_len=14):
-    """SSZ(BeaconStateDeneb), mainnet preset.  all_default=True leaves every non-validator field zero so the
-    ZERO_HASHES ladder paths are exercised."""
+                           n_summaries=600, extra_data_len=14, fork="deneb"):
+    """SSZ(BeaconState<fork>), mainnet preset; fork in altair / bellatrix / capella / deneb (beacon_state.rs:224-571: later
+    forks append fields and widen the execution payload header).  all_default=True leaves every non-validator field
+    zero so the ZERO_HASHES ladder paths are exercised."""
+    hdr_fixed = {"altair": 0, "bellatrix": 536, "capella": 568, "deneb": 584}[fork]
+    has_tail = fork in ("capella", "deneb")
     rng = np.random.default_rng(seed)
     V = n_validators
 
@@ -53,11 +56,13 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
         inact = rng.integers(0, 64, size=V, dtype="<u8").tobytes()
         slash = rng.integers(0, 1 << 40, size=8192, dtype="<u8").tobytes()
     leph = (rnd(32) + rnd(20) + rnd(32) + rnd(32) + rnd(256) + rnd(32) + rnd(8) + rnd(8) + rnd(8) + rnd(8)
-            + struct.pack("<I", 584) + rnd(32) + rnd(32) + rnd(32) + rnd(32) + rnd(8) + rnd(8) + rnd(extra_data_len))
-    assert len(leph) == 584 + extra_data_len
-    summ = rnd(64 * n_summaries)
+            + struct.pack("<I", hdr_fixed) + rnd(32) + rnd(32) + rnd(32) + rnd(32) + rnd(8) + rnd(8))
+    leph = (leph[:hdr_fixed] + rnd(extra_data_len)) if hdr_fixed else b""
+    assert len(leph) == (hdr_fixed + extra_data_len if hdr_fixed else 0)
+    summ = rnd(64 * n_summaries) if has_tail else b""
+    fixed_len = DENEB_FIXED - (0 if has_tail else 20) - (0 if hdr_fixed else 4)
 
-    o_hist = DENEB_FIXED
+    o_hist = fixed_len
     o_votes = o_hist + len(hist)
     o_val = o_votes + len(votes)
     o_bal = o_val + len(vals)
@@ -81,9 +86,9 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
         u32(o_inact),
         (vals[:48] * 1 if False else rnd(513 * 48)),   # current_sync_committee (512 pubkeys + aggregate)
         rnd(513 * 48),                                 # next_sync_committee
-        u32(o_leph), rnd(8), rnd(8), u32(o_hs),
+        (u32(o_leph) if hdr_fixed else b""), ((rnd(8) + rnd(8) + u32(o_hs)) if has_tail else b""),
     ])
-    assert len(fixed) == DENEB_FIXED, len(fixed)
+    assert len(fixed) == fixed_len, len(fixed)
     return b"".join([fixed, hist, votes, vals, bal, pp, cp, inact, leph, summ])
 
 

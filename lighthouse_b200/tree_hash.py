@@ -116,6 +116,22 @@ def beacon_state_root_deneb(ssz, want_field_roots=False):
     return out.raw
 
 
+FORKS = {"altair": 1, "bellatrix": 2, "capella": 3, "deneb": 4}   # LHB200_FORK_*
+
+
+def beacon_state_root(ssz, fork="deneb", want_field_roots=False):
+    """BeaconState::update_tree_hash_cache (cold) for any post-Altair variant of the superstruct
+    (consensus/types/src/beacon_state.rs:224-571): lhb200_beacon_state_root."""
+    out = C.create_string_buffer(32)
+    fr = C.create_string_buffer(28 * 32) if want_field_roots else None
+    p, keep = buf(ssz)
+    n = len(ssz) if isinstance(ssz, (bytes, bytearray)) else keep.nbytes
+    check(lib.lhb200_beacon_state_root(p, n, FORKS[fork], out, fr), "lhb200_beacon_state_root")
+    if want_field_roots:
+        return out.raw, [fr.raw[32 * i: 32 * i + 32] for i in range(28)]
+    return out.raw
+
+
 def beacon_block_roots_deneb(blocks, want_body_roots=False, blinded=False):
     """BeaconBlock::canonical_root (beacon_block.rs:158-160) of a batch of BeaconBlockDeneb SSZ blobs in one pass
     (blinded=True: BlindedBeaconBlockDeneb blobs, whose body carries the payload header)."""

@@ -306,3 +306,30 @@ def test_signing_root_and_domain_helpers(gpu):
         assert got[32 * i:32 * i + 32] == hashlib.sha256(roots[32 * i:32 * i + 32] + dom).digest()
     leaves = [hashlib.sha256(bytes([i])).digest() for i in range(5)]
     assert T.container_root(leaves) == O.merkleize(b"".join(leaves), 3)
+
+
+@pytest.mark.parametrize("fork", ["altair", "bellatrix", "capella", "deneb"])
+@pytest.mark.parametrize("nv,kw", [(0, {"all_default": True}), (37, {}), (1500, {"n_hist_roots": 3, "n_votes": 5, "n_summaries": 2})])
+def test_beacon_state_root_every_post_altair_fork(gpu, fork, nv, kw):
+    """BeaconState superstruct variants (consensus/types/src/beacon_state.rs:224-571) through the fork-parametrised
+    describer: root and every field root against the GENERIC from-spec merkleization of tests/ssz_spec.py over the
+    decoded value (type descriptors in lighthouse_b200/ssz_schema.py) — no fork-specific oracle code involved."""
+    from lighthouse_b200 import ssz_schema as S, tree_hash as T
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    from tests import ssz_spec
+    ssz = beacon_state_deneb_ssz(nv, seed=100 + nv, fork=fork, **kw)
+    typ = S.BEACON_STATE_BY_FORK[fork]
+    value = ssz_spec.deserialize(typ, ssz)
+    assert S.serialize(typ, value) == ssz
+    root, fields = T.beacon_state_root(ssz, fork, want_field_roots=True)
+    want_fields = [ssz_spec.hash_tree_root(ft, value[name]) for name, ft in typ[1]]
+    assert fields[:len(want_fields)] == want_fields, [i for i, (a, b) in enumerate(zip(fields, want_fields)) if a != b]
+    assert root == ssz_spec.hash_tree_root(typ, value)
+    if fork == "deneb":
+        assert root == T.beacon_state_root_deneb(ssz)
+    # the wrong fork id must not silently produce a root of the same bytes' other interpretation
+    other = {"altair": "deneb", "bellatrix": "capella", "capella": "deneb", "deneb": "capella"}[fork]
+    try:
+        assert T.beacon_state_root(ssz, other) != root
+    except Exception:
+        pass                                          # rejected as malformed: also fine
