@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_pk_aggregate(const uint8_t* __res
 // stages are in flight.  Ragged sets are natural: a thread copies min(PK_TMA_KEYS, keys left) and, once its set is
 // exhausted, keeps arriving with zero bytes until the block's longest set is done.
 constexpr int PK_TMA_KEYS = 2;
-constexpr int PK_TMA_STAGES = 3;
+constexpr int PK_TMA_STAGES = 2;   // 24.6 KB of ring per block: 8 resident blocks per SM, the register limit (3 stages: 6)
 constexpr int PK_TMA_SLOT = PK_TMA_KEYS * 96;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

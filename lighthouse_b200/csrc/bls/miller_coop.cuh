@@ -96,7 +96,6 @@ struct Args {
     const G1Proj3* extra_p;
     uint32_t lo, hi;           // this warp's sets [lo, hi)
     uint32_t* scratch;         // this warp's parking area: rounds * 2 * TWORDS * NT words (T and Q per set)
-    Fp12* out;                 // this warp's NT / 6 group products
 };
 
 template <int NT>
@@ -126,7 +125,9 @@ LHB_HD LHB_INLINE void unpark_point(const Col<NT>& c, const Roles& r, const uint
 template <int NT>
 LHB_HD LHB_INLINE void lane_select(Lane<NT>& L, const Args& a, uint32_t r) {
     const uint32_t n_total = a.n + (a.extra_q ? 1u : 0u);
-    L.set = a.lo + r * Geom<NT>::LANES_USED + L.lane;
+    // sets are dealt to the GROUPS of the warp first (set j of a round -> group j mod NG, slot j / NG): a warp with few
+    // sets keeps every group short, and the serial sparse products of a group are what an iteration waits for
+    L.set = a.lo + r * Geom<NT>::LANES_USED + L.t * (Geom<NT>::LANES_USED / 6) + L.lane / 6;
     L.extra = false;
     bool act = L.set < a.hi && L.set < n_total;
     if (act) {
@@ -283,6 +284,33 @@ LHB_HD LHB_INLINE void phase_sparse_compute(Lane<NT>& L, const Roles& r, int own
     const Col<NT> yc[3] = {L.c, g.lane(i1), g.lane(i2)};
     sum_fp2_products<3>(L, x0, x1, yc);
 }
+// ---- f <- f * g (dense): lane t's coefficient  sum_i a_i b_{(t - i) mod 6} xi^[i > t]  of its OWN group's f times the f
+// held by the six columns starting at `src0` (another group of this warp, or group 0 of another warp's region).
+// Two fused sums of three Fp2 terms each (K X <= 8 forbids six at once).  Used by the product tree of the epilogue.
+template <int NT>
+LHB_HD LHB_INLINE void phase_mul_compute(Lane<NT>& L, const Col<NT>& src0) {
+    const Col<NT> g = L.c.lane(-L.t);
+    Fp acc_a, acc_b;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        SopX<3> x0, x1;
+        Col<NT> yc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i = 3 * half + k;
+            Fp2 u;
+            g.lane(i).ld2(u, S_F0);
+            if (i > L.t) fp2_mul_xi_inl(u, u);
+            x0.x[k] = u.c0; x1.x[k] = u.c1;
+            yc[k] = src0.lane(i > L.t ? L.t - i + 6 : L.t - i);
+        }
+        sum_fp2_products<3>(L, x0, x1, yc);
+        if (half == 0) { acc_a = L.ra; acc_b = L.rb; }
+    }
+    fp_add_inl(L.ra, L.ra, acc_a);
+    fp_add_inl(L.rb, L.rb, acc_b);
+}
+
 template <int NT>
 LHB_HD LHB_INLINE void phase_store_f(Lane<NT>& L) {
     Fp s;
@@ -346,12 +374,31 @@ LHB_HD LHB_INLINE void miller_program(Exec& ex, const Args& a) {
         }
         R = R_out;
     }
-    // conjugate (x < 0): negate the odd powers of w; write the group's product in tower layout
-    MC_PHASE(Fp2 v; L.c.ld2(v, S_F0);
-             if (L.t & 1) { fp_neg(v.c0, v.c0); fp_neg(v.c1, v.c1); }
-             Fp12& o = a.out[L.lane / 6];
-             Fp2& dst = L.t == 0 ? o.c0.c0 : L.t == 1 ? o.c1.c0 : L.t == 2 ? o.c0.c1 : L.t == 3 ? o.c1.c1 : L.t == 4 ? o.c0.c2 : o.c1.c2;
-             dst = v);
+    // conjugate (x < 0): negate the odd powers of w (in place, keeping the (re, im, re + im) form)
+    MC_PHASE(if (L.t & 1) {
+                 Fp2 v; L.c.ld2(v, S_F0);
+                 fp_neg(v.c0, v.c0); fp_neg(v.c1, v.c1);
+                 L.ra = v.c0; L.rb = v.c1;
+                 phase_store_f(L);
+             });
+    // product tree over the warp's groups: after it group 0 holds the product of all of them
+    constexpr int NG = LU / 6;
+    for (int stride = 1; stride < NG; stride *= 2) {
+        MC_PHASE(const int gi = L.lane / 6;
+                 L.active = (gi % (2 * stride) == 0) && gi + stride < NG;
+                 if (L.active) phase_mul_compute(L, L.c.lane(-L.t + 6 * stride)));
+        MC_PHASE(if (L.active) phase_store_f(L));
+    }
+}
+
+// write group 0's f (the warp's product) in tower layout
+template <int NT>
+LHB_HD LHB_INLINE void store_group0(const Lane<NT>& L, Fp12& o) {
+    if (L.idle || L.lane >= 6) return;
+    Fp2 v;
+    L.c.ld2(v, S_F0);
+    Fp2& dst = L.t == 0 ? o.c0.c0 : L.t == 1 ? o.c1.c0 : L.t == 2 ? o.c0.c1 : L.t == 3 ? o.c1.c1 : L.t == 4 ? o.c0.c2 : o.c1.c2;
+    dst = v;
 }
 
 #ifndef LHB_HOSTSIM
@@ -364,9 +411,10 @@ constexpr int MC_WARPS = 8;                       // warps per block = per SM
 constexpr int MC_GROUPS_PER_WARP = 5;
 constexpr size_t mc_smem_bytes() { return Geom<32>::REGION_WORDS * 4 * MC_WARPS; }
 
-// One warp = 30 working lanes = 5 groups; global warp w owns sets [w * sets_per_warp, (w + 1) * sets_per_warp) of the
-// n (+1) pairs and writes 5 group products to out_f[5 w ...].  scratch: per warp sets_per_warp rounded up to whole
-// rounds of 30, 2 * TWORDS words per lane and round.
+// One warp = 30 working lanes = 5 groups; global warp w (= warp_in_block * gridDim.x + blockIdx.x) owns sets
+// [w * sets_per_warp, (w + 1) * sets_per_warp) of the n (+1) pairs.  The epilogue multiplies the groups of a warp and then the warps of the block together (the same
+// cooperative w-basis product), so the kernel emits ONE Miller value per block: out_f[blockIdx.x].  scratch: per warp
+// sets_per_warp rounded up to whole rounds of 30, 2 * TWORDS words per lane and round.
 __global__ void __launch_bounds__(32 * MC_WARPS, 1) k_miller_coop(const G1Proj3* __restrict__ P, const G2Jac* __restrict__ H,
                                                                    const uint8_t* __restrict__ status, uint32_t n,
                                                                    const G2Jac* __restrict__ extra_q,
@@ -375,7 +423,7 @@ __global__ void __launch_bounds__(32 * MC_WARPS, 1) k_miller_coop(const G1Proj3*
                                                                    Fp12* __restrict__ out_f) {
     constexpr int NT = 32;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t gw = blockIdx.x * MC_WARPS + wib;
+    const uint32_t gw = wib * gridDim.x + blockIdx.x;   // interleaved: a batch of few warps spreads over all SMs
     uint32_t* region = lhb_dyn_smem + (size_t)wib * Geom<NT>::REGION_WORDS;
     Lane<NT> L;
     L.lane = lane;
@@ -391,9 +439,23 @@ __global__ void __launch_bounds__(32 * MC_WARPS, 1) k_miller_coop(const G1Proj3*
     a.hi = min(n_total, a.lo + sets_per_warp);
     const uint32_t rounds_cap = (sets_per_warp + Geom<NT>::LANES_USED - 1) / Geom<NT>::LANES_USED;
     a.scratch = scratch + (size_t)gw * rounds_cap * 2 * TWORDS * NT;
-    a.out = out_f + (size_t)gw * MC_GROUPS_PER_WARP;
     ExecDev<NT> ex{L};
-    miller_program<NT>(ex, a);
+    if (a.lo < a.hi) {
+        miller_program<NT>(ex, a);
+    } else if (!L.idle) {                       // a warp without sets contributes f = 1 to the block's product
+        Fp z; fp_set_zero(z); Fp one = FP_ONE;
+        L.c.st(S_F0, L.t == 0 ? one : z); L.c.st(S_F1, z); L.c.st(S_FS, L.t == 0 ? one : z);
+    }
+    // product over the block's warps (their group 0), then ONE Miller value per block
+    for (int stride = 1; stride < MC_WARPS; stride *= 2) {
+        __syncthreads();
+        const bool mine = !L.idle && lane < 6 && (wib % (2 * stride) == 0) && wib + stride < MC_WARPS;
+        if (mine) phase_mul_compute(L, Col<NT>::make(region + (size_t)stride * Geom<NT>::REGION_WORDS, 0));
+        __syncthreads();
+        if (mine) phase_store_f(L);
+    }
+    __syncthreads();
+    if (wib == 0) store_group0(L, out_f[blockIdx.x]);
 }
 #endif
 

@@ -616,10 +616,13 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         const uint32_t max_warps = (uint32_t)n_sm * mc::MC_WARPS;
         uint32_t spw = cdiv(n_total, max_warps);             // sets per warp
         spw = cdiv(spw, LU) * LU;                            // whole rounds
-        spw = std::max<uint32_t>(spw, 6);
-        if (n_total <= max_warps * 6) spw = 6;               // tiny batches: one group per warp, as many SMs as possible
+        // batches below one full round per warp: as few sets per warp as the warp budget allows (the kernel deals them to
+        // the warp's five groups first): the sparse products of a group are serial over its sets, so a 1-set group
+        // iterates in 81 multiply units instead of the 141 of a full one
+        if (n_total <= max_warps * LU) spw = std::max<uint32_t>(1, cdiv(n_total, max_warps));
         const uint32_t n_warps = cdiv(n_total, spw);
-        const uint32_t mgrid = cdiv(n_warps, mc::MC_WARPS);
+        // warps are dealt round-robin to blocks (gw = warp_in_block * grid + block): few warps spread over all SMs
+        const uint32_t mgrid = std::max<uint32_t>(std::min<uint32_t>((uint32_t)n_sm, n_warps), cdiv(n_warps, mc::MC_WARPS));
         const uint32_t rounds_cap = cdiv(spw, LU);
         const size_t need = (size_t)mgrid * mc::MC_WARPS * rounds_cap * 2 * mc::TWORDS * 32;
         if (need > b->mc_scratch_words) {
@@ -635,7 +638,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
                                                                                 b->d_neg_g1, spw, b->d_mc_scratch, b->d_f);
         LHB_CUDA(cudaEventRecord(b->e_k1, s));
         launches += 1;
-        uint32_t m = mgrid * mc::MC_WARPS * mc::MC_GROUPS_PER_WARP;
+        uint32_t m = mgrid;   // the kernel multiplies groups and warps together: one value per block
         int flip = 0;
         while (m > COOP_TAIL) {
             const uint32_t mo = cdiv(m, REDUCE_CHUNK);

@@ -486,7 +486,13 @@ struct lhb200_state {
     std::vector<int32_t> copy_tree;         // copies[k] -> index of its resident tree (warm path), -1 if none
     size_t copy_tree_trees = 0;
     // warm path (lhb200_state_enable_incremental): full level arrays per big list + dirty leaves since the last root
-    struct Tree { lhb200::TreeDev dev; uint64_t src_off, src_bytes; uint32_t item_bytes; std::vector<uint32_t> dirty; };
+    // dirty leaves since the last root: a host BITMAP per tree (marking is O(1) per edit and dedups for free; the next
+    // root extracts the sorted index list with a ctz scan — no sort) plus the number of marks made
+    struct Tree {
+        lhb200::TreeDev dev; uint64_t src_off, src_bytes; uint32_t item_bytes;
+        std::vector<uint64_t> dirty_bits; std::vector<uint32_t> dirty; uint64_t n_marks = 0;
+        void mark(uint64_t leaf) { dirty_bits[leaf >> 6] |= 1ull << (leaf & 63); n_marks++; }
+    };
     bool incremental = false, need_full = false;
     std::vector<Tree> trees;
     uint8_t* d_levels = nullptr;
@@ -1036,15 +1042,18 @@ int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* offsets, cons
     }
     // pass 1: every edit must hit resident bytes — validated BEFORE anything is modified, so a rejected batch leaves the
     // handle (host literals, dirty lists, device copy) exactly as it was
+    size_t hit = ~(size_t)0;
     for (uint32_t i = 0; i < n; i++) {
         const uint64_t lo = offsets[i], hi = lo + lens[i];
         if (lens[i] == 0) continue;
         bool touched = false;
+        if (hit < st->copy_order.size() && st->copies[st->copy_order[hit]].src_off <= lo &&
+            hi <= st->copies[st->copy_order[hit]].src_off + st->copies[st->copy_order[hit]].nbytes) continue;   // same field as the last edit
         size_t k = std::partition_point(st->copy_order.begin(), st->copy_order.end(), [&](uint32_t ci) {
                        const StageCopy& cp = st->copies[ci];
                        return cp.src_off + cp.nbytes <= lo;
                    }) - st->copy_order.begin();
-        if (k < st->copy_order.size() && st->copies[st->copy_order[k]].src_off < hi) touched = true;
+        if (k < st->copy_order.size() && st->copies[st->copy_order[k]].src_off < hi) { touched = true; hit = k; }
         if (!touched) {
             size_t m = std::partition_point(st->lit_order.begin(), st->lit_order.end(), [&](uint32_t li) {
                            const Plan::LitSrc& ls = pl.lit_src[li];
@@ -1058,15 +1067,20 @@ int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* offsets, cons
             return LHB200_EINVAL;
         }
     }
+    size_t last_k = ~(size_t)0;
     for (uint32_t i = 0; i < n; i++) {
         const uint64_t lo = offsets[i], hi = lo + lens[i];
         const uint8_t* src = data + blob_off;
         bool touched = lens[i] == 0;
-        // first resident range whose end lies beyond lo
-        size_t k = std::partition_point(st->copy_order.begin(), st->copy_order.end(), [&](uint32_t ci) {
-                       const StageCopy& cp = st->copies[ci];
-                       return cp.src_off + cp.nbytes <= lo;
-                   }) - st->copy_order.begin();
+        // first resident range whose end lies beyond lo (consecutive edits usually hit the same field: try it first)
+        size_t k = last_k;
+        if (!(k < st->copy_order.size() && st->copies[st->copy_order[k]].src_off <= lo &&
+              lo < st->copies[st->copy_order[k]].src_off + st->copies[st->copy_order[k]].nbytes))
+            k = std::partition_point(st->copy_order.begin(), st->copy_order.end(), [&](uint32_t ci) {
+                    const StageCopy& cp = st->copies[ci];
+                    return cp.src_off + cp.nbytes <= lo;
+                }) - st->copy_order.begin();
+        last_k = k;
         for (; k < st->copy_order.size(); k++) {
             const uint32_t ci = st->copy_order[k];
             const StageCopy& cp = st->copies[ci];
@@ -1080,8 +1094,8 @@ int32_t lhb200_state_patch_batch(lhb200_state* st, const uint64_t* offsets, cons
                 if (ti < 0) { st->need_full = true; continue; }   // a list without a resident tree (votes, summaries, ...)
                 lhb200_state::Tree& t = st->trees[ti];
                 const uint64_t i0 = (a - t.src_off) / t.item_bytes, i1 = (b - 1 - t.src_off) / t.item_bytes;
-                if (t.dirty.size() + (i1 - i0 + 1) > lhb200_state::DIRTY_CAP) { st->need_full = true; continue; }
-                for (uint64_t q = i0; q <= i1; q++) t.dirty.push_back((uint32_t)q);
+                if (t.n_marks + (i1 - i0 + 1) > 4ull * lhb200_state::DIRTY_CAP) { st->need_full = true; continue; }
+                for (uint64_t q = i0; q <= i1; q++) t.mark(q);
             }
         }
         size_t m = std::partition_point(st->lit_order.begin(), st->lit_order.end(), [&](uint32_t li) {
@@ -1143,6 +1157,8 @@ static int32_t state_build_levels(lhb200_state* st, cudaStream_t s) {
             n = ceil_div(n, 2);
         }
         t.dirty.clear();
+        std::fill(t.dirty_bits.begin(), t.dirty_bits.end(), 0ull);
+        t.n_marks = 0;
     }
     st->need_full = false;
     LHB_CUDA(cudaGetLastError());
@@ -1152,8 +1168,22 @@ static int32_t state_build_levels(lhb200_state* st, cudaStream_t s) {
 static int32_t state_incremental_enqueue(lhb200_state* st, cudaStream_t s) {
     uint32_t total = 0;
     for (lhb200_state::Tree& t : st->trees) {
-        if (!std::is_sorted(t.dirty.begin(), t.dirty.end())) std::sort(t.dirty.begin(), t.dirty.end());
-        t.dirty.erase(std::unique(t.dirty.begin(), t.dirty.end()), t.dirty.end());
+        t.dirty.clear();
+        if (t.n_marks) {
+            for (size_t w = 0; w < t.dirty_bits.size(); w++) {
+                uint64_t bits = t.dirty_bits[w];
+                while (bits) {
+                    t.dirty.push_back((uint32_t)(w * 64 + (uint32_t)__builtin_ctzll(bits)));
+                    bits &= bits - 1;
+                }
+                t.dirty_bits[w] = 0;
+            }
+            t.n_marks = 0;
+        }
+        if (t.dirty.size() > lhb200_state::DIRTY_CAP) {   // too many distinct leaves for the warm buffers: cold root instead
+            st->need_full = true;
+            return 1;   // (positive: not an error) the caller falls back to the cold path, which also rebuilds the levels
+        }
         total += (uint32_t)t.dirty.size();
     }
     uint64_t hashes = st->plan.ops.size();
@@ -1236,6 +1266,7 @@ int32_t lhb200_state_enable_incremental(lhb200_state* st) {
             off += align_up(n * 32, 256);
         }
         t.src_off = ts.src_off; t.src_bytes = ts.src_bytes; t.item_bytes = ts.item_bytes;
+        t.dirty_bits.assign((ts.n_chunks + 63) / 64, 0ull);
         st->trees.push_back(t);
     }
     LHB_CUDA(cudaMalloc(reinterpret_cast<void**>(&st->d_trees), st->trees.size() * sizeof(TreeDev) + 256));
@@ -1252,9 +1283,9 @@ int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
     if (!st->e_k0) { cudaEventCreate(&st->e_k0); cudaEventCreate(&st->e_k1); }
     int32_t rc;
-    if (st->incremental && !st->need_full) {
-        rc = state_incremental_enqueue(st, s);
-    } else {
+    rc = 1;
+    if (st->incremental && !st->need_full) rc = state_incremental_enqueue(st, s);
+    if (rc > 0) {
         rc = plan_enqueue(st->plan, s, st->e_k0, st->e_k1);
         st->last_root_hashes = st->plan.hash_units;
         if (!rc && st->incremental) rc = state_build_levels(st, s);   // a cold root leaves the level arrays stale

@@ -120,12 +120,26 @@ class MerkleTree:
         return leaf, branch
 
     def finalize_deposits(self, deposits_to_finalize, level=None):
-        """lib.rs:185-219: every subtree entirely inside the first `deposits_to_finalize` leaves becomes a Finalized
-        node.  Descending into an unpopulated (Zero) subtree is the error ZeroNodeFinalized; a count of 0 still
-        finalizes leaf 0 (the reference's Leaf arm has no count check)."""
+        """lib.rs:185-219: every subtree the reference's recursion marks Finalized.  It descends from the root: a node
+        of 2^l leaves with 2^l <= count is finalized whole (even when partly populated: its hash then covers zero
+        leaves), otherwise its left child is visited and, when count exceeds half, its right child with the rest —
+        which is the error ZeroNodeFinalized if that child holds no leaf.  A count of 0 still finalizes leaf 0 (the
+        Leaf arm has no count check)."""
         n = max(int(deposits_to_finalize), 1)
-        if n > len(self):
+        m = len(self)
+        if m == 0:
             raise MerkleTreeError("ZeroNodeFinalized")
+        pos, rem, lvl = 0, n, self.depth
+        while True:                                   # the reference's walk, to find the Zero-node error cases
+            if (1 << lvl) <= rem or lvl == 0:
+                break
+            half = 1 << (lvl - 1)
+            if rem > half:
+                if m <= pos + half:                   # right child is Zero(lvl - 1)
+                    raise MerkleTreeError("ZeroNodeFinalized")
+                pos, rem = pos + half, rem - half
+            lvl -= 1
+        n = min(n, 1 << self.depth)
         if n <= self.finalized_count:
             return
         levels = self._levels()
@@ -133,7 +147,8 @@ class MerkleTree:
         for l in range(self.depth, -1, -1):
             if (n >> l) & 1:
                 start, nodes = levels[l]
-                hashes.append(nodes[(pos >> l) - start])
+                k = (pos >> l) - start
+                hashes.append(nodes[k] if 0 <= k < len(nodes) else _zero_hash(l))
                 pos += 1 << l
         self.leaves = self.leaves[n - self.finalized_count:]
         self.finalized, self.finalized_count = hashes, n

@@ -260,7 +260,7 @@ EXPORT int hs_miller_coop(const uint8_t* p96, const uint8_t* q96, const uint8_t*
     const uint32_t n_total = n + (have_extra ? 1 : 0);
     const uint32_t n_blocks = (n_total + spb - 1) / spb;          // "warps" of NT lanes
     const uint32_t rounds_cap = (spb + NT - 1) / NT;
-    std::vector<Fp12> outs(n_blocks * (NT / 6));
+    std::vector<Fp12> outs(n_blocks);
     G1Proj3 neg_g1; neg_g1.px = G1_GEN_X; fp_neg(neg_g1.py, G1_GEN_Y); neg_g1.pz = FP_ONE;
     for (uint32_t b = 0; b < n_blocks; b++) {
         std::vector<uint32_t> smem(mc::region_words<NT>(), 0xdeadbeefu);
@@ -276,8 +276,9 @@ EXPORT int hs_miller_coop(const uint8_t* p96, const uint8_t* q96, const uint8_t*
         mc::Args a;
         a.P = P.data(); a.H = H.data(); a.status = status; a.n = n; a.extra_q = have_extra ? &extra : nullptr; a.extra_p = &neg_g1;
         a.lo = b * spb; a.hi = std::min<uint32_t>(n_total, a.lo + spb);
-        a.scratch = scratch.data(); a.out = &outs[b * (NT / 6)];
+        a.scratch = scratch.data();
         mc::miller_program<NT>(ex, a);
+        for (int t = 0; t < 6; t++) mc::store_group0(ex.lanes[t], outs[b]);
     }
     Fp12 f = outs[0];
     for (size_t i = 1; i < outs.size(); i++) fp12_mul(f, f, outs[i]);

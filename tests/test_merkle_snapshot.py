@@ -49,13 +49,22 @@ def test_finalize_snapshot_roundtrip(gpu, depth, n):
 
 def test_finalize_and_snapshot_errors(gpu):
     from lighthouse_b200.merkle_proof import MerkleTree, MerkleTreeError
-    t = MerkleTree.create(leaves_of(3), 4)
-    with pytest.raises(MerkleTreeError):                      # ZeroNodeFinalized (lib.rs:192)
-        t.finalize_deposits(4, 4)
-    with pytest.raises(SP.SpecError):
-        SP.finalize(SP.create(leaves_of(3), 4), 4, 4)
-    t.finalize_deposits(0, 4)                                 # the reference's Leaf arm finalizes leaf 0 regardless
-    assert t.get_finalized_hashes() == SP.finalized_hashes(SP.finalize(SP.create(leaves_of(3), 4), 0, 4))
+    # every (leaf count, finalize count) of a depth-4 tree: same Ok / ZeroNodeFinalized outcome and the same finalized
+    # hashes as the reference's recursion (a partly populated subtree IS finalized whole when the count covers it)
+    for m in range(0, 12):
+        for n in range(0, 17):
+            t = MerkleTree.create(leaves_of(m), 4)
+            try:
+                want = SP.finalized_hashes(SP.finalize(SP.create(leaves_of(m), 4), n, 4))
+            except SP.SpecError:
+                want = None
+            if want is None:
+                with pytest.raises(MerkleTreeError):
+                    t.finalize_deposits(n, 4)
+            else:
+                t.finalize_deposits(n, 4)
+                assert t.get_finalized_hashes() == want, (m, n)
+                assert t.hash() == SP.node_hash(SP.create(leaves_of(m), 4))
     with pytest.raises(MerkleTreeError):                      # EmptyBranchWithNonZeroDeposits (lib.rs:243-248)
         MerkleTree.from_finalized_snapshot([], 3, 4)
     with pytest.raises(MerkleTreeError):                      # EndOfTree (lib.rs:258-260)
