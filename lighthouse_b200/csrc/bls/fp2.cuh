@@ -228,6 +228,17 @@ LHB_HD LHB_INLINE void fp2_inv(Fp2& r, const Fp2& a) {
     fp_mul(t, a.c1, n);
     fp_neg(r.c1, t);
 }
+// the same with the variable-time Fp inversion (public values only: the final exponentiation)
+LHB_HD LHB_INLINE void fp2_inv_vartime(Fp2& r, const Fp2& a) {
+    Fp n, t;
+    fp_sqr(n, a.c0);
+    fp_sqr(t, a.c1);
+    fp_add(n, n, t);
+    fp_inv_vartime(n, n);
+    fp_mul(r.c0, a.c0, n);
+    fp_mul(t, a.c1, n);
+    fp_neg(r.c1, t);
+}
 // RFC 9380 sgn0 (m = 2) of a Montgomery-form element
 LHB_HD LHB_INLINE uint32_t fp2_sgn0(const Fp2& a) {
     Fp c0, c1;
@@ -370,7 +381,7 @@ LHB_HD LHB_NOINLINE void fp6_inv(Fp6& r, const Fp6& a) {
     fp2_mul_xi(d, d);
     fp2_mul(s, a.c0, t0);
     fp2_add(d, d, s);
-    fp2_inv(d, d);
+    fp2_inv_vartime(d, d);   // fp6_inv / fp12_inv only serve the final exponentiation (public values)
     fp2_mul(r.c0, t0, d);
     fp2_mul(r.c1, t1, d);
     fp2_mul(r.c2, t2, d);

@@ -30,6 +30,7 @@ EXPORT int hs_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
         case 3: fp_inv(r, x); break;
         case 4: fp_neg(r, x); break;
         case 5: ok = fp_sqrt(r, x); break;
+        case 6: fp_inv_vartime(r, x); break;
         default: return -1;
     }
     fp_out(out, r);

@@ -41,6 +41,8 @@ def test_fp_ops(L):
             assert op(1, a, b)[1] == (a + b) % P
             assert op(2, a, b)[1] == (a - b) % P
         assert op(4, a)[1] == -a % P
+    for a in vals:
+        assert op(6, a)[1] == (pow(a, -1, P) if a else 0)     # binary-GCD inversion (final exponentiation)
     for a in vals[:40]:
         if a:
             assert op(3, a)[1] == pow(a, -1, P)
