@@ -442,10 +442,11 @@ def run_ours(args):
         stream2 = torch.cuda.Stream(device=dev)
 
         def cfg4_step():
-            roots4.zero_()
+            stream2.wait_stream(stream)          # after the previous step's root all-reduce on `stream`
             with torch.cuda.stream(stream):
                 b4.enqueue(sp)
             with torch.cuda.stream(stream2):     # the state roots run beside the BLS kernels on a second stream
+                roots4.zero_()
                 for i in my_states:
                     d_root = st.enqueue(stream2.cuda_stream)
                     roots4[32 * i:32 * i + 32].copy_(torch.as_tensor(DevPtr(d_root, 32), device=dev), non_blocking=True)
@@ -469,7 +470,12 @@ def run_ours(args):
             e1.record(stream)
         barrier()
         ms4 = max_over_ranks(e0.elapsed_time(e1)) / n4
-        assert bytes(roots4[32 * my_states[0]:32 * my_states[0] + 32].cpu().tolist()) == root0 if my_states else True
+        torch.cuda.synchronize()
+        got4 = bytes(roots4.cpu().tolist())
+        for i in range(CFG4_STATES):             # every slot (mine and the ones the all-reduce brought) is the cold root
+            if got4[32 * i:32 * i + 32] != root0:
+                raise RuntimeError(f"cfg4: state root slot {i} on rank {rank} is {got4[32 * i:32 * i + 32].hex()}, "
+                                   f"expected {root0.hex()}")
         ideal_bls = CFG4_SETS / bls_value * 1e3 * 1.0          # ms at the cfg2 rate of this run (all ranks)
         cfg4 = {"workload": f"mixed epoch: {CFG4_SETS} aggregate attestations x {KEYS_PER_SET} keys + {CFG4_STATES} cold "
                             f"{N_VALIDATORS_STATE}-validator state roots, sets sharded and whole states round-robin over "

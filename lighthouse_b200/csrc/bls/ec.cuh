@@ -272,6 +272,23 @@ LHB_HD LHB_INLINE bool jac_eq(const Jac<F>& a, const Jac<F>& b) {
     return f_eq(l, r);
 }
 
+// G1 membership (key_validate, blst.rs:130-140 -> blst's POINTonE1_in_G1) without the 255-bit [r]P: with
+// phi(x, y) = (beta x, y) acting on G1 as multiplication by -x^2, P is in G1 <=> phi(P) == -[x^2]P (Scott 2021, sec. 6);
+// two sparse 64-bit multiplications (126 doublings + 10 additions) instead of 255 doublings + ~128 additions.
+// The [x]P == P guard rejects the points of E(Fp) on which [x] is the identity before the comparison.
+LHB_HD LHB_NOINLINE bool g1_in_subgroup(const G1Affine& a) {
+    if (a.inf) return true;
+    G1Jac p, t;
+    jac_from_affine(p, a);
+    jac_mul_x_abs(t, p);                  // [|x|]P
+    if (jac_eq(t, p)) return false;
+    jac_mul_x_abs(t, t);                  // [x^2]P
+    jac_neg(t, t);
+    G1Jac e = p;
+    fp_mul(e.X, p.X, G1_BETA);            // phi(P)
+    return jac_eq(t, e);
+}
+
 // [r]P for a 64-bit r, SIMT-friendly: right-to-left over signed base-4 digits d_j in {-2,-1,0,1} with two
 // buckets (B1 collects +-4^j P for |d_j| = 1, B2 for |d_j| = 2), result B1 + 2 B2.  Every lane performs the same
 // 33 additions at the same program points (only the target bucket / sign differ), so a warp does 33 + 2 additions

@@ -539,12 +539,7 @@ __global__ void __launch_bounds__(BLS_BLOCK) k_g1_decompress_validate(const uint
     if (rc == DEC_BAD) s = 2;
     else if (rc == DEC_INFINITY) s = 1;
     else {
-        // [r]P == inf  (r = group order, 255 bits)
-        const uint32_t R_ORDER[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
-                                     0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
-        G1Jac j;
-        jac_mul_affine(j, a, R_ORDER, 255);
-        if (!jac_is_inf(j)) s = 3;
+        if (!g1_in_subgroup(a)) s = 3;
     }
     g1_to_uncompressed(b, a);
     for (int t = 0; t < 96; t++) pk96[96ull * i + t] = (s == 0) ? b[t] : 0;

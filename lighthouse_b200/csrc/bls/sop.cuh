@@ -67,6 +67,12 @@ LHB_HD LHB_INLINE void sop_finish(Fp& r, uint32_t* even, uint32_t* odd) {
     fp_final_sub(r, even, 0);
 }
 
+#ifndef LHB_SOP_UNROLL_SMALL
+#define LHB_SOP_UNROLL_SMALL 0   // measured: -11 % instructions but +1.3 ms in k_miller_coop (instruction cache), DESIGN.md §9
+#endif
+#ifndef LHB_SOP_UNROLL_BIG
+#define LHB_SOP_UNROLL_BIG 1
+#endif
 // K register-resident x operands
 template <int K>
 struct SopX {
@@ -98,7 +104,10 @@ LHB_HD LHB_INLINE void fp_sop2(Fp& ra, Fp& rb, const SopX<K>& xa, const SopY<K>&
     uint32_t ea[NL], oa[NL], eb[NL], ob[NL];
 #pragma unroll
     for (int i = 0; i < NL; i++) { ea[i] = 0; oa[i] = 0; eb[i] = 0; ob[i] = 0; }
-#pragma unroll 1
+    // the rolled loop rotates its window registers with MOVs (a sixth of the instructions); LHB_SOP_UNROLL_SMALL=1 unrolls
+    // the K <= 2 bodies fully to remove them — fewer instructions, but the 4 x 19 KB bodies miss the instruction cache
+    constexpr int ROW_UNROLL = (LHB_SOP_UNROLL_SMALL && K <= 2) ? 6 : LHB_SOP_UNROLL_BIG;
+#pragma unroll ROW_UNROLL
     for (int jp = 0; jp < NL; jp += 2) {
         uint32_t sa0[K], sa1[K], sb0[K], sb1[K];
 #pragma unroll

@@ -418,7 +418,6 @@ static int32_t run_simple(const uint8_t* h_in, size_t in_bytes, uint8_t out[32],
 // ---------------------------------------------------------------------------------------------------------
 // Deneb BeaconState (mainnet preset).  Fixed-part offsets: see DESIGN.md §3 / oracle for the derivation.
 namespace deneb {
-constexpr uint32_t FIXED = 2736653;
 constexpr uint32_t O_GENESIS_TIME = 0, O_GVR = 8, O_SLOT = 40, O_FORK = 48, O_LBH = 64, O_BLOCK_ROOTS = 176,
                    O_STATE_ROOTS = 262320, O_HIST_OFF = 524464, O_ETH1_DATA = 524468, O_VOTES_OFF = 524540,
                    O_DEPOSIT_INDEX = 524544, O_VAL_OFF = 524552, O_BAL_OFF = 524556, O_RANDAO = 524560,
@@ -429,7 +428,6 @@ constexpr uint32_t SYNC_COMMITTEE_BYTES = 513 * 48;
 }  // namespace deneb
 
 static inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
-static inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
 
 }  // namespace lhb200
 
@@ -1619,18 +1617,23 @@ struct BlockDescriber {
 }  // namespace
 extern "C" {
 
-// n BeaconBlockDeneb SSZ blobs, concatenated; offsets[n+1]; roots n*32; body_roots n*32 or NULL.
-static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
-                                 uint8_t* body_roots, bool blinded) {
-    LHB_REQUIRE_READY();
-    if (!ssz || !offsets || !roots || n == 0) { set_error("beacon_block_roots: null argument or zero blocks"); return LHB200_EINVAL; }
-    for (uint32_t i = 0; i < n; i++)
-        if (offsets[i] > offsets[i + 1]) { set_error("beacon_block_roots: offsets not monotone"); return LHB200_EINVAL; }
-    Ctx& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    const uint64_t base = offsets[0], total = offsets[n] - offsets[0];
-    const size_t in_pad = align_up(total + 64, 256);
-    const size_t lit_cap = align_up(8 * total + 4096, 256);  // every 4 input bytes yield at most one 32-byte literal
+constexpr int32_t LHB200_ERETRY = -1000;   // internal: the plan did not fit the arena bound of this attempt
+
+// transactions in one BeaconBlockDeneb blob (0 when the offsets are not plausible — the describer reports that)
+static uint64_t prescan_transactions(const uint8_t* blk, uint64_t len) {
+    auto rd = [&](uint64_t o) { uint32_t v; memcpy(&v, blk + o, 4); return (uint64_t)v; };
+    if (len < 84 + 392) return 0;
+    const uint64_t body = 84, o_ep = rd(body + 380), o_bc = rd(body + 384);
+    if (o_ep > o_bc || body + o_bc > len || o_bc - o_ep < 528) return 0;
+    const uint64_t pay = body + o_ep, plen = o_bc - o_ep, o_tx = rd(pay + 504), o_wd = rd(pay + 508);
+    if (o_tx > o_wd || o_wd > plen || o_wd - o_tx < 4) return 0;
+    const uint64_t first = rd(pay + o_tx);
+    return first <= o_wd - o_tx ? first / 4 : 0;
+}
+
+static int32_t block_roots_attempt(Ctx& c, const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
+                                   uint8_t* body_roots, bool blinded, uint64_t base, uint64_t total, size_t in_pad,
+                                   size_t max_nodes, size_t lit_cap) {
     uint8_t *d_in = nullptr, *d_roots = nullptr, *d_body = nullptr;
     bool bad = false;
     auto build = [&](Plan& p) {
@@ -1646,9 +1649,7 @@ static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, ui
                      reinterpret_cast<uint64_t>(d_body + 32ull * i));
         bad = bd.bad;
     };
-    // One planning pass over a conservatively sized arena (host time matters here: a block is only ~10^4 hashes).
-    // Nodes (ops + items) <= one per 4 input bytes + the zero ladders of the 10 lists of a block.
-    const size_t max_nodes = total / 4 + 512ull * n;
+    // One planning pass over the bounded arena (host time matters here: a block is only ~10^4 hashes).
     const size_t prog_bytes = align_up(max_nodes * sizeof(HashOp), 256) + align_up((max_nodes + 2) * 4, 256) +
                               align_up(max_nodes * sizeof(ByteItem), 256) + 1024;
     // literals | node pool (op outputs) | staged blob | roots | item outputs | program blobs
@@ -1660,11 +1661,12 @@ static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, ui
     Plan pl;
     int32_t rc = build_plan(pl, arena, need, lit_cap, build, max_nodes);
     if (bad) { set_error("BeaconBlockDeneb SSZ: malformed offsets or lengths"); return LHB200_EINVAL; }
-    if (rc) return rc;
-    if (pl.ops.size() + pl.items.size() > max_nodes || pl.bump + prog_bytes > need) {
+    if (pl.node_overflow || pl.lit.size() > lit_cap || pl.ops.size() + pl.items.size() > max_nodes ||
+        pl.bump + prog_bytes > need) {
         set_error("internal: block plan exceeds its arena bound");
-        return LHB200_EINVAL;
+        return LHB200_ERETRY;
     }
+    if (rc) return rc;
     memcpy(hst, ssz + base, total);
     memset(hst + total, 0, align_up(total, 256) - total);
     LHB_CUDA(cudaMemcpyAsync(d_in, hst, align_up(total, 256), cudaMemcpyHostToDevice, c.stream));
@@ -1682,6 +1684,35 @@ static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, ui
     memcpy(roots, h_out, 32ull * n);
     if (body_roots) memcpy(body_roots, h_out + 32ull * n, 32ull * n);
     return LHB200_OK;
+}
+
+// n BeaconBlockDeneb SSZ blobs, concatenated; offsets[n+1]; roots n*32; body_roots n*32 or NULL.
+static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
+                                 uint8_t* body_roots, bool blinded) {
+    LHB_REQUIRE_READY();
+    if (!ssz || !offsets || !roots || n == 0) { set_error("beacon_block_roots: null argument or zero blocks"); return LHB200_EINVAL; }
+    for (uint32_t i = 0; i < n; i++)
+        if (offsets[i] > offsets[i + 1]) { set_error("beacon_block_roots: offsets not monotone"); return LHB200_EINVAL; }
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    const uint64_t base = offsets[0], total = offsets[n] - offsets[0];
+    const size_t in_pad = align_up(total + 64, 256);
+    // Offset pre-scan: the only SSZ shape with more than one tree node per ~14 input bytes is a run of (near-)empty
+    // transactions — a 4-byte offset each, one byte item + one list node + one length literal.  Count them per block
+    // (three offset reads) so the arena bound is tight for real blocks and still holds for that shape.
+    uint64_t n_tx = 0;
+    if (!blinded)
+        for (uint32_t i = 0; i < n; i++) n_tx += prescan_transactions(ssz + offsets[i], offsets[i + 1] - offsets[i]);
+    int32_t rc = LHB200_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // attempt 0: transactions counted, everything else <= one node per 12 bytes and one literal per 8 bytes;
+        // attempt 1 (only if a plan ever exceeds that): the unconditional bound of one node and literal per 2 bytes.
+        const size_t max_nodes = attempt == 0 ? 2 * n_tx + total / 12 + 512ull * n : total / 2 + 512ull * n;
+        const size_t lit_cap = align_up(32 * (attempt == 0 ? n_tx + total / 8 + 128ull * n : total / 2 + 128ull * n), 256);
+        rc = block_roots_attempt(c, ssz, offsets, n, roots, body_roots, blinded, base, total, in_pad, max_nodes, lit_cap);
+        if (rc != LHB200_ERETRY) break;
+    }
+    return rc == LHB200_ERETRY ? LHB200_EINVAL : rc;
 }
 int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
                                         uint8_t* body_roots) {

@@ -118,6 +118,10 @@ EXPORT int hs_g2_subgroup(const uint8_t* p96) {
     G2Affine a; int rc = g2_decompress(a, p96); if (rc == DEC_BAD) return -1;
     return g2_in_subgroup(a) ? 1 : 0;
 }
+EXPORT int hs_g1_subgroup(const uint8_t* p48) {
+    G1Affine a; int rc = g1_decompress(a, p48); if (rc == DEC_BAD) return -1;
+    return g1_in_subgroup(a) ? 1 : 0;
+}
 EXPORT int hs_g2_mul(const uint8_t* p96, const uint32_t* k, int nbits, uint8_t* out96) {
     G2Affine a; if (g2_decompress(a, p96) == DEC_BAD) return -1;
     G2Jac j; jac_mul_affine(j, a, k, nbits);

@@ -76,6 +76,20 @@ def test_gpu_block_root_large_transaction(gpu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tx_sizes", [[0] * 50_000, [1, 0, 3] * 9_000], ids=["empty_txs", "tiny_txs"])
+def test_gpu_block_of_many_tiny_transactions(gpu, tx_sizes):
+    """Valid SSZ with two tree nodes per 4-byte offset (far outside any gas limit): the offset pre-scan sizes the arena
+    for it (round 1 refused this shape with EINVAL), alone and inside a batch with ordinary blocks."""
+    from lighthouse_b200 import tree_hash
+    _, ssz = synthetic.beacon_block_deneb(seed=21, n_attestations=3, tx_sizes=tx_sizes)
+    want = O.beacon_block_root_deneb(ssz)
+    assert tree_hash.beacon_block_root_deneb(ssz, want_body_root=True) == want
+    other = synthetic.beacon_block_deneb(seed=22)[1]
+    assert tree_hash.beacon_block_roots_deneb([other, ssz, other]) == [O.beacon_block_root_deneb(other)[0], want[0],
+                                                                       O.beacon_block_root_deneb(other)[0]]
+
+
+@pytest.mark.gpu
 def test_gpu_rejects_malformed_blocks(gpu):
     from lighthouse_b200 import tree_hash, Lhb200Error
     from lighthouse_b200._ffi import EINVAL

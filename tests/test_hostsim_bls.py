@@ -175,6 +175,35 @@ def test_g1(L):
     assert L.hs_g1_sum(B.g1_uncompressed(pts[0]) + B.g1_uncompressed(B.g1_neg(pts[0])), 2, o) == 0 and o.raw[0] == 0x40
 
 
+def test_g1_subgroup_check_by_endomorphism(L):
+    """g1_in_subgroup (phi(P) == -[x^2]P) against the definition [r]P == inf (oracle), on subgroup points, on curve points
+    outside the subgroup, and on points of the cofactor's small prime orders (3, 11)"""
+    rnd = random.Random(11)
+    for _ in range(3):
+        assert L.hs_g1_subgroup(B.g1_compress(B.g1_mul(B.G1_GEN, rnd.randrange(1, B.R)))) == 1
+    h = (B.X_ABS + 1) ** 2 // 3
+    assert h % 3 == 0 and h % 11 == 0
+    x, seen = 1, 0
+    while seen < 6:
+        y = B.fp_sqrt((x ** 3 + 4) % B.P)
+        x += 1
+        if y is None:
+            continue
+        pt = (x - 1, y)
+        assert not B.g1_in_subgroup(pt)
+        assert L.hs_g1_subgroup(B.g1_compress(pt)) == 0
+        co = B.g1_mul(pt, B.R)                       # a point of the cofactor group
+        if co is not None:
+            assert L.hs_g1_subgroup(B.g1_compress(co)) == 0
+            for q in (3, 11):
+                t = B.g1_mul(co, h // q)             # order q (or infinity)
+                if t is not None:
+                    assert L.hs_g1_subgroup(B.g1_compress(t)) == 0
+            mixed = B.g1_add(co, B.G1_GEN)           # subgroup component + cofactor component
+            assert L.hs_g1_subgroup(B.g1_compress(mixed)) == 0
+        seen += 1
+
+
 def test_g2_and_hash_to_curve(L):
     rnd = random.Random(5)
     Q = B.g2_mul(B.G2_GEN, rnd.randrange(B.R))
