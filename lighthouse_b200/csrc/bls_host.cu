@@ -528,8 +528,14 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     }
     uint64_t launches = 0;
     // key ingest through the TMA unit (bulk async copies into a shared-memory ring); needs 16-byte aligned keys
-    static const int pk_tma_env = [] { const char* e = getenv("LHB_PK_TMA"); return e ? atoi(e) : 1; }();
-    const bool pk_tma = pk_tma_env && b->in_pks && ((uintptr_t)b->in_pks & 15) == 0;
+    // Only for batches that fill the GPU by themselves: the ring needs a shared-memory carve-out, and an SM that is
+    // running blocks of the (shared-memory-free, full-L1) k_sig_prepare / k_hash_to_g2 cannot take a block with a
+    // different carve-out until it drains — on the 5 216-set block-import batch that serialised the three stages
+    // (32.5 ms against 19.9 ms with the plain kernel, which also copes better with ragged 1 ... 512-key lists).
+    // LHB_PK_TMA=0 / 1 forces the choice (tuning, tests).
+    static const int pk_tma_env = [] { const char* e = getenv("LHB_PK_TMA"); return e ? atoi(e) : -1; }();
+    const bool pk_tma_fit = b->in_pks && ((uintptr_t)b->in_pks & 15) == 0;
+    const bool pk_tma = pk_tma_fit && (pk_tma_env < 0 ? n >= 4u * BLS_BLOCK * (uint32_t)n_sm : pk_tma_env != 0);
     if (b->n_chunks) LHB_CUDA(cudaStreamWaitEvent(s, b->e_small, 0));  // streamed upload: small arrays first
     LHB_CUDA(cudaMemsetAsync(b->d_status, 0, n, s));
     LHB_CUDA(cudaMemsetAsync(b->d_fail, 0, 4, s));

@@ -1663,7 +1663,9 @@ static int32_t block_roots_attempt(Ctx& c, const uint8_t* ssz, const uint64_t* o
     if (bad) { set_error("BeaconBlockDeneb SSZ: malformed offsets or lengths"); return LHB200_EINVAL; }
     if (pl.node_overflow || pl.lit.size() > lit_cap || pl.ops.size() + pl.items.size() > max_nodes ||
         pl.bump + prog_bytes > need) {
-        set_error("internal: block plan exceeds its arena bound");
+        set_error("internal: block plan exceeds its arena bound (%zu ops + %zu items of %zu nodes, %zu of %zu literal bytes, "
+                  "%zu of %zu arena bytes)", pl.ops.size(), pl.items.size(), max_nodes, pl.lit.size(), lit_cap,
+                  pl.bump + prog_bytes, need);
         return LHB200_ERETRY;
     }
     if (rc) return rc;
