@@ -197,7 +197,7 @@ __device__ __forceinline__ const Fp2& coop_tower_coeff(const Fp12& a, int k) {
 }
 // Largest tail of the Miller product tree that k_final_coop folds itself (a cooperative Fp12 product is ~6 us, one level
 // of the single-thread tree ~350 us of latency).
-constexpr uint32_t COOP_TAIL = 32;
+constexpr uint32_t COOP_TAIL = 64;
 
 // verdict = !fail && final_exp(prod[0] * ... * prod[n_prod-1] * f_last) == 1
 __global__ void __launch_bounds__(COOP_THREADS) k_final_coop(const Fp12* __restrict__ prod, uint32_t n_prod,

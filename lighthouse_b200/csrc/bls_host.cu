@@ -74,6 +74,9 @@ struct lhb200_bls_batch {
     size_t mc_scratch_words = 0;
     G1Proj3* d_neg_g1 = nullptr;
     const G2Jac* d_sig_sum = nullptr;
+    // small / medium batches: slice sums of the key lists (k_pk_partial -> k_pk_combine), PK_SLICES per set
+    G1Jac* d_pk_part = nullptr;
+    uint8_t* d_pk_part_bad = nullptr;
     // streamed key upload (lhb200_bls_batch_upload_async): the key copy is cut into chunks of whole sets on its own
     // stream; k_pk_aggregate runs per chunk as it lands while the signature / hash-to-curve kernels already compute
     static constexpr int MAX_CHUNKS = 16;
@@ -93,7 +96,7 @@ static void batch_free(lhb200_bls_batch* b) {
     if (b->d_indices) cudaFree(b->d_indices);
     void* ptrs[] = {b->d_sigs, b->d_msgs, b->d_pks, b->d_offsets, b->d_rands, b->d_sigr, b->d_sig_tmp[0],
                     b->d_sig_tmp[1], b->d_p, b->d_h, b->d_f, b->d_f_tmp[0], b->d_f_tmp[1], b->d_flast, b->d_gt,
-                    b->d_status, b->d_fail, b->d_ok, b->d_mc_scratch, b->d_neg_g1};
+                    b->d_status, b->d_fail, b->d_ok, b->d_mc_scratch, b->d_neg_g1, b->d_pk_part, b->d_pk_part_bad};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (b->h_res) cudaFreeHost(b->h_res);
@@ -116,6 +119,9 @@ static void batch_free(lhb200_bls_batch* b) {
 }
 
 constexpr uint32_t REDUCE_CHUNK = 8;
+// latency modes of the per-set stages (batches that do not fill the GPU): slice-parallel key sums, two threads per hash
+constexpr uint32_t PK_SPLIT_MAX_SETS = 8192;
+constexpr uint32_t HASH_PAIR_MAX_SETS = 4096;
 
 // ---- pool of batch handles behind lhb200_verify_signature_sets -------------------------------------------------
 namespace {
@@ -199,6 +205,8 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     ALLOC(b->d_fail, 4);
     ALLOC(b->d_ok, 4);
     ALLOC(b->d_neg_g1, sizeof(G1Proj3));
+    ALLOC(b->d_pk_part, std::min<uint64_t>(n, PK_SPLIT_MAX_SETS) * PK_SLICES * sizeof(G1Jac));
+    ALLOC(b->d_pk_part_bad, std::min<uint64_t>(n, PK_SPLIT_MAX_SETS) * PK_SLICES);
 #undef ALLOC
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b->h_res), n + 64 + sizeof(Fp12), cudaHostAllocDefault);
     if (e != cudaSuccess) { batch_free(b); return cuda_fail(e, "cudaHostAlloc(result)"); }
@@ -569,12 +577,36 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         }
         LHB_CUDA(cudaEventRecord(b->e_join, b->s2));
     }
-    k_hash_to_g2<<<grid, BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);
+    if (n <= HASH_PAIR_MAX_SETS)   // latency mode: two threads per message (one SSWU map each)
+        k_hash_to_g2_pair<<<cdiv(2 * n, BLS_BLOCK), BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);
+    else
+        k_hash_to_g2<<<grid, BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);
+    launches++;
     LHB_CUDA(cudaEventRecord(b->e_h2c, b->s3));
-    if (b->table)
+    // explicit keys, sets [lo, lo + cnt): TMA ring for GPU-filling batches, slice-parallel sums for small and medium
+    // ones (a 512-key list is 64 + 8 additions deep instead of 512), one thread per set in between
+    auto launch_pk = [&](uint32_t lo, uint32_t cnt, cudaStream_t st) {
+        if (pk_tma) {
+            k_pk_aggregate_tma<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, st>>>(b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt,
+                                                                          b->d_p + lo, b->d_status + lo, b->d_fail);
+        } else if (n <= PK_SPLIT_MAX_SETS) {
+            k_pk_partial<<<cdiv(cnt * PK_SLICES, BLS_BLOCK), BLS_BLOCK, 0, st>>>(
+                b->in_pks, b->in_offsets + lo, cnt, b->d_pk_part + (size_t)lo * PK_SLICES, b->d_pk_part_bad + (size_t)lo * PK_SLICES);
+            k_pk_combine<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, st>>>(
+                b->d_pk_part + (size_t)lo * PK_SLICES, b->d_pk_part_bad + (size_t)lo * PK_SLICES, b->in_offsets + lo,
+                b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
+            launches++;
+        } else {
+            k_pk_aggregate<<<std::min<uint32_t>(grid, cdiv(cnt, BLS_BLOCK)), BLS_BLOCK, 0, st>>>(
+                b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
+        }
+        launches++;
+    };
+    if (b->table) {
+        launches++;
         k_pk_aggregate_indexed<<<grid, BLS_BLOCK, 0, s>>>(b->table->d_keys, (uint32_t)b->table->len, b->in_indices,
                                                          b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
-    else if (b->n_chunks) {
+    } else if (b->n_chunks) {
         // aggregate each chunk of sets on the (high-priority) stream that copies it, as soon as its keys have landed
         for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++) LHB_CUDA(cudaStreamWaitEvent(b->s_pk[j], b->e_fork, 0));
         for (int c = 0; c < b->n_chunks; c++) {
@@ -584,24 +616,14 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
                 LHB_CUDA(cudaMemcpyAsync(b->d_pks + k0 * 96, b->h_pks + k0 * 96, (k1 - k0) * 96, cudaMemcpyHostToDevice,
                                          b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]));
             if (cnt == 0) continue;
-            if (pk_tma)
-                k_pk_aggregate_tma<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]>>>(
-                    b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
-            else
-                k_pk_aggregate<<<cdiv(cnt, BLS_BLOCK), BLS_BLOCK, 0, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]>>>(
-                    b->in_pks, b->in_offsets + lo, b->in_rands + lo, cnt, b->d_p + lo, b->d_status + lo, b->d_fail);
-            launches++;
+            launch_pk(lo, cnt, b->s_pk[c % lhb200_bls_batch::N_PK_STREAMS]);
         }
         for (int j = 0; j < lhb200_bls_batch::N_PK_STREAMS; j++) {
             LHB_CUDA(cudaEventRecord(b->e_pk[j], b->s_pk[j]));
             LHB_CUDA(cudaStreamWaitEvent(s, b->e_pk[j], 0));
         }
-        launches--;  // (the single-launch form below counts one)
-    } else if (pk_tma)
-        k_pk_aggregate_tma<<<cdiv(n, BLS_BLOCK), BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status,
-                                                                    b->d_fail);
-    else
-        k_pk_aggregate<<<grid, BLS_BLOCK, 0, s>>>(b->in_pks, b->in_offsets, b->in_rands, n, b->d_p, b->d_status, b->d_fail);
+    } else
+        launch_pk(0, n, s);
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_h2c, 0));
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_sig, 0));    // the Miller kernel reads the status bytes k_sig_prepare may set
     static const int miller_coop = [] { const char* e = getenv("LHB_MILLER_COOP"); return e ? atoi(e) : 1; }();
@@ -620,15 +642,56 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         constexpr uint32_t LU = 30;
         const uint32_t n_total = n + 1;
         const uint32_t max_warps = (uint32_t)n_sm * mc::MC_WARPS;
+        // Latency mode (bls/miller_warp.cuh): while every pair can have a warp of its own in one wave, a whole warp runs
+        // one Miller loop at Fp granularity — 0.x ms instead of the 3.7 ms of a lane-per-set loop.  Four warps per block
+        // (one per scheduler) up to 256 pairs, eight above; <= 64 block products go straight to k_final_coop.
+        static const int miller_warp_env = [] { const char* e = getenv("LHB_MILLER_WARP"); return e ? atoi(e) : 1; }();
+        if (miller_warp_env && n_total <= max_warps) {
+            static const bool mw_attr_ok = [] {
+                return cudaFuncSetAttribute(mw::k_miller_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(mc::MC_WARPS * mw::REGION_WORDS * 4)) == cudaSuccess;
+            }();
+            if (!mw_attr_ok) { set_error("k_miller_warp: cannot reserve shared memory"); return LHB200_ECUDA; }
+            const uint32_t wpb = n_total <= 4 * COOP_TAIL ? 4 : mc::MC_WARPS;
+            const uint32_t mgrid = cdiv(n_total, wpb);
+            LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));   // sum r sig (and -g1) ready
+            LHB_CUDA(cudaEventRecord(b->e_k0, s));
+            mw::k_miller_warp<<<mgrid, 32 * wpb, (size_t)wpb * mw::REGION_WORDS * 4, s>>>(b->d_p, b->d_h, b->d_status, n,
+                                                                                         b->d_sig_sum, b->d_neg_g1, b->d_f);
+            LHB_CUDA(cudaEventRecord(b->e_k1, s));
+            launches += 1;
+            uint32_t m = mgrid;
+            int flip = 0;
+            while (m > COOP_TAIL) {
+                const uint32_t mo = cdiv(m, REDUCE_CHUNK);
+                k_fp12_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, s>>>(cur, m, REDUCE_CHUNK, b->d_f_tmp[flip]);
+                launches++;
+                cur = b->d_f_tmp[flip];
+                flip ^= 1;
+                m = mo;
+            }
+            n_tail = m;
+            f_last = nullptr;
+        } else {
         uint32_t spw = cdiv(n_total, max_warps);             // sets per warp
         spw = cdiv(spw, LU) * LU;                            // whole rounds
-        // batches below one full round per warp: as few sets per warp as the warp budget allows (the kernel deals them to
-        // the warp's five groups first): the sparse products of a group are serial over its sets, so a 1-set group
-        // iterates in 81 multiply units instead of the 141 of a full one
-        if (n_total <= max_warps * LU) spw = std::max<uint32_t>(1, cdiv(n_total, max_warps));
-        const uint32_t n_warps = cdiv(n_total, spw);
-        // warps are dealt round-robin to blocks (gw = warp_in_block * grid + block): few warps spread over all SMs
-        const uint32_t mgrid = std::max<uint32_t>(std::min<uint32_t>((uint32_t)n_sm, n_warps), cdiv(n_warps, mc::MC_WARPS));
+        uint32_t n_warps, mgrid;
+        // Batches below one full round per warp.  A warp's five groups take one set each at no extra latency (SIMT), and
+        // every further set of a group adds one serial sparse product per iteration (81 multiply units for a 1-set
+        // group, 141 for a full one).  Small batches therefore use at least five sets per warp, at most 256 warps, four
+        // per block (one per scheduler): <= 64 block products, which k_final_coop folds itself (no k_fp12_reduce level,
+        // 0.55 ms of single-thread latency).  Above that: as few sets per warp as the 8 x n_sm warp budget allows.
+        constexpr uint32_t FEW_WARPS = 4 * COOP_TAIL;
+        if (n_total <= FEW_WARPS * LU) {
+            spw = std::min<uint32_t>(LU, std::max<uint32_t>(5, cdiv(cdiv(n_total, FEW_WARPS), 5) * 5));
+            n_warps = cdiv(n_total, spw);
+            mgrid = cdiv(n_warps, 4);
+        } else {
+            if (n_total <= max_warps * LU) spw = std::max<uint32_t>(1, cdiv(n_total, max_warps));
+            n_warps = cdiv(n_total, spw);
+            // warps are dealt round-robin to blocks (gw = warp_in_block * grid + block): few warps spread over all SMs
+            mgrid = std::max<uint32_t>(std::min<uint32_t>((uint32_t)n_sm, n_warps), cdiv(n_warps, mc::MC_WARPS));
+        }
         const uint32_t rounds_cap = cdiv(spw, LU);
         const size_t need = (size_t)mgrid * mc::MC_WARPS * rounds_cap * 2 * mc::TWORDS * 32;
         if (need > b->mc_scratch_words) {
@@ -656,6 +719,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         }
         n_tail = m;
         f_last = nullptr;
+        }
     } else {
     LHB_CUDA(cudaEventRecord(b->e_k0, s));
     // Sets per thread: k = ceil(n / resident threads) (<= MILLER_KMAX) share their Fp12 squarings in one thread, so a
@@ -673,7 +737,7 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     k_miller_multi<<<std::min<uint32_t>(cdiv(n_groups, MILLER_BLOCK), (uint32_t)(n_sm * miller_occ)), MILLER_BLOCK, 0, s>>>(
         b->d_p, b->d_h, b->d_status, n, mk, n_groups, b->d_f);
     LHB_CUDA(cudaEventRecord(b->e_k1, s));
-    launches += 3;
+    launches += 1;
     {
         uint32_t m = n_groups;
         int flip = 0;

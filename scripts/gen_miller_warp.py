@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""Assembler + checker for the warp-per-pairing Miller program (lighthouse_b200/csrc/bls/miller_warp.cuh).
+
+Small batches are latency bound: one lane (or six) per SignatureSet leaves a 63-iteration chain of ~60 dependent
+Fp products per iteration.  miller_warp.cuh gives ONE WARP to one pairing and runs the arithmetic at Fp granularity:
+every lane computes one Fp value per phase,
+
+    MUL phase (K terms):   slot[d] = ( sum_{q<K} X_q * slot[y_q] ) / R mod p,   X_q = +-slot[x_q] or +-2 slot[x_q]
+    LIN phase:             slot[d] = ( sum_q c_q * slot[s_q] ) / 2^h mod p,     c_q small signed integers
+
+with a warp barrier between phases.  This script writes the phase tables (which lane computes what) from the same
+formulas bls/miller_coop.cuh uses, runs them on Python integers and checks the result against the oracle:
+    * one whole Miller loop + the oracle's final exponentiation == the oracle's pairing,
+    * the dense product section == f12_mul.
+It then emits bls/miller_warp_tables.inc.  Run:  python scripts/gen_miller_warp.py
+"""
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import bls_ref as B  # noqa: E402
+
+P = B.P
+KMAX = 4
+NLANES = 32
+# x-operand modes of a MUL term
+X_ZERO, X_POS, X_NEG, X_DBL, X_NEGDBL = 0, 1, 2, 3, 4
+
+
+class Prog:
+    def __init__(self):
+        self.slots = {}
+        self.sections = {}      # name -> list of phases
+        self.cur = None
+
+    def slot(self, name):
+        if name not in self.slots:
+            self.slots[name] = len(self.slots)
+        return self.slots[name]
+
+    def section(self, name):
+        self.cur = []
+        self.sections[name] = self.cur
+
+    # ---- phases
+    def mul_phase(self, K, ops):
+        """ops: list of (dst, [(mode, xslot, yslot), ...])  one per lane"""
+        assert 1 <= K <= KMAX and len(ops) <= NLANES, (K, len(ops))
+        for d, terms in ops:
+            assert len(terms) <= K
+        self.cur.append(("mul", K, ops))
+
+    def lin_phase(self, ops):
+        """ops: list of (dst, [(coef, slot), ...], halvings)"""
+        assert len(ops) <= NLANES, len(ops)
+        for d, terms, h in ops:
+            assert 1 <= len(terms) <= 4 and all(abs(c) in (1, 2, 3, 12) for c, _ in terms) and 0 <= h <= 2
+        self.cur.append(("lin", 0, ops))
+
+
+def run_section(prog, name, mem):
+    for kind, K, ops in prog.sections[name]:
+        out = []
+        if kind == "mul":
+            for d, terms in ops:
+                acc = 0
+                for mode, xs, ys in terms:
+                    x = mem[xs]
+                    xv = {X_ZERO: 0, X_POS: x, X_NEG: P - x, X_DBL: 2 * x, X_NEGDBL: 2 * P - 2 * x}[mode]
+                    assert 0 <= mem[ys] < P and 0 <= xv <= 2 * P
+                    acc += xv * mem[ys]
+                out.append((d, acc % P))       # (Montgomery factors cancel: values here are plain residues)
+        else:
+            for d, terms, h in ops:
+                acc = sum(c * mem[s] for c, s in terms) % P
+                for _ in range(h):
+                    acc = acc * pow(2, -1, P) % P
+                out.append((d, acc))
+        for d, v in out:                       # all lanes read before any lane writes (barrier semantics)
+            mem[d] = v
+
+
+# ------------------------------------------------------------------------------------------------ Fp2-level builders
+class B2:
+    """collects Fp2-level operations of one phase and lowers them to lane ops"""
+
+    def __init__(self, prog):
+        self.p = prog
+        self.mops = []
+        self.lops = []
+
+    def s2(self, name):
+        return (self.p.slot(name + ".0"), self.p.slot(name + ".1"))
+
+    # d = a * b   (K = 2):  re = a0 b0 - a1 b1,  im = a0 b1 + a1 b0
+    def mul(self, d, a, b):
+        d, a, b = self.s2(d), self.s2(a), self.s2(b)
+        self.mops.append((d[0], [(X_POS, a[0], b[0]), (X_NEG, a[1], b[1])]))
+        self.mops.append((d[1], [(X_POS, a[0], b[1]), (X_POS, a[1], b[0])]))
+
+    # d = a^2:  re = a0 a0 - a1 a1,  im = 2 a0 a1
+    def sqr(self, d, a):
+        d, a = self.s2(d), self.s2(a)
+        self.mops.append((d[0], [(X_POS, a[0], a[0]), (X_NEG, a[1], a[1])]))
+        self.mops.append((d[1], [(X_DBL, a[0], a[1])]))
+
+    # d = a * s, s an Fp slot
+    def mul_fp(self, d, a, s):
+        d, a = self.s2(d), self.s2(a)
+        s = self.p.slot(s)
+        self.mops.append((d[0], [(X_POS, s, a[0])]))
+        self.mops.append((d[1], [(X_POS, s, a[1])]))
+
+    def flush_mul(self, K=2):
+        if self.mops:
+            self.p.mul_phase(K, self.mops)
+            self.mops = []
+
+    # d = sum c_k * a_k  (component-wise), / 2^h
+    def lin(self, d, terms, h=0):
+        d = self.s2(d)
+        for comp in (0, 1):
+            self.lops.append((d[comp], [(c, self.s2(a)[comp]) for c, a in terms], h))
+
+    # d = k * xi * a:   re = k (a0 - a1),  im = k (a0 + a1)
+    def lin_xi(self, d, a, k):
+        d, a = self.s2(d), self.s2(a)
+        self.lops.append((d[0], [(k, a[0]), (-k, a[1])], 0))
+        self.lops.append((d[1], [(k, a[0]), (k, a[1])], 0))
+
+    def flush_lin(self):
+        if self.lops:
+            self.p.lin_phase(self.lops)
+            self.lops = []
+
+
+def coef_slots(prog, base, j):
+    """the four stored forms of coefficient j of an Fp12 value: a0, a1, s = a0 + a1, d = a0 - a1"""
+    return [prog.slot(f"{base}{j}.{c}") for c in ("0", "1", "s", "d")]
+
+
+def build():
+    pr = Prog()
+    # fixed slots first (the kernel addresses them by name): f coefficients, T, Q, P
+    for j in range(6):
+        coef_slots(pr, "f", j)
+    for n in ("X", "Y", "Z", "QX", "QY", "QZ", "HX", "HY", "HZ"):
+        pr.slot(n + ".0"); pr.slot(n + ".1")
+    for n in ("px", "py", "pz"):
+        pr.slot(n)
+    for j in range(6):
+        coef_slots(pr, "g", j)
+    pr.slot("dummy")
+
+    # ---------------------------------------------------------------- INIT: H (Jacobian) -> T = Q = (X Z, Y, Z^3)
+    pr.section("init")
+    b = B2(pr)
+    b.mul("X", "HX", "HZ"); b.sqr("t0", "HZ"); b.flush_mul()
+    b.mul("Z", "t0", "HZ"); b.flush_mul()
+    b.lin("Y", [(1, "HY")]); b.lin("QX", [(1, "X")]); b.lin("QY", [(1, "HY")]); b.lin("QZ", [(1, "Z")]); b.flush_lin()
+
+    # ---------------------------------------------------------------- DBL (Costello-Lange-Naehrig, as miller_coop.cuh)
+    # A = X Y / 2, B = Y^2, C = Z^2, E = 3 b' C = 12 xi C, F = 3 E, X3 = A (B - F), G = (B + F) / 2, Y3 = G^2 - 3 E^2,
+    # H = (Y + Z)^2 - B - C, Z3 = B H;  line c0 = (B - E) pz, c1 = -3 X^2 px, c4 = H py
+    pr.section("dbl")
+    b = B2(pr)
+    b.lin("s1", [(1, "X"), (1, "Y")]); b.lin("s2", [(1, "Y"), (1, "Z")]); b.flush_lin()
+    b.sqr("XX", "X"); b.sqr("B", "Y"); b.sqr("C", "Z"); b.sqr("S2", "s2"); b.sqr("S1", "s1"); b.flush_mul()
+    b.lin_xi("E", "C", 12)
+    b.lin("H", [(1, "S2"), (-1, "B"), (-1, "C")])
+    b.lin("A", [(1, "S1"), (-1, "XX"), (-1, "B")], h=2)          # (2 X Y) / 4
+    b.flush_lin()
+    b.lin("BmF", [(1, "B"), (-3, "E")]); b.lin("BmE", [(1, "B"), (-1, "E")]); b.lin("G", [(1, "B"), (3, "E")], h=1)
+    b.flush_lin()
+    b.mul("X", "A", "BmF"); b.mul("Z", "B", "H"); b.sqr("GG", "G"); b.sqr("EE", "E")
+    b.mul_fp("l1p", "XX", "px"); b.mul_fp("l0", "BmE", "pz"); b.mul_fp("l4", "H", "py"); b.flush_mul()
+    b.lin("Y", [(1, "GG"), (-3, "EE")]); b.lin("l1", [(-3, "l1p")]); b.flush_lin()
+
+    # ---------------------------------------------------------------- ADD (T <- T + Q, add-1998-cmo-2, as miller_coop.cuh)
+    pr.section("add")
+    b = B2(pr)
+    b.mul("d", "Y", "QZ"); b.mul("e", "X", "QZ"); b.mul("ff", "Z", "QZ"); b.mul("y2z1", "QY", "Z"); b.mul("x2z1", "QX", "Z")
+    b.flush_mul()
+    b.lin("u", [(1, "y2z1"), (-1, "d")]); b.lin("v", [(1, "x2z1"), (-1, "e")]); b.flush_lin()
+    b.sqr("vv", "v"); b.sqr("uu", "u"); b.mul("ux2", "u", "QX"); b.mul("vy2", "v", "QY"); b.mul("uz2", "u", "QZ")
+    b.mul("vz2", "v", "QZ"); b.flush_mul()
+    b.lin("l0p", [(1, "ux2"), (-1, "vy2")]); b.flush_lin()
+    b.mul("vvv", "v", "vv"); b.mul("R", "vv", "e"); b.mul("uuz", "uu", "ff"); b.mul_fp("l0", "l0p", "pz")
+    b.mul_fp("l1p", "uz2", "px"); b.mul_fp("l4", "vz2", "py"); b.flush_mul()
+    b.lin("Aa", [(1, "uuz"), (-1, "vvv"), (-2, "R")]); b.lin("l1", [(-1, "l1p")]); b.flush_lin()
+    b.lin("RmA", [(1, "R"), (-1, "Aa")]); b.flush_lin()
+    b.mul("Z", "vvv", "ff"); b.mul("dY", "vvv", "d"); b.mul("X", "v", "Aa"); b.mul("uRA", "u", "RmA"); b.flush_mul()
+    b.lin("Y", [(1, "uRA"), (-1, "dY")]); b.flush_lin()
+
+    # ---------------------------------------------------------------- products into f (w-basis, w^6 = xi)
+    def product_section(name, terms_of):
+        """terms_of(t) -> list of (xname (Fp2 slot name), j, c, xi): out_t = sum c * [xi] * x * a_j over the f
+        coefficients a_j.  Schoolbook on Fp level with the stored forms (a0, a1, s, d) of a_j so that a multiplication by
+        xi costs nothing:  re = c (x0 a0 - x1 a1) | c (x0 d - x1 s),   im = c (x0 a1 + x1 a0) | c (x0 s + x1 d)."""
+        pr.section(name)
+        parts = {}
+        ops = []
+        for t in range(6):
+            terms = terms_of(t)
+            re, im = [], []
+            for xn, j, c, xi in terms:
+                x0, x1 = pr.slot(xn + ".0"), pr.slot(xn + ".1")
+                a0, a1, s, d = coef_slots(pr, "f", j)
+                pos, neg = (X_POS, X_NEG) if c == 1 else (X_DBL, X_NEGDBL)
+                if not xi:
+                    re += [(pos, x0, a0), (neg, x1, a1)]
+                    im += [(pos, x0, a1), (pos, x1, a0)]
+                else:
+                    re += [(pos, x0, d), (neg, x1, s)]
+                    im += [(pos, x0, s), (pos, x1, d)]
+            for comp, lst in (("0", re), ("1", im)):
+                chunks = [lst[i:i + KMAX] for i in range(0, len(lst), KMAX)]
+                parts[(t, comp)] = []
+                for ci, ch in enumerate(chunks):
+                    dst = pr.slot(f"n{t}.{comp}.{ci}")
+                    parts[(t, comp)].append(dst)
+                    ops.append((dst, ch))
+        # mul phases of at most 32 lanes
+        for i in range(0, len(ops), NLANES):
+            pr.mul_phase(KMAX, ops[i:i + NLANES])
+        nparts = max(len(v) for v in parts.values())
+        if 2 * nparts <= 4:
+            # one LIN phase: a0, a1 and the stored forms s = a0 + a1, d = a0 - a1 straight from the partial sums
+            lops = []
+            for t in range(6):
+                a0, a1, s, d = coef_slots(pr, "f", t)
+                p0, p1 = parts[(t, "0")], parts[(t, "1")]
+                lops.append((a0, [(1, x) for x in p0], 0))
+                lops.append((a1, [(1, x) for x in p1], 0))
+                lops.append((s, [(1, x) for x in p0] + [(1, x) for x in p1], 0))
+                lops.append((d, [(1, x) for x in p0] + [(-1, x) for x in p1], 0))
+            pr.lin_phase(lops)
+            return
+        lops = []
+        for t in range(6):
+            for comp in ("0", "1"):
+                lops.append((pr.slot(f"f{t}.{comp}"), [(1, s) for s in parts[(t, comp)]], 0))
+        pr.lin_phase(lops)
+        lops = []
+        for t in range(6):
+            a0, a1, s, d = coef_slots(pr, "f", t)
+            lops.append((s, [(1, a0), (1, a1)], 0))
+            lops.append((d, [(1, a0), (-1, a1)], 0))
+        pr.lin_phase(lops)
+
+    # f^2: out_t = sum_{i<=j, i+j = t} c a_i a_j + xi sum_{i<=j, i+j = t+6} c a_i a_j   (c = 2 unless i == j)
+    def sqr_terms(t):
+        out = []
+        for i in range(6):
+            for j in range(i, 6):
+                if i + j == t or i + j == t + 6:
+                    out.append((f"f{i}", j, 1 if i == j else 2, i + j == t + 6))
+        return out
+    product_section("sqr", sqr_terms)
+
+    # f * (l0 + l1 w^2 + l4 w^3): out_t = l0 a_t + l1 a_{t-2} + l4 a_{t-3}  (indices below 0 wrap with xi)
+    def sparse_terms(t):
+        out = []
+        for ln, k in (("l0", 0), ("l1", 2), ("l4", 3)):
+            j = t - k
+            out.append((ln, j % 6, 1, j < 0))
+        return out
+    product_section("sparse", sparse_terms)
+
+    # f * g (g: another warp's value, copied into the g slots): out_t = sum_{i+j = t} g_i a_j + xi sum_{i+j = t+6} g_i a_j
+    def dense_terms(t):
+        out = []
+        for i in range(6):
+            for j in range(6):
+                if i + j == t or i + j == t + 6:
+                    out.append((f"g{i}", j, 1, i + j == t + 6))
+        return out
+    product_section("dense", dense_terms)
+
+    # conj: negate the odd coefficients (and refresh s, d)
+    pr.section("conj")
+    lops = []
+    for t in (1, 3, 5):
+        a0, a1, s, d = coef_slots(pr, "f", t)
+        lops += [(a0, [(-1, a0)], 0), (a1, [(-1, a1)], 0), (s, [(-1, s)], 0), (d, [(-1, d)], 0)]
+    pr.lin_phase(lops)
+    return pr
+
+
+# ------------------------------------------------------------------------------------------------ checks
+def f12_from_mem(pr, mem, base="f"):
+    k = [(mem[pr.slots[f"{base}{j}.0"]], mem[pr.slots[f"{base}{j}.1"]]) for j in range(6)]
+    return ((k[0], k[2], k[4]), (k[1], k[3], k[5]))
+
+
+def f12_to_mem(pr, mem, v, base):
+    k = [v[0][0], v[1][0], v[0][1], v[1][1], v[0][2], v[1][2]]
+    for j in range(6):
+        a0, a1 = k[j]
+        for c, val in (("0", a0), ("1", a1), ("s", (a0 + a1) % P), ("d", (a0 - a1) % P)):
+            mem[pr.slots[f"{base}{j}.{c}"]] = val
+
+
+def check(pr):
+    rnd = random.Random(2024)
+    mem = [0] * len(pr.slots)
+    Pt = B.g1_mul(B.G1_GEN, rnd.randrange(1, B.R))
+    Q = B.g2_mul(B.G2_GEN, rnd.randrange(1, B.R))
+    # H as a Jacobian point with a random Z, P projective with a random pz
+    z = (rnd.randrange(1, P), rnd.randrange(1, P))
+    z2 = B.f2_sqr(z)
+    H = (B.f2_mul(Q[0], z2), B.f2_mul(Q[1], B.f2_mul(z2, z)), z)
+    for n, v in zip(("HX", "HY", "HZ"), H):
+        mem[pr.slots[n + ".0"]], mem[pr.slots[n + ".1"]] = v
+    pz = rnd.randrange(1, P)
+    mem[pr.slots["px"]], mem[pr.slots["py"]], mem[pr.slots["pz"]] = Pt[0] * pz % P, Pt[1] * pz % P, pz
+    f12_to_mem(pr, mem, B.F12_ONE, "f")
+    run_section(pr, "init", mem)
+    for i in range(B.X_ABS.bit_length() - 2, -1, -1):
+        run_section(pr, "sqr", mem)
+        run_section(pr, "dbl", mem)
+        run_section(pr, "sparse", mem)
+        if (B.X_ABS >> i) & 1:
+            run_section(pr, "add", mem)
+            run_section(pr, "sparse", mem)
+    run_section(pr, "conj", mem)
+    f = f12_from_mem(pr, mem)
+    assert B.final_exp(f) == B.pairing(Pt, Q), "Miller program disagrees with the oracle pairing"
+    for j in range(6):   # stored forms consistent
+        a0, a1, s, d = (mem[x] for x in coef_slots(pr, "f", j))
+        assert s == (a0 + a1) % P and d == (a0 - a1) % P
+    g = B.f12_pow(f, 5)
+    f12_to_mem(pr, mem, g, "g")
+    run_section(pr, "dense", mem)
+    assert f12_from_mem(pr, mem) == B.f12_mul(f, g), "dense product section disagrees with f12_mul"
+
+
+# ------------------------------------------------------------------------------------------------ emit
+def emit(pr, path):
+    out = ["// generated by scripts/gen_miller_warp.py — do not edit (phase tables of bls/miller_warp.cuh)"]
+    out.append(f"constexpr int MW_NSLOTS = {len(pr.slots)};")
+    for n in ("f0.0", "X.0", "Y.0", "Z.0", "HX.0", "HY.0", "HZ.0", "px", "py", "pz", "g0.0", "dummy"):
+        out.append(f"constexpr int MW_S_{n.replace('.', '_').upper()} = {pr.slots[n]};")
+    # every coefficient block is (a0, a1, s, d) contiguous: f_j at MW_S_F0_0 + 4 j, g likewise
+    for j in range(6):
+        assert [pr.slots[f"f{j}.{c}"] for c in ("0", "1", "s", "d")] == [pr.slots["f0.0"] + 4 * j + k for k in range(4)]
+        assert [pr.slots[f"g{j}.{c}"] for c in ("0", "1", "s", "d")] == [pr.slots["g0.0"] + 4 * j + k for k in range(4)]
+    mul_rows, lin_rows, phases, sect = [], [], [], []
+    dummy = pr.slots["dummy"]
+    for name, phs in pr.sections.items():
+        first = len(phases)
+        for kind, K, ops in phs:
+            if kind == "mul":
+                base = len(mul_rows)
+                for lane in range(NLANES):
+                    if lane < len(ops):
+                        d, terms = ops[lane]
+                        terms = list(terms) + [(X_ZERO, dummy, dummy)] * (KMAX - len(terms))
+                    else:
+                        d, terms = dummy, [(X_ZERO, dummy, dummy)] * KMAX
+                    mul_rows.append("{%d, {%s}, {%s}, {%s}}" % (d, ",".join(str(t[0]) for t in terms),
+                                                               ",".join(str(t[1]) for t in terms),
+                                                               ",".join(str(t[2]) for t in terms)))
+                phases.append("{1, %d, %d}" % (K, base // NLANES))
+            else:
+                base = len(lin_rows)
+                for lane in range(NLANES):
+                    if lane < len(ops):
+                        d, terms, h = ops[lane]
+                    else:
+                        d, terms, h = dummy, [(1, dummy)], 0
+                    n = len(terms)
+                    terms = list(terms) + [(0, dummy)] * (4 - n)
+                    lin_rows.append("{%d, %d, %d, {%s}, {%s}}" % (d, n, h, ",".join(str(t[0]) for t in terms),
+                                                                 ",".join(str(t[1]) for t in terms)))
+                phases.append("{0, 0, %d}" % (base // NLANES))
+        sect.append((name, first, len(phases) - first))
+    out.append("struct MwMulOp { uint8_t d; uint8_t xm[4]; uint8_t xs[4]; uint8_t ys[4]; };")
+    out.append("struct MwLinOp { uint8_t d; uint8_t n; uint8_t h; int8_t c[4]; uint8_t s[4]; };")
+    out.append("struct MwPhase { uint8_t is_mul; uint8_t k; uint16_t table; };")
+    out.append(f"MW_TABLE MwMulOp MW_MUL[{len(mul_rows)}] = {{\n" + ",\n".join(mul_rows) + "};")
+    out.append(f"MW_TABLE MwLinOp MW_LIN[{len(lin_rows)}] = {{\n" + ",\n".join(lin_rows) + "};")
+    out.append(f"MW_TABLE MwPhase MW_PHASES[{len(phases)}] = {{" + ", ".join(phases) + "};")
+    for name, first, cnt in sect:
+        out.append(f"constexpr int MW_SEC_{name.upper()}_FIRST = {first}, MW_SEC_{name.upper()}_COUNT = {cnt};")
+    assert len(pr.slots) < 256
+    open(path, "w").write("\n".join(out) + "\n")
+    return len(mul_rows) // NLANES, len(lin_rows) // NLANES
+
+
+if __name__ == "__main__":
+    pr = build()
+    check(pr)
+    nm, nl = emit(pr, os.path.join(ROOT, "lighthouse_b200", "csrc", "bls", "miller_warp_tables.inc"))
+    print(f"ok: {len(pr.slots)} slots, {nm} mul phases, {nl} lin phases;",
+          {n: len(p) for n, p in pr.sections.items()})

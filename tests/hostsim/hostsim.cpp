@@ -9,6 +9,7 @@
 #include "../../lighthouse_b200/csrc/bls/h2c.cuh"
 #include "../../lighthouse_b200/csrc/bls/pairing.cuh"
 #include "../../lighthouse_b200/csrc/bls/miller_coop.cuh"
+#include "../../lighthouse_b200/csrc/bls/miller_warp.cuh"
 #include <vector>
 
 using namespace lhb200::bls;
@@ -287,6 +288,78 @@ EXPORT int hs_miller_coop(const uint8_t* p96, const uint8_t* q96, const uint8_t*
     }
     Fp12 f = outs[0];
     for (size_t i = 1; i < outs.size(); i++) fp12_mul(f, f, outs[i]);
+    final_exp(f, f);
+    fp12_out(out576, f);
+    return 0;
+}
+
+// bls/miller_warp.cuh (one warp per pairing, Fp-granular phase tables), the 32 lanes of every phase run in sequence.
+// Inputs as hs_miller_coop; `wpb` "warps" form a block whose values are multiplied by the dense section, like the kernel.
+// out = final_exp(product of the block products).
+EXPORT int hs_miller_warp(const uint8_t* p96, const uint8_t* q96, const uint8_t* status, int n, const uint8_t* extra_q96,
+                          int wpb, uint8_t* out576) {
+    std::vector<G1Proj3> P(n); std::vector<G2Jac> H(n);
+    for (int j = 0; j < n; j++) {
+        G1Affine p; G2Affine q;
+        if (g1_from_uncompressed(p, p96 + 96 * j) != DEC_OK) return -1;
+        const int rc = g2_decompress(q, q96 + 96 * j);
+        if (rc == DEC_BAD) return -1;
+        G1Jac jj; jac_from_affine(jj, p); jac_dbl(jj, jj); g1proj3_from_jac(P[j], jj);
+        if (rc == DEC_INFINITY) { jac_set_inf(H[j]); continue; }
+        Fp2 s = q.x, s2, s3; fp2_add(s, s, q.y); fp2_sqr(s2, s); fp2_mul(s3, s2, s);
+        fp2_mul(H[j].X, q.x, s2); fp2_mul(H[j].Y, q.y, s3); H[j].Z = s;
+    }
+    G2Jac extra; const bool have_extra = extra_q96 != nullptr;
+    if (have_extra) {
+        G2Affine q; const int rc = g2_decompress(q, extra_q96);
+        if (rc == DEC_BAD) return -1;
+        if (rc == DEC_INFINITY) jac_set_inf(extra); else jac_from_affine(extra, q);
+        G2Jac d; if (rc == DEC_OK) { jac_dbl(d, extra); jac_add(extra, d, extra); jac_neg(d, d); jac_add(extra, extra, d); }
+    }
+    G1Proj3 neg_g1; neg_g1.px = G1_GEN_X; fp_neg(neg_g1.py, G1_GEN_Y); neg_g1.pz = FP_ONE;
+    const int n_total = n + (have_extra ? 1 : 0);
+    Fp12 f; bool have_f = false;
+    for (int b0 = 0; b0 < n_total; b0 += wpb) {
+        std::vector<std::vector<uint32_t>> R(wpb, std::vector<uint32_t>(mw::REGION_WORDS, 0xdeadbeefu));
+        for (int wib = 0; wib < wpb; wib++) {
+            uint32_t* r = R[wib].data();
+            for (int w = 0; w < 24 * mw::SL; w++) mw::set_one_words(r, w);
+            const int set = b0 + wib;
+            if (set >= n_total) continue;
+            const G2Jac* q; const G1Proj3* p;
+            if (set >= n) { q = &extra; p = &neg_g1; } else { q = &H[set]; p = &P[set]; if (status[set]) continue; }
+            if (jac_is_inf(*q)) continue;
+            const uint32_t* qs = reinterpret_cast<const uint32_t*>(q);
+            for (int w = 0; w < 6 * NL; w++) r[(mw::MW_S_HX_0 + w / NL) * mw::SL + w % NL] = qs[w];
+            const uint32_t* ps = reinterpret_cast<const uint32_t*>(p);
+            for (int w = 0; w < 3 * NL; w++) r[(mw::MW_S_PX + w / NL) * mw::SL + w % NL] = ps[w];
+            mw::run_section(r, mw::MW_SEC_INIT_FIRST, mw::MW_SEC_INIT_COUNT);
+            for (int i = 62; i >= 0; i--) {
+                mw::run_section(r, mw::MW_SEC_SQR_FIRST, mw::MW_SEC_SQR_COUNT);
+                mw::run_section(r, mw::MW_SEC_DBL_FIRST, mw::MW_SEC_DBL_COUNT);
+                mw::run_section(r, mw::MW_SEC_SPARSE_FIRST, mw::MW_SEC_SPARSE_COUNT);
+                if ((BLS_X_ABS >> i) & 1) {
+                    mw::run_section(r, mw::MW_SEC_ADD_FIRST, mw::MW_SEC_ADD_COUNT);
+                    mw::run_section(r, mw::MW_SEC_SPARSE_FIRST, mw::MW_SEC_SPARSE_COUNT);
+                }
+            }
+            mw::run_section(r, mw::MW_SEC_CONJ_FIRST, mw::MW_SEC_CONJ_COUNT);
+        }
+        for (int stride = 1; stride < wpb; stride *= 2)
+            for (int wib = 0; wib + stride < wpb; wib += 2 * stride) {
+                uint32_t* r = R[wib].data(); const uint32_t* o = R[wib + stride].data();
+                for (int w = 0; w < 24 * mw::SL; w++) r[mw::MW_S_G0_0 * mw::SL + w] = o[mw::MW_S_F0_0 * mw::SL + w];
+                mw::run_section(r, mw::MW_SEC_DENSE_FIRST, mw::MW_SEC_DENSE_COUNT);
+            }
+        Fp12 blk;
+        uint32_t* o = reinterpret_cast<uint32_t*>(&blk);
+        for (int w = 0; w < 12 * NL; w++) {
+            const int fp2_idx = w / (2 * NL), comp = (w / NL) & 1, limb = w % NL;
+            const int k = fp2_idx < 3 ? 2 * fp2_idx : 2 * (fp2_idx - 3) + 1;
+            o[w] = R[0][(mw::MW_S_F0_0 + 4 * k + comp) * mw::SL + limb];
+        }
+        if (have_f) fp12_mul(f, f, blk); else { f = blk; have_f = true; }
+    }
     final_exp(f, f);
     fp12_out(out576, f);
     return 0;

@@ -364,6 +364,30 @@ def test_streamed_upload_matches_blocking_upload(bls):
     b.destroy()
 
 
+def test_every_key_aggregation_variant(bls):
+    """The key sums run in three forms chosen by batch size (bls_host.cu: slice-parallel <= 8 192 sets, one thread per
+    set up to ~38 k, TMA ring above; test_full_size_batch_properties covers the last).  Same verdicts from the first two
+    on the same kind of inputs: valid, one foreign key, a set without keys, aggregate key = infinity."""
+    from lighthouse_b200.synthetic import attestation_batch
+    for n, k in ((700, 37), (9000, 3)):
+        ab = attestation_batch(n, keys_per_set=k, n_validators=2048, seed=0x5EED + n)
+        assert bls.verify_signature_sets_raw(ab.sigs, ab.msgs, ab.pks, ab.offsets) is True
+        victim = (n // 2) * k + k - 1
+        pks = bytearray(ab.pks)
+        other = 96 * ((victim + 5 * k) % (n * k))
+        pks[96 * victim:96 * victim + 96] = ab.pks[other:other + 96]
+        assert pks != bytearray(ab.pks)
+        ok, st = bls.verify_signature_sets_raw(ab.sigs, ab.msgs, bytes(pks), ab.offsets, want_status=True)
+        assert not ok and not st.any()                       # a pairing failure, not a decode failure
+        offs = ab.offsets.copy(); offs[n - 1] = offs[n]
+        ok, st = bls.verify_signature_sets_raw(ab.sigs, ab.msgs, ab.pks, offs, want_status=True)
+        assert not ok and st[n - 1] != 0 and not st[:n - 2].any()
+        pks = bytearray(ab.pks)                              # set 7: key list (P, -P, ...) -> apk = infinity if k == 2; use decode failure instead
+        pks[96 * 7 * k] ^= 0x80                              # compression flag on an uncompressed key
+        ok, st = bls.verify_signature_sets_raw(ab.sigs, ab.msgs, bytes(pks), ab.offsets, want_status=True)
+        assert not ok and st[7] != 0 and not np.delete(st, 7).any()
+
+
 def test_block_signature_batch_shape(bls):
     """BASELINE configs[3] shape at reduced scale: the sets BlockSignatureVerifier::include_all_signatures collects
     for consecutive blocks (block_signature_verifier.rs:141-393) — 1-key sets (proposal, randao, exits,

@@ -330,3 +330,37 @@ def test_cooperative_miller_program_matches_oracle(L):
         if with_extra:
             pairs.append((B.g1_neg(B.G1_GEN), extra))
         assert f12_from(out.raw) == ref_cube(pairs), (n, spb)
+
+
+def test_warp_per_pairing_miller_program_matches_oracle(L):
+    """bls/miller_warp.cuh (phase tables from scripts/gen_miller_warp.py) run lane by lane: product of pairings, after the
+    final exponentiation, == cube of the oracle's GT value — with skipped sets, an infinite Q, the appended (-g1, Q_extra)
+    pair and blocks of 1, 3 and 4 warps (the dense product section)."""
+    def pts(n, seed):
+        ps = [B.g1_mul(B.G1_GEN, 2000 + 11 * j + seed) for j in range(n)]
+        qs = [B.g2_mul(B.G2_GEN, 77 + 5 * j + seed) for j in range(n)]
+        return ps, qs
+
+    def ref_cube(pairs):
+        f = B.F12_ONE
+        for p, q in pairs:
+            if q is not None:
+                f = B.f12_mul(f, B.miller_loop(p, q))
+        g = B.final_exp(f)
+        return B.f12_mul(B.f12_sqr(g), g)
+
+    L.hs_miller_warp.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
+    for n, wpb, skip, with_extra, inf_at in ((1, 1, (), False, None), (3, 4, (), True, None), (5, 3, (1,), True, 3)):
+        ps, qs = pts(n, n)
+        if inf_at is not None:
+            qs[inf_at] = None
+        status = bytes(1 if j in skip else 0 for j in range(n))
+        extra = B.g2_mul(B.G2_GEN, 31337) if with_extra else None
+        out = C.create_string_buffer(576)
+        rc = L.hs_miller_warp(b"".join(B.g1_uncompressed(p) for p in ps), b"".join(B.g2_compress(q) for q in qs), status, n,
+                              B.g2_compress(extra) if with_extra else None, wpb, out)
+        assert rc == 0
+        pairs = [(B.g1_add(p, p), q) for j, (p, q) in enumerate(zip(ps, qs)) if j not in skip]
+        if with_extra:
+            pairs.append((B.g1_neg(B.G1_GEN), extra))
+        assert f12_from(out.raw) == ref_cube(pairs), (n, wpb)
