@@ -43,6 +43,12 @@ __device__ __forceinline__ void load_bytes16(uint8_t* dst, const uint8_t* src, i
     }
 }
 
+}  // namespace bls
+}  // namespace lhb200
+#include "g2_warp.cuh"   // latency-mode twins of the two kernels below (one warp per signature / message)
+namespace lhb200 {
+namespace bls {
+
 __global__ void __launch_bounds__(BLS_BLOCK) k_sig_prepare(const uint8_t* __restrict__ sigs,
                                                             const uint64_t* __restrict__ rands, uint32_t n,
                                                             G2Jac* __restrict__ sig_r, uint8_t* __restrict__ status,

@@ -92,41 +92,55 @@ LHB_HD LHB_INLINE void lin_lane(Fp& r, const uint32_t* R, const MwLinOp& op) {
     r = acc;
 }
 
+// the three tables of a program (this file: the Miller program; g2_warp.cuh: the G2 ladders)
+struct Tables {
+    const MwPhase* ph;
+    const MwMulOp* mul;
+    const MwLinOp* lin;
+};
+
 // one lane's value of phase ph (reads only)
-LHB_HD LHB_INLINE int phase_compute(Fp& r, const uint32_t* R, int lane, int ph) {
-    const MwPhase P = MW_PHASES[ph];
+LHB_HD LHB_INLINE int phase_compute(Fp& r, const uint32_t* R, int lane, int ph, const Tables& T) {
+    const MwPhase P = T.ph[ph];
     if (P.is_mul) {
-        const MwMulOp& op = MW_MUL[(int)P.table * 32 + lane];
+        const MwMulOp& op = T.mul[(int)P.table * 32 + lane];
         if (P.k == 2) mul_lane<2>(r, R, op);                  // the tables use K = 2 (point steps) and K = 4 (products)
         else mul_lane<4>(r, R, op);
         return op.d;
     }
-    const MwLinOp& op = MW_LIN[(int)P.table * 32 + lane];
+    const MwLinOp& op = T.lin[(int)P.table * 32 + lane];
     lin_lane(r, R, op);
     return op.d;
 }
 
 #ifdef LHB_HOSTSIM
 // the CPU runs the 32 lanes of a phase one after the other: all reads first, then all writes
-inline void run_section(uint32_t* R, int first, int count) {
+inline void run_section(uint32_t* R, int first, int count, const Tables& T) {
     for (int ph = first; ph < first + count; ph++) {
         Fp r[32];
         int d[32];
-        for (int lane = 0; lane < 32; lane++) d[lane] = phase_compute(r[lane], R, lane, ph);
+        for (int lane = 0; lane < 32; lane++) d[lane] = phase_compute(r[lane], R, lane, ph, T);
         for (int lane = 0; lane < 32; lane++) st(R, d[lane], r[lane]);
     }
 }
 #else
-__device__ __noinline__ void run_section(uint32_t* R, int lane, int first, int count) {   // ONE copy of the interpreter
+__device__ __noinline__ void run_section(uint32_t* R, int lane, int first, int count, Tables T) {   // ONE copy of the interpreter
 #pragma unroll 1
     for (int ph = first; ph < first + count; ph++) {
         Fp r;
-        const int d = phase_compute(r, R, lane, ph);
+        const int d = phase_compute(r, R, lane, ph, T);
         __syncwarp();
         st(R, d, r);
         __syncwarp();
     }
 }
+#endif
+
+LHB_HD LHB_INLINE Tables miller_tables() { return Tables{MW_PHASES, MW_MUL, MW_LIN}; }
+#ifdef LHB_HOSTSIM
+#define MW_RUN(R, lane, SEC) run_section(R, MW_SEC_##SEC##_FIRST, MW_SEC_##SEC##_COUNT, T)
+#else
+#define MW_RUN(R, lane, SEC) run_section(R, lane, MW_SEC_##SEC##_FIRST, MW_SEC_##SEC##_COUNT, T)
 #endif
 
 // f = 1 in the stored form (a0, a1, s, d) of every coefficient
@@ -148,6 +162,7 @@ __global__ void __launch_bounds__(256, 1) k_miller_warp(const G1Proj3* __restric
                                                         Fp12* __restrict__ out_f) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     uint32_t* R = lhb_dyn_smem + (size_t)wib * REGION_WORDS;
+    const Tables T = miller_tables();
     const uint32_t n_total = n + (extra_q ? 1u : 0u);
     const uint32_t set = blockIdx.x * nw + wib;
     for (int w = lane; w < 24 * SL; w += 32) set_one_words(R, w);
@@ -165,18 +180,18 @@ __global__ void __launch_bounds__(256, 1) k_miller_warp(const G1Proj3* __restric
         const uint32_t* ps = reinterpret_cast<const uint32_t*>(p);     // px py pz
         for (int w = lane; w < 3 * NL; w += 32) R[(MW_S_PX + w / NL) * SL + w % NL] = ps[w];
         __syncwarp();
-        run_section(R, lane, MW_SEC_INIT_FIRST, MW_SEC_INIT_COUNT);
+        MW_RUN(R, lane, INIT);
 #pragma unroll 1
         for (int i = 62; i >= 0; i--) {
-            run_section(R, lane, MW_SEC_SQR_FIRST, MW_SEC_SQR_COUNT);
-            run_section(R, lane, MW_SEC_DBL_FIRST, MW_SEC_DBL_COUNT);
-            run_section(R, lane, MW_SEC_SPARSE_FIRST, MW_SEC_SPARSE_COUNT);
+            MW_RUN(R, lane, SQR);
+            MW_RUN(R, lane, DBL);
+            MW_RUN(R, lane, SPARSE);
             if ((BLS_X_ABS >> i) & 1) {
-                run_section(R, lane, MW_SEC_ADD_FIRST, MW_SEC_ADD_COUNT);
-                run_section(R, lane, MW_SEC_SPARSE_FIRST, MW_SEC_SPARSE_COUNT);
+                MW_RUN(R, lane, ADD);
+                MW_RUN(R, lane, SPARSE);
             }
         }
-        run_section(R, lane, MW_SEC_CONJ_FIRST, MW_SEC_CONJ_COUNT);
+        MW_RUN(R, lane, CONJ);
     }
     // product over the block's warps
     for (int stride = 1; stride < nw; stride *= 2) {
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(256, 1) k_miller_warp(const G1Proj3* __restric
             const uint32_t* O = R + (size_t)stride * REGION_WORDS;
             for (int w = lane; w < 24 * SL; w += 32) R[MW_S_G0_0 * SL + w] = O[MW_S_F0_0 * SL + w];
             __syncwarp();
-            run_section(R, lane, MW_SEC_DENSE_FIRST, MW_SEC_DENSE_COUNT);
+            MW_RUN(R, lane, DENSE);
         }
     }
     if (wib == 0) {

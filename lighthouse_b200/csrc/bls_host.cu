@@ -554,7 +554,17 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaEventRecord(b->e_fork, s));
     LHB_CUDA(cudaStreamWaitEvent(b->s2, b->e_fork, 0));
     LHB_CUDA(cudaStreamWaitEvent(b->s3, b->e_fork, 0));
-    k_sig_prepare<<<grid, BLS_BLOCK, 0, b->s2>>>(b->in_sigs, b->in_rands, n, b->d_sigr, b->d_status, b->d_fail);
+    // latency mode of the two G2 stages (bls/g2_warp.cuh): one warp per signature / message while the batch is small
+    // enough for every warp to have a scheduler of its own (four per block, n / 4 blocks <= SMs)
+    static const int g2_warp_env = [] { const char* e = getenv("LHB_G2_WARP"); return e ? atoi(e) : 1; }();
+    const bool g2_warp = g2_warp_env && n <= 4u * (uint32_t)n_sm;
+    constexpr uint32_t GW_WPB = 4;
+    const size_t gw_smem = (size_t)GW_WPB * gw::REGION_WORDS * 4;
+    if (g2_warp)
+        gw::k_sig_prepare_warp<<<cdiv(n, GW_WPB), 32 * GW_WPB, gw_smem, b->s2>>>(b->in_sigs, b->in_rands, n, b->d_sigr,
+                                                                               b->d_status, b->d_fail);
+    else
+        k_sig_prepare<<<grid, BLS_BLOCK, 0, b->s2>>>(b->in_sigs, b->in_rands, n, b->d_sigr, b->d_status, b->d_fail);
     launches++;
     LHB_CUDA(cudaEventRecord(b->e_sig, b->s2));
     {
@@ -577,7 +587,9 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         }
         LHB_CUDA(cudaEventRecord(b->e_join, b->s2));
     }
-    if (n <= HASH_PAIR_MAX_SETS)   // latency mode: two threads per message (one SSWU map each)
+    if (g2_warp)
+        gw::k_hash_to_g2_warp<<<cdiv(n, GW_WPB), 32 * GW_WPB, gw_smem, b->s3>>>(b->in_msgs, n, b->d_h);
+    else if (n <= HASH_PAIR_MAX_SETS)   // latency mode: two threads per message (one SSWU map each)
         k_hash_to_g2_pair<<<cdiv(2 * n, BLS_BLOCK), BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);
     else
         k_hash_to_g2<<<grid, BLS_BLOCK, 0, b->s3>>>(b->in_msgs, n, b->d_h);

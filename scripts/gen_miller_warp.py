@@ -337,16 +337,218 @@ def check(pr):
     assert f12_from_mem(pr, mem) == B.f12_mul(f, g), "dense product section disagrees with f12_mul"
 
 
+
+# ================================================================================================ G2 programs
+# Homogeneous projective points (X : Y : Z) on E2: y^2 = x^3 + 4 xi.  Accumulators A (and A2), base Bp; the same
+# doubling (Costello-Lange-Naehrig) and addition (add-1998-cmo-2) formulas as the Miller sections, without the lines.
+def g2_dbl_stages(b, pts):
+    """T <- 2 T for every point name in pts, all in the same phases (temporaries are suffixed with the point name)"""
+    for T in pts:
+        b.lin(f"s1{T}", [(1, f"{T}X"), (1, f"{T}Y")]); b.lin(f"s2{T}", [(1, f"{T}Y"), (1, f"{T}Z")])
+    b.flush_lin()
+    for T in pts:
+        b.sqr(f"XX{T}", f"{T}X"); b.sqr(f"B{T}", f"{T}Y"); b.sqr(f"C{T}", f"{T}Z"); b.sqr(f"S2{T}", f"s2{T}")
+        b.sqr(f"S1{T}", f"s1{T}")
+    b.flush_mul()
+    for T in pts:
+        b.lin_xi(f"E{T}", f"C{T}", 12)
+        b.lin(f"H{T}", [(1, f"S2{T}"), (-1, f"B{T}"), (-1, f"C{T}")])
+        b.lin(f"Ah{T}", [(1, f"S1{T}"), (-1, f"XX{T}"), (-1, f"B{T}")], h=2)
+    b.flush_lin()
+    for T in pts:
+        b.lin(f"BmF{T}", [(1, f"B{T}"), (-3, f"E{T}")]); b.lin(f"G{T}", [(1, f"B{T}"), (3, f"E{T}")], h=1)
+    b.flush_lin()
+    for T in pts:
+        b.mul(f"{T}X", f"Ah{T}", f"BmF{T}"); b.mul(f"{T}Z", f"B{T}", f"H{T}"); b.sqr(f"GG{T}", f"G{T}")
+        b.sqr(f"EE{T}", f"E{T}")
+    b.flush_mul()
+    for T in pts:
+        b.lin(f"{T}Y", [(1, f"GG{T}"), (-3, f"EE{T}")])
+    b.flush_lin()
+
+
+def g2_add_stages(b, T, Q):
+    """T <- T + Q (both projective; T != +-Q, neither at infinity: see the callers)"""
+    b.mul("d", f"{T}Y", f"{Q}Z"); b.mul("e", f"{T}X", f"{Q}Z"); b.mul("ff", f"{T}Z", f"{Q}Z")
+    b.mul("y2z1", f"{Q}Y", f"{T}Z"); b.mul("x2z1", f"{Q}X", f"{T}Z"); b.flush_mul()
+    b.lin("u", [(1, "y2z1"), (-1, "d")]); b.lin("v", [(1, "x2z1"), (-1, "e")]); b.flush_lin()
+    b.sqr("vv", "v"); b.sqr("uu", "u"); b.flush_mul()
+    b.mul("vvv", "v", "vv"); b.mul("R", "vv", "e"); b.mul("uuz", "uu", "ff"); b.flush_mul()
+    b.lin("Aa", [(1, "uuz"), (-1, "vvv"), (-2, "R")]); b.flush_lin()
+    b.lin("RmA", [(1, "R"), (-1, "Aa")]); b.flush_lin()
+    b.mul(f"{T}Z", "vvv", "ff"); b.mul("dY", "vvv", "d"); b.mul(f"{T}X", "v", "Aa"); b.mul("uRA", "u", "RmA"); b.flush_mul()
+    b.lin(f"{T}Y", [(1, "uRA"), (-1, "dY")]); b.flush_lin()
+
+
+def g2_copy(b, D, S, neg=False):
+    b.lin(f"{D}X", [(1, f"{S}X")]); b.lin(f"{D}Y", [(-1 if neg else 1, f"{S}Y")]); b.lin(f"{D}Z", [(1, f"{S}Z")])
+
+
+def g2_psi(b, D, S):
+    """D <- psi(S) = (conj(X) CX : conj(Y) CY : conj(Z)); one MUL phase + one LIN phase (caller flushes)"""
+    for c, k in (("X", "CX"), ("Y", "CY")):
+        d, a, kk = b.s2(f"{D}{c}"), b.s2(f"{S}{c}"), b.s2(k)
+        b.mops.append((d[0], [(X_POS, a[0], kk[0]), (X_POS, a[1], kk[1])]))      # (a0 - a1 i)(k0 + k1 i)
+        b.mops.append((d[1], [(X_POS, a[0], kk[1]), (X_NEG, a[1], kk[0])]))
+    dz, az = b.s2(f"{D}Z"), b.s2(f"{S}Z")
+    b.lops.append((dz[0], [(1, az[0])], 0)); b.lops.append((dz[1], [(-1, az[1])], 0))
+
+
+def build_g2():
+    pr = Prog()
+    for n in ("AX", "AY", "AZ", "A2X", "A2Y", "A2Z", "BpX", "BpY", "BpZ", "HX", "HY", "HZ", "CX", "CY", "JX", "JY", "JZ"):
+        pr.slot(n + ".0"); pr.slot(n + ".1")
+    for n in ("c2x", "e1.0", "e1.1", "e2.0", "e2.1", "dummy"):
+        pr.slot(n)
+    b = B2(pr)
+    # ---- shared by both kernels
+    pr.section("setA"); g2_copy(b, "A", "Bp"); b.flush_lin()
+    pr.section("setA2"); g2_copy(b, "A2", "Bp"); b.flush_lin()
+    pr.section("dblA"); g2_dbl_stages(b, ["A"])
+    pr.section("dblAA2"); g2_dbl_stages(b, ["A", "A2"])
+    pr.section("addA"); g2_add_stages(b, "A", "Bp")
+    pr.section("addA2"); g2_add_stages(b, "A2", "Bp")
+    # A (projective) -> Jacobian (X Z, Y Z^2, Z) in J
+    pr.section("tojac")
+    b.mul("JX", "AX", "AZ"); b.sqr("zz", "AZ"); b.flush_mul()
+    b.mul("JY", "AY", "zz"); b.flush_mul()
+    b.lin("JZ", [(1, "AZ")]); b.flush_lin()
+    # ---- signatures: Bp = (x, y, 1) affine sigma; A = [r] sigma, A2 = [|x|] sigma.
+    # in G2  <=>  psi(sigma) == [x] sigma = -A2:  e1 = psi_x Z2 - X2 = 0 and e2 = psi_y Z2 + Y2 = 0 (and Z2 != 0)
+    pr.section("sigcheck")
+    g2_psi(b, "Ps", "Bp"); b.flush_mul(); b.flush_lin()
+    b.mul("t1", "PsX", "A2Z"); b.mul("t2", "PsY", "A2Z"); b.flush_mul()
+    b.lin("e1", [(1, "t1"), (-1, "A2X")]); b.lin("e2", [(1, "t2"), (1, "A2Y")]); b.flush_lin()
+    # ---- hash_to_curve: clear_cofactor (Budroni-Pintore, RFC 9380 G.3), as g2_clear_cofactor in ec.cuh
+    # input H Jacobian -> P0 projective (X Z, Y, Z^3)
+    pr.section("hinit")
+    b.mul("P0X", "HX", "HZ"); b.sqr("zz", "HZ"); b.flush_mul()
+    b.mul("P0Z", "zz", "HZ"); b.flush_mul()
+    b.lin("P0Y", [(1, "HY")]); b.flush_lin()
+    g2_copy(b, "Bp", "P0"); g2_copy(b, "A", "P0"); b.flush_lin()
+    # after ladder 1 (A = [|x|] P0):  T1 = -A = [x] P0;  T2 = psi(P0);  A = P0 (to be doubled)
+    pr.section("hmid1")
+    g2_copy(b, "T1", "A", neg=True); g2_psi(b, "T2", "P0"); b.flush_mul(); b.flush_lin()
+    g2_copy(b, "A", "P0"); b.flush_lin()
+    # (dblA) then A = psi^2(2 P0) = (X c2x : -Y : Z);  Bp = -T2
+    pr.section("hmid2")
+    b.mul_fp("AX", "AX", "c2x"); b.flush_mul()
+    b.lin("AY", [(-1, "AY")]); g2_copy(b, "Bp", "T2", neg=True); b.flush_lin()
+    # (addA: A = t3 = psi^2(2P) - psi(P))  T3 = A;  A = T2;  Bp = T1
+    pr.section("hmid3")
+    g2_copy(b, "T3", "A"); g2_copy(b, "Bp", "T1"); b.flush_lin()
+    g2_copy(b, "A", "T2"); b.flush_lin()
+    # (addA: A = t1 + t2)  Bp = A  (base of ladder 2; A stays the accumulator start)
+    pr.section("hmid4")
+    g2_copy(b, "Bp", "A"); b.flush_lin()
+    # (ladder 2: A = [|x|](t1 + t2))  A = -A;  Bp = T3
+    pr.section("hmid5")
+    b.lin("AY", [(-1, "AY")]); g2_copy(b, "Bp", "T3"); b.flush_lin()
+    # (addA)  Bp = -T1
+    pr.section("hmid6")
+    g2_copy(b, "Bp", "T1", neg=True); b.flush_lin()
+    # (addA)  Bp = -P0
+    pr.section("hmid7")
+    g2_copy(b, "Bp", "P0", neg=True); b.flush_lin()
+    # (addA) (tojac)
+    return pr
+
+
+def g2_set_point(pr, mem, name, pt, z=None):
+    """store an affine oracle point projectively (x z : y z : z)"""
+    z = z or (1, 0)
+    for c, v in (("X", B.f2_mul(pt[0], z)), ("Y", B.f2_mul(pt[1], z)), ("Z", z)):
+        mem[pr.slots[f"{name}{c}.0"]], mem[pr.slots[f"{name}{c}.1"]] = v
+
+
+def g2_get_affine(pr, mem, name):
+    X, Y, Z = [(mem[pr.slots[f"{name}{c}.0"]], mem[pr.slots[f"{name}{c}.1"]]) for c in "XYZ"]
+    if Z == (0, 0):
+        return None
+    zi = B.f2_inv(Z)
+    return (B.f2_mul(X, zi), B.f2_mul(Y, zi))
+
+
+def g2_get_jac_affine(pr, mem):
+    X, Y, Z = [(mem[pr.slots[f"J{c}.0"]], mem[pr.slots[f"J{c}.1"]]) for c in "XYZ"]
+    zi = B.f2_inv(Z); zi2 = B.f2_sqr(zi)
+    return (B.f2_mul(X, zi2), B.f2_mul(Y, B.f2_mul(zi2, zi)))
+
+
+def g2_consts(pr, mem):
+    mem[pr.slots["CX.0"]], mem[pr.slots["CX.1"]] = B.PSI_CX
+    mem[pr.slots["CY.0"]], mem[pr.slots["CY.1"]] = B.PSI_CY
+    cx2 = B.f2_mul(B.f2_conj(B.PSI_CX), B.PSI_CX)
+    assert cx2[1] == 0
+    mem[pr.slots["c2x"]] = cx2[0]
+
+
+def ladder(pr, mem, k, two=False, k2=0):
+    """A = [k] Bp (and A2 = [k2] Bp), left to right, exactly the control flow of the kernels"""
+    started = started2 = False
+    for i in range(63, -1, -1):
+        if started or started2:
+            run_section(pr, "dblAA2" if two else "dblA", mem)
+        if (k >> i) & 1:
+            run_section(pr, "addA" if started else "setA", mem); started = True
+        if two and (k2 >> i) & 1:
+            run_section(pr, "addA2" if started2 else "setA2", mem); started2 = True
+
+
+def check_g2(pr):
+    rnd = random.Random(77)
+    mem = [0] * len(pr.slots)
+    g2_consts(pr, mem)
+    # ---- signature program
+    sig = B.g2_mul(B.G2_GEN, rnd.randrange(1, B.R))
+    r = rnd.randrange(1, 1 << 64)
+    g2_set_point(pr, mem, "Bp", sig)
+    ladder(pr, mem, r, True, B.X_ABS)
+    assert g2_get_affine(pr, mem, "A") == B.g2_mul(sig, r)
+    assert g2_get_affine(pr, mem, "A2") == B.g2_mul(sig, B.X_ABS)
+    run_section(pr, "sigcheck", mem)
+    assert all(mem[pr.slots[n]] == 0 for n in ("e1.0", "e1.1", "e2.0", "e2.1")), "a G2 point failed the subgroup check"
+    run_section(pr, "tojac", mem)
+    assert g2_get_jac_affine(pr, mem) == B.g2_mul(sig, r)
+    # a curve point outside G2 must fail it
+    x = (5, 1)
+    while True:
+        y = B.f2_sqrt(B.f2_add(B.f2_mul(B.f2_sqr(x), x), B.B2))
+        if y and not B.g2_in_subgroup((x, y)):
+            break
+        x = (x[0] + 1, 1)
+    g2_set_point(pr, mem, "Bp", (x, y))
+    ladder(pr, mem, 3, True, B.X_ABS)
+    run_section(pr, "sigcheck", mem)
+    assert any(mem[pr.slots[n]] != 0 for n in ("e1.0", "e1.1", "e2.0", "e2.1"))
+    # ---- clear_cofactor program on a curve point outside G2 given in Jacobian form
+    z = (rnd.randrange(1, P), rnd.randrange(1, P)); z2 = B.f2_sqr(z)
+    Hj = (B.f2_mul(x, z2), B.f2_mul(y, B.f2_mul(z2, z)), z)
+    for n, v in zip(("HX", "HY", "HZ"), Hj):
+        mem[pr.slots[n + ".0"]], mem[pr.slots[n + ".1"]] = v
+    run_section(pr, "hinit", mem)
+    ladder(pr, mem, B.X_ABS)
+    run_section(pr, "hmid1", mem); run_section(pr, "dblA", mem); run_section(pr, "hmid2", mem)
+    run_section(pr, "addA", mem); run_section(pr, "hmid3", mem); run_section(pr, "addA", mem)
+    run_section(pr, "hmid4", mem)
+    ladder(pr, mem, B.X_ABS)
+    run_section(pr, "hmid5", mem); run_section(pr, "addA", mem); run_section(pr, "hmid6", mem)
+    run_section(pr, "addA", mem); run_section(pr, "hmid7", mem); run_section(pr, "addA", mem)
+    run_section(pr, "tojac", mem)
+    assert g2_get_jac_affine(pr, mem) == B.g2_mul((x, y), B.H_EFF), "clear_cofactor program disagrees with [h_eff]P"
+
+
 # ------------------------------------------------------------------------------------------------ emit
-def emit(pr, path):
+def emit(pr, path, PX="MW", exported=("f0.0", "X.0", "Y.0", "Z.0", "HX.0", "HY.0", "HZ.0", "px", "py", "pz", "g0.0", "dummy"),
+         structs=True):
     out = ["// generated by scripts/gen_miller_warp.py — do not edit (phase tables of bls/miller_warp.cuh)"]
-    out.append(f"constexpr int MW_NSLOTS = {len(pr.slots)};")
-    for n in ("f0.0", "X.0", "Y.0", "Z.0", "HX.0", "HY.0", "HZ.0", "px", "py", "pz", "g0.0", "dummy"):
-        out.append(f"constexpr int MW_S_{n.replace('.', '_').upper()} = {pr.slots[n]};")
-    # every coefficient block is (a0, a1, s, d) contiguous: f_j at MW_S_F0_0 + 4 j, g likewise
-    for j in range(6):
-        assert [pr.slots[f"f{j}.{c}"] for c in ("0", "1", "s", "d")] == [pr.slots["f0.0"] + 4 * j + k for k in range(4)]
-        assert [pr.slots[f"g{j}.{c}"] for c in ("0", "1", "s", "d")] == [pr.slots["g0.0"] + 4 * j + k for k in range(4)]
+    out.append(f"constexpr int {PX}_NSLOTS = {len(pr.slots)};")
+    for n in exported:
+        out.append(f"constexpr int {PX}_S_{n.replace('.', '_').upper()} = {pr.slots[n]};")
+    if PX == "MW":   # every coefficient block is (a0, a1, s, d) contiguous: f_j at MW_S_F0_0 + 4 j, g likewise
+        for j in range(6):
+            assert [pr.slots[f"f{j}.{c}"] for c in ("0", "1", "s", "d")] == [pr.slots["f0.0"] + 4 * j + k for k in range(4)]
+            assert [pr.slots[f"g{j}.{c}"] for c in ("0", "1", "s", "d")] == [pr.slots["g0.0"] + 4 * j + k for k in range(4)]
     mul_rows, lin_rows, phases, sect = [], [], [], []
     dummy = pr.slots["dummy"]
     for name, phs in pr.sections.items():
@@ -377,14 +579,15 @@ def emit(pr, path):
                                                                  ",".join(str(t[1]) for t in terms)))
                 phases.append("{0, 0, %d}" % (base // NLANES))
         sect.append((name, first, len(phases) - first))
-    out.append("struct MwMulOp { uint8_t d; uint8_t xm[4]; uint8_t xs[4]; uint8_t ys[4]; };")
-    out.append("struct MwLinOp { uint8_t d; uint8_t n; uint8_t h; int8_t c[4]; uint8_t s[4]; };")
-    out.append("struct MwPhase { uint8_t is_mul; uint8_t k; uint16_t table; };")
-    out.append(f"MW_TABLE MwMulOp MW_MUL[{len(mul_rows)}] = {{\n" + ",\n".join(mul_rows) + "};")
-    out.append(f"MW_TABLE MwLinOp MW_LIN[{len(lin_rows)}] = {{\n" + ",\n".join(lin_rows) + "};")
-    out.append(f"MW_TABLE MwPhase MW_PHASES[{len(phases)}] = {{" + ", ".join(phases) + "};")
+    if structs:
+        out.append("struct MwMulOp { uint8_t d; uint8_t xm[4]; uint8_t xs[4]; uint8_t ys[4]; };")
+        out.append("struct MwLinOp { uint8_t d; uint8_t n; uint8_t h; int8_t c[4]; uint8_t s[4]; };")
+        out.append("struct MwPhase { uint8_t is_mul; uint8_t k; uint16_t table; };")
+    out.append(f"MW_TABLE MwMulOp {PX}_MUL[{len(mul_rows)}] = {{\n" + ",\n".join(mul_rows) + "};")
+    out.append(f"MW_TABLE MwLinOp {PX}_LIN[{len(lin_rows)}] = {{\n" + ",\n".join(lin_rows) + "};")
+    out.append(f"MW_TABLE MwPhase {PX}_PHASES[{len(phases)}] = {{" + ", ".join(phases) + "};")
     for name, first, cnt in sect:
-        out.append(f"constexpr int MW_SEC_{name.upper()}_FIRST = {first}, MW_SEC_{name.upper()}_COUNT = {cnt};")
+        out.append(f"constexpr int {PX}_SEC_{name.upper()}_FIRST = {first}, {PX}_SEC_{name.upper()}_COUNT = {cnt};")
     assert len(pr.slots) < 256
     open(path, "w").write("\n".join(out) + "\n")
     return len(mul_rows) // NLANES, len(lin_rows) // NLANES
@@ -396,3 +599,10 @@ if __name__ == "__main__":
     nm, nl = emit(pr, os.path.join(ROOT, "lighthouse_b200", "csrc", "bls", "miller_warp_tables.inc"))
     print(f"ok: {len(pr.slots)} slots, {nm} mul phases, {nl} lin phases;",
           {n: len(p) for n, p in pr.sections.items()})
+    g2 = build_g2()
+    check_g2(g2)
+    nm, nl = emit(g2, os.path.join(ROOT, "lighthouse_b200", "csrc", "bls", "g2_warp_tables.inc"), PX="GW",
+                  exported=("AX.0", "A2X.0", "BpX.0", "HX.0", "CX.0", "CY.0", "JX.0", "c2x", "e1.0", "e2.0", "dummy"),
+                  structs=False)
+    print(f"ok: g2 programs, {len(g2.slots)} slots, {nm} mul phases, {nl} lin phases;",
+          {n: len(p) for n, p in g2.sections.items()})

@@ -10,6 +10,7 @@
 #include "../../lighthouse_b200/csrc/bls/pairing.cuh"
 #include "../../lighthouse_b200/csrc/bls/miller_coop.cuh"
 #include "../../lighthouse_b200/csrc/bls/miller_warp.cuh"
+#include "../../lighthouse_b200/csrc/bls/g2_warp.cuh"
 #include <vector>
 
 using namespace lhb200::bls;
@@ -318,6 +319,7 @@ EXPORT int hs_miller_warp(const uint8_t* p96, const uint8_t* q96, const uint8_t*
     }
     G1Proj3 neg_g1; neg_g1.px = G1_GEN_X; fp_neg(neg_g1.py, G1_GEN_Y); neg_g1.pz = FP_ONE;
     const int n_total = n + (have_extra ? 1 : 0);
+    const mw::Tables T = mw::miller_tables();
     Fp12 f; bool have_f = false;
     for (int b0 = 0; b0 < n_total; b0 += wpb) {
         std::vector<std::vector<uint32_t>> R(wpb, std::vector<uint32_t>(mw::REGION_WORDS, 0xdeadbeefu));
@@ -333,23 +335,25 @@ EXPORT int hs_miller_warp(const uint8_t* p96, const uint8_t* q96, const uint8_t*
             for (int w = 0; w < 6 * NL; w++) r[(mw::MW_S_HX_0 + w / NL) * mw::SL + w % NL] = qs[w];
             const uint32_t* ps = reinterpret_cast<const uint32_t*>(p);
             for (int w = 0; w < 3 * NL; w++) r[(mw::MW_S_PX + w / NL) * mw::SL + w % NL] = ps[w];
-            mw::run_section(r, mw::MW_SEC_INIT_FIRST, mw::MW_SEC_INIT_COUNT);
+            using namespace mw;
+            MW_RUN(r, 0, INIT);
             for (int i = 62; i >= 0; i--) {
-                mw::run_section(r, mw::MW_SEC_SQR_FIRST, mw::MW_SEC_SQR_COUNT);
-                mw::run_section(r, mw::MW_SEC_DBL_FIRST, mw::MW_SEC_DBL_COUNT);
-                mw::run_section(r, mw::MW_SEC_SPARSE_FIRST, mw::MW_SEC_SPARSE_COUNT);
+                MW_RUN(r, 0, SQR);
+                MW_RUN(r, 0, DBL);
+                MW_RUN(r, 0, SPARSE);
                 if ((BLS_X_ABS >> i) & 1) {
-                    mw::run_section(r, mw::MW_SEC_ADD_FIRST, mw::MW_SEC_ADD_COUNT);
-                    mw::run_section(r, mw::MW_SEC_SPARSE_FIRST, mw::MW_SEC_SPARSE_COUNT);
+                    MW_RUN(r, 0, ADD);
+                    MW_RUN(r, 0, SPARSE);
                 }
             }
-            mw::run_section(r, mw::MW_SEC_CONJ_FIRST, mw::MW_SEC_CONJ_COUNT);
+            MW_RUN(r, 0, CONJ);
         }
         for (int stride = 1; stride < wpb; stride *= 2)
             for (int wib = 0; wib + stride < wpb; wib += 2 * stride) {
                 uint32_t* r = R[wib].data(); const uint32_t* o = R[wib + stride].data();
                 for (int w = 0; w < 24 * mw::SL; w++) r[mw::MW_S_G0_0 * mw::SL + w] = o[mw::MW_S_F0_0 * mw::SL + w];
-                mw::run_section(r, mw::MW_SEC_DENSE_FIRST, mw::MW_SEC_DENSE_COUNT);
+                using namespace mw;
+                MW_RUN(r, 0, DENSE);
             }
         Fp12 blk;
         uint32_t* o = reinterpret_cast<uint32_t*>(&blk);
@@ -362,5 +366,43 @@ EXPORT int hs_miller_warp(const uint8_t* p96, const uint8_t* q96, const uint8_t*
     }
     final_exp(f, f);
     fp12_out(out576, f);
+    return 0;
+}
+
+// bls/g2_warp.cuh, lane by lane: the signature program (r * sig, subgroup test) and clear_cofactor.
+// hs_sig_warp: rc -1 bad encoding, 0 not in G2, 1 in G2 (out96 = compressed [r] sig).
+EXPORT int hs_sig_warp(const uint8_t* sig96, uint64_t r, uint8_t* out96) {
+    using namespace gw;
+    G2Affine a;
+    if (g2_decompress(a, sig96) != DEC_OK) return -1;
+    std::vector<uint32_t> Rv(REGION_WORDS, 0xdeadbeefu);
+    uint32_t* R = Rv.data();
+    const mw::Tables T = tables();
+    put_consts(R);
+    put_fp2(R, GW_S_BPX_0, a.x); put_fp2(R, GW_S_BPX_0 + 2, a.y);
+    Fp2 one; fp2_set_one(one); put_fp2(R, GW_S_BPX_0 + 4, one);
+    GW_RUN(R, 0, SETA);
+    GW_LADDER(R, 0, r, true, BLS_X_ABS);
+    GW_RUN(R, 0, SIGCHECK);
+    if (!(slots_zero(R, GW_S_E1_0, 4) && !slots_zero(R, GW_S_A2X_0 + 4, 2))) return 0;
+    GW_RUN(R, 0, TOJAC);
+    G2Jac j; get_fp2(j.X, R, GW_S_JX_0); get_fp2(j.Y, R, GW_S_JX_0 + 2); get_fp2(j.Z, R, GW_S_JX_0 + 4);
+    G2Affine o; jac_to_affine(o, j); g2_compress(out96, o);
+    return 1;
+}
+// out96 = compressed clear_cofactor(P) for the curve point P (compressed, not necessarily in G2)
+EXPORT int hs_clear_cofactor_warp(const uint8_t* p96, uint8_t* out96) {
+    using namespace gw;
+    G2Affine a;
+    if (g2_decompress(a, p96) != DEC_OK) return -1;
+    G2Jac h; jac_from_affine(h, a); jac_dbl(h, h); G2Jac a2; jac_from_affine(a2, a); jac_neg(a2, a2); jac_add(h, h, a2);  // P with Z != 1
+    std::vector<uint32_t> Rv(REGION_WORDS, 0xdeadbeefu);
+    uint32_t* R = Rv.data();
+    const mw::Tables T = tables();
+    put_consts(R);
+    put_fp2(R, GW_S_HX_0, h.X); put_fp2(R, GW_S_HX_0 + 2, h.Y); put_fp2(R, GW_S_HX_0 + 4, h.Z);
+    GW_CLEAR_COFACTOR(R, 0);
+    G2Jac j; get_fp2(j.X, R, GW_S_JX_0); get_fp2(j.Y, R, GW_S_JX_0 + 2); get_fp2(j.Z, R, GW_S_JX_0 + 4);
+    G2Affine o; jac_to_affine(o, j); g2_compress(out96, o);
     return 0;
 }

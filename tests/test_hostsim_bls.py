@@ -364,3 +364,36 @@ def test_warp_per_pairing_miller_program_matches_oracle(L):
         if with_extra:
             pairs.append((B.g1_neg(B.G1_GEN), extra))
         assert f12_from(out.raw) == ref_cube(pairs), (n, wpb)
+
+
+def test_g2_warp_programs_match_oracle(L):
+    """bls/g2_warp.cuh lane by lane: [r] sig and the psi-based subgroup test for a G2 point and for a curve point outside
+    G2, and clear_cofactor == [h_eff] P (RFC 9380 G.3) on a point outside G2."""
+    L.hs_sig_warp.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
+    L.hs_clear_cofactor_warp.argtypes = [C.c_char_p, C.c_char_p]
+    rnd = random.Random(99)
+    o = C.create_string_buffer(96)
+    for r in (1, 2, 3, (1 << 64) - 1, rnd.randrange(1, 1 << 64)):
+        sig = B.g2_mul(B.G2_GEN, rnd.randrange(1, B.R))
+        assert L.hs_sig_warp(B.g2_compress(sig), r, o) == 1 and o.raw == B.g2_compress(B.g2_mul(sig, r)), r
+    x = (7, 1)
+    while True:
+        y = B.f2_sqrt(B.f2_add(B.f2_mul(B.f2_sqr(x), x), B.B2))
+        if y and not B.g2_in_subgroup((x, y)):
+            break
+        x = (x[0] + 1, 1)
+    assert L.hs_sig_warp(B.g2_compress((x, y)), 12345, o) == 0
+    # points of order 13 and 23 (the cofactor of G2 is 13^2 23^2 2713 ...): the additions of both ladders degenerate
+    # (T == +-Q), Z becomes 0 and stays 0, and the test must reject them — for every scalar
+    xx = -B.X_ABS
+    h2 = (xx ** 8 - 4 * xx ** 7 + 5 * xx ** 6 - 4 * xx ** 4 + 6 * xx ** 3 - 4 * xx ** 2 - 4 * xx + 13) // 9
+    assert h2 % (13 * 13 * 23 * 23) == 0
+    co = B.g2_mul((x, y), B.R)
+    for q in (13, 23):
+        t = B.g2_mul(co, h2 // (q * q))
+        if t is not None and B.g2_mul(t, q) is not None:
+            t = B.g2_mul(t, q)
+        assert t is not None and B.g2_mul(t, q) is None
+        for r in (1, 5, q, q + 1, (1 << 64) - 1):
+            assert L.hs_sig_warp(B.g2_compress(t), r, o) == 0, (q, r)
+    assert L.hs_clear_cofactor_warp(B.g2_compress((x, y)), o) == 0 and o.raw == B.g2_compress(B.g2_mul((x, y), B.H_EFF))
