@@ -46,6 +46,7 @@ __device__ __forceinline__ void load_bytes16(uint8_t* dst, const uint8_t* src, i
 }  // namespace bls
 }  // namespace lhb200
 #include "g2_warp.cuh"   // latency-mode twins of the two kernels below (one warp per signature / message)
+#include "fe_warp.cuh"   // product of the Miller values + final exponentiation by one warp
 namespace lhb200 {
 namespace bls {
 

@@ -177,7 +177,8 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
     lhb200_bls_batch* b = new lhb200_bls_batch();
     b->cap_sets = max_sets;
     b->cap_keys = max_keys;
-    const uint64_t n = max_sets, n1 = cdiv(n, REDUCE_CHUNK) + 1, n2 = cdiv(n1, REDUCE_CHUNK) + 1;
+    // sum-tree buffers: sized for the narrowest chunk in use (4 points per warp in latency mode, REDUCE_CHUNK otherwise)
+    const uint64_t n = max_sets, n1 = cdiv(n, 4) + 1, n2 = cdiv(n1, 4) + 1;
     // Miller values: one per set (old kernels) or 5 per warp of the cooperative kernel (<= ceil((n+1)/6) + 40 warps)
     const uint64_t nf = std::max<uint64_t>(n, (cdiv(n + 1, 6) + 48) * 5), nf1 = cdiv(nf, REDUCE_CHUNK) + 1,
                    nf2 = cdiv(nf1, REDUCE_CHUNK) + 1;
@@ -572,6 +573,16 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         uint32_t m = n;
         int flip = 0;
         while (m > 1) {
+            if (g2_warp) {   // latency mode: warp-wide additions, four points per warp and level
+                constexpr uint32_t CH = 4;
+                const uint32_t mo = cdiv(m, CH);
+                gw::k_g2_sum_warp<<<cdiv(mo, GW_WPB), 32 * GW_WPB, gw_smem, b->s2>>>(cur, m, CH, b->d_sig_tmp[flip]);
+                launches++;
+                cur = b->d_sig_tmp[flip];
+                flip ^= 1;
+                m = mo;
+                continue;
+            }
             const uint32_t mo = cdiv(m, REDUCE_CHUNK);
             k_g2_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, b->s2>>>(cur, m, REDUCE_CHUNK, b->d_sig_tmp[flip]);
             launches++;
@@ -765,7 +776,12 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     }
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));
     }
-    k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, n_tail, f_last, b->d_fail, b->d_ok, b->d_gt);
+    static const int final_warp_env = [] { const char* e = getenv("LHB_FINAL_WARP"); return e ? atoi(e) : 1; }();
+    if (final_warp_env && !f_last)   // phase-interpreter tail (bls/fe_warp.cuh): 1.1 ms instead of 2.2
+        fe::k_final_warp<<<1, 32 * fe::FE_WARPS, (size_t)fe::FE_WARPS * fe::REGION_WORDS * 4, s>>>(cur, n_tail, b->d_fail, b->d_ok,
+                                                                                                 b->d_gt);
+    else
+        k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, n_tail, f_last, b->d_fail, b->d_ok, b->d_gt);
     launches++;
     LHB_CUDA(cudaGetLastError());
     count_launch(launches);

@@ -426,6 +426,11 @@ def build_g2():
     b.mul("P0Z", "zz", "HZ"); b.flush_mul()
     b.lin("P0Y", [(1, "HY")]); b.flush_lin()
     g2_copy(b, "Bp", "P0"); g2_copy(b, "A", "P0"); b.flush_lin()
+    # sums of Jacobian points (the sum r_i sig_i tree): Bp <- projective form of the Jacobian point in H, A untouched
+    pr.section("hbp")
+    b.mul("BpX", "HX", "HZ"); b.sqr("zz", "HZ"); b.flush_mul()
+    b.mul("BpZ", "zz", "HZ"); b.flush_mul()
+    b.lin("BpY", [(1, "HY")]); b.flush_lin()
     # after ladder 1 (A = [|x|] P0):  T1 = -A = [x] P0;  T2 = psi(P0);  A = P0 (to be doubled)
     pr.section("hmid1")
     g2_copy(b, "T1", "A", neg=True); g2_psi(b, "T2", "P0"); b.flush_mul(); b.flush_lin()
@@ -536,6 +541,179 @@ def check_g2(pr):
     run_section(pr, "addA", mem); run_section(pr, "hmid7", mem); run_section(pr, "addA", mem)
     run_section(pr, "tojac", mem)
     assert g2_get_jac_affine(pr, mem) == B.g2_mul((x, y), B.H_EFF), "clear_cofactor program disagrees with [h_eff]P"
+    # ---- sum of Jacobian points: hinit (first), then hbp + addA per further point
+    pts = [B.g2_mul(B.G2_GEN, rnd.randrange(1, B.R)) for _ in range(3)]
+    acc = None
+    for k, pt in enumerate(pts):
+        z = (rnd.randrange(1, P), rnd.randrange(1, P)); z2 = B.f2_sqr(z)
+        for n, v in zip(("HX", "HY", "HZ"), (B.f2_mul(pt[0], z2), B.f2_mul(pt[1], B.f2_mul(z2, z)), z)):
+            mem[pr.slots[n + ".0"]], mem[pr.slots[n + ".1"]] = v
+        if k == 0:
+            run_section(pr, "hinit", mem)
+        else:
+            run_section(pr, "hbp", mem); run_section(pr, "addA", mem)
+        acc = B.g2_add(acc, pt)
+    run_section(pr, "tojac", mem)
+    assert g2_get_jac_affine(pr, mem) == acc, "point sum program disagrees with g2_add"
+
+
+
+# ================================================================================================ final exponentiation
+FE_REGS = ("f", "t0", "t1", "t2")
+# the sequence of coop_final_exp (bls/coop.cuh) = final_exp (bls/pairing.cuh): f^(3 (p^12 - 1) / r)
+FE_MULS = [("f", "t0", "t1"), ("f", "t0", "f"), ("t0", "t0", "t1"), ("t0", "t1", "t2"), ("t2", "t2", "t1"), ("t1", "t1", "f"),
+           ("f", "t2", "t1"), ("t0", "t0", "f"), ("t1", "t1", "t0"), ("t2", "t2", "t1"), ("f", "f", "t0")]
+FE_COPIES = [("t0", "f"), ("t1", "t0"), ("t2", "t1"), ("t1", "f")]
+FE_CONJS = [("t0", "t0"), ("t1", "t1"), ("t2", "t2"), ("t0", "f"), ("t1", "f"), ("t2", "t0"), ("t1", "t0")]
+FE_FROB2 = [("t0", "f"), ("t1", "t0")]
+FE_FROB = [("t2", "t0")]
+
+
+def build_fe():
+    pr = Prog()
+    for V in FE_REGS:
+        for k in range(6):
+            pr.slot(f"{V}{k}.0"); pr.slot(f"{V}{k}.1")
+    for k in range(6):
+        pr.slot(f"g1_{k}.0"); pr.slot(f"g1_{k}.1")
+    for k in range(6):
+        pr.slot(f"g2_{k}")
+    pr.slot("dummy")
+
+    def c(V, k, comp):
+        return pr.slot(f"{V}{k}.{comp}")
+
+    done = set()
+    for dst, a, bb in FE_MULS:
+        name = f"mul_{dst}_{a}_{bb}"
+        if name in done:
+            continue
+        done.add(name)
+        pr.section(name)
+        lops = []
+        for j in range(6):
+            lops.append((pr.slot(f"ys{j}"), [(1, c(bb, j, 0)), (1, c(bb, j, 1))], 0))
+            lops.append((pr.slot(f"yd{j}"), [(1, c(bb, j, 0)), (-1, c(bb, j, 1))], 0))
+        pr.lin_phase(lops)
+        ops, parts = [], {}
+        for t in range(6):
+            re, im = [], []
+            for i in range(6):
+                for j in range(6):
+                    if i + j == t:
+                        re += [(X_POS, c(a, i, 0), c(bb, j, 0)), (X_NEG, c(a, i, 1), c(bb, j, 1))]
+                        im += [(X_POS, c(a, i, 0), c(bb, j, 1)), (X_POS, c(a, i, 1), c(bb, j, 0))]
+                    elif i + j == t + 6:
+                        re += [(X_POS, c(a, i, 0), pr.slot(f"yd{j}")), (X_NEG, c(a, i, 1), pr.slot(f"ys{j}"))]
+                        im += [(X_POS, c(a, i, 0), pr.slot(f"ys{j}")), (X_POS, c(a, i, 1), pr.slot(f"yd{j}"))]
+            for comp, lst in ((0, re), (1, im)):
+                assert len(lst) == 12
+                parts[(t, comp)] = []
+                for ci in range(3):
+                    d = pr.slot(f"mp{t}.{comp}.{ci}")
+                    parts[(t, comp)].append(d)
+                    ops.append((d, lst[4 * ci:4 * ci + 4]))
+        pr.mul_phase(KMAX, ops[:18]); pr.mul_phase(KMAX, ops[18:])
+        pr.lin_phase([(c(dst, t, comp), [(1, x) for x in parts[(t, comp)]], 0) for t in range(6) for comp in (0, 1)])
+
+    for V in ("t0", "t1", "t2"):    # cyclotomic squaring in place (Granger-Scott, pairs (a0,a3) (a1,a4) (a2,a5))
+        pr.section(f"cyc_{V}")
+        ops = []
+        for pp in range(3):
+            x0, x1, y0, y1 = c(V, pp, 0), c(V, pp, 1), c(V, pp + 3, 0), c(V, pp + 3, 1)
+            ops.append((pr.slot(f"sx{pp}.0"), [(X_POS, x0, x0), (X_NEG, x1, x1)]))
+            ops.append((pr.slot(f"sx{pp}.1"), [(X_DBL, x0, x1)]))
+            ops.append((pr.slot(f"sy{pp}.0"), [(X_POS, y0, y0), (X_NEG, y1, y1)]))
+            ops.append((pr.slot(f"sy{pp}.1"), [(X_DBL, y0, y1)]))
+            ops.append((pr.slot(f"bb{pp}.0"), [(X_DBL, x0, y0), (X_NEGDBL, x1, y1)]))      # B = 2 x y
+            ops.append((pr.slot(f"bb{pp}.1"), [(X_DBL, x0, y1), (X_DBL, x1, y0)]))
+        pr.mul_phase(2, ops)
+        S = pr.slot
+        lops = []
+
+        def A_minus(dst_k, pp):      # 3 (sx + xi sy) - 2 a
+            lops.append((c(V, dst_k, 0), [(3, S(f"sx{pp}.0")), (3, S(f"sy{pp}.0")), (-3, S(f"sy{pp}.1")), (-2, c(V, dst_k, 0))], 0))
+            lops.append((c(V, dst_k, 1), [(3, S(f"sx{pp}.1")), (3, S(f"sy{pp}.0")), (3, S(f"sy{pp}.1")), (-2, c(V, dst_k, 1))], 0))
+
+        def B_plus(dst_k, pp, xi):   # 3 [xi] B + 2 a
+            if not xi:
+                for comp in (0, 1):
+                    lops.append((c(V, dst_k, comp), [(3, S(f"bb{pp}.{comp}")), (2, c(V, dst_k, comp))], 0))
+            else:
+                lops.append((c(V, dst_k, 0), [(3, S(f"bb{pp}.0")), (-3, S(f"bb{pp}.1")), (2, c(V, dst_k, 0))], 0))
+                lops.append((c(V, dst_k, 1), [(3, S(f"bb{pp}.0")), (3, S(f"bb{pp}.1")), (2, c(V, dst_k, 1))], 0))
+        A_minus(0, 0); B_plus(3, 0, False); B_plus(1, 2, True); A_minus(4, 2); A_minus(2, 1); B_plus(5, 1, False)
+        pr.lin_phase(lops)
+
+    for dst, src in FE_COPIES:
+        pr.section(f"copy_{dst}_{src}")
+        pr.lin_phase([(c(dst, k, comp), [(1, c(src, k, comp))], 0) for k in range(6) for comp in (0, 1)])
+    for dst, src in FE_CONJS:     # a^(p^6): negate the odd powers of w
+        pr.section(f"conj_{dst}_{src}")
+        pr.lin_phase([(c(dst, k, comp), [(-1 if k & 1 else 1, c(src, k, comp))], 0) for k in range(6) for comp in (0, 1)])
+    for dst, src in FE_FROB2:     # a^(p^2): coefficient k times the Fp constant gamma2_k
+        pr.section(f"frob2_{dst}_{src}")
+        pr.mul_phase(2, [(c(dst, k, comp), [(X_POS, pr.slot(f"g2_{k}"), c(src, k, comp))]) for k in range(6) for comp in (0, 1)])
+    for dst, src in FE_FROB:      # a^p: conj(a_k) * gamma_k
+        pr.section(f"frob_{dst}_{src}")
+        ops = []
+        for k in range(6):
+            s0, s1, g0, g1 = c(src, k, 0), c(src, k, 1), pr.slot(f"g1_{k}.0"), pr.slot(f"g1_{k}.1")
+            ops.append((c(dst, k, 0), [(X_POS, s0, g0), (X_POS, s1, g1)]))       # (s0 - s1 i)(g0 + g1 i)
+            ops.append((c(dst, k, 1), [(X_POS, s0, g1), (X_NEG, s1, g0)]))
+        pr.mul_phase(2, ops)
+    return pr
+
+
+def fe_get(pr, mem, V):
+    k = [(mem[pr.slots[f"{V}{j}.0"]], mem[pr.slots[f"{V}{j}.1"]]) for j in range(6)]
+    return ((k[0], k[2], k[4]), (k[1], k[3], k[5]))
+
+
+def fe_put(pr, mem, V, v):
+    k = [v[0][0], v[1][0], v[0][1], v[1][1], v[0][2], v[1][2]]
+    for j in range(6):
+        mem[pr.slots[f"{V}{j}.0"]], mem[pr.slots[f"{V}{j}.1"]] = k[j]
+
+
+def fe_program(run, inv):
+    """the control flow of k_final_warp: run(section name), inv() = t1 <- f^-1 (single-lane code on the device)"""
+    def pow_x(r, a):
+        run(f"copy_{r}_{a}")
+        for i in range(62, -1, -1):
+            run(f"cyc_{r}")
+            if (B.X_ABS >> i) & 1:
+                run(f"mul_{r}_{r}_{a}")
+        run(f"conj_{r}_{r}")
+    inv()
+    run("conj_t0_f"); run("mul_f_t0_t1"); run("frob2_t0_f"); run("mul_f_t0_f")
+    pow_x("t0", "f"); run("conj_t1_f"); run("mul_t0_t0_t1")
+    pow_x("t1", "t0"); run("conj_t2_t0"); run("mul_t0_t1_t2")
+    pow_x("t1", "t0"); run("frob_t2_t0"); run("mul_t0_t1_t2")
+    pow_x("t1", "t0"); pow_x("t2", "t1"); run("frob2_t1_t0"); run("mul_t2_t2_t1"); run("conj_t1_t0"); run("mul_t2_t2_t1")
+    run("copy_t1_f"); run("cyc_t1"); run("mul_t1_t1_f"); run("mul_f_t2_t1")
+
+
+def check_fe(pr):
+    rnd = random.Random(5)
+    mem = [0] * len(pr.slots)
+    G = [B.f2_pow(B.XI, k * (P - 1) // 6) for k in range(6)]
+    for k in range(6):
+        mem[pr.slots[f"g1_{k}.0"]], mem[pr.slots[f"g1_{k}.1"]] = G[k]
+        n = B.f2_mul(B.f2_conj(G[k]), G[k])
+        assert n[1] == 0
+        mem[pr.slots[f"g2_{k}"]] = n[0]
+    f_in = B.miller_loop(B.g1_mul(B.G1_GEN, rnd.randrange(1, B.R)), B.g2_mul(B.G2_GEN, rnd.randrange(1, B.R)))
+    fe_put(pr, mem, "f", f_in)
+    # product section used by the kernel to fold its inputs: f <- f * t0
+    other = B.f12_pow(f_in, 7)
+    fe_put(pr, mem, "t0", other)
+    run_section(pr, "mul_f_f_t0", mem)
+    assert fe_get(pr, mem, "f") == B.f12_mul(f_in, other)
+    fe_put(pr, mem, "f", f_in)
+    fe_program(lambda name: run_section(pr, name, mem), lambda: fe_put(pr, mem, "t1", B.f12_inv(fe_get(pr, mem, "f"))))
+    g = B.final_exp(f_in)
+    assert fe_get(pr, mem, "f") == B.f12_mul(B.f12_sqr(g), g), "final exponentiation program != oracle GT value cubed"
 
 
 # ------------------------------------------------------------------------------------------------ emit
@@ -606,3 +784,8 @@ if __name__ == "__main__":
                   structs=False)
     print(f"ok: g2 programs, {len(g2.slots)} slots, {nm} mul phases, {nl} lin phases;",
           {n: len(p) for n, p in g2.sections.items()})
+    fe = build_fe()
+    check_fe(fe)
+    nm, nl = emit(fe, os.path.join(ROOT, "lighthouse_b200", "csrc", "bls", "fe_warp_tables.inc"), PX="FE",
+                  exported=("f0.0", "t0" + "0.0", "t10.0", "t20.0", "g1_0.0", "g2_0", "dummy"), structs=False)
+    print(f"ok: final exponentiation, {len(fe.slots)} slots, {nm} mul phases, {nl} lin phases, {len(fe.sections)} sections")

@@ -11,6 +11,7 @@
 #include "../../lighthouse_b200/csrc/bls/miller_coop.cuh"
 #include "../../lighthouse_b200/csrc/bls/miller_warp.cuh"
 #include "../../lighthouse_b200/csrc/bls/g2_warp.cuh"
+#include "../../lighthouse_b200/csrc/bls/fe_warp.cuh"
 #include <vector>
 
 using namespace lhb200::bls;
@@ -404,5 +405,28 @@ EXPORT int hs_clear_cofactor_warp(const uint8_t* p96, uint8_t* out96) {
     GW_CLEAR_COFACTOR(R, 0);
     G2Jac j; get_fp2(j.X, R, GW_S_JX_0); get_fp2(j.Y, R, GW_S_JX_0 + 2); get_fp2(j.Z, R, GW_S_JX_0 + 4);
     G2Affine o; jac_to_affine(o, j); g2_compress(out96, o);
+    return 0;
+}
+
+// bls/fe_warp.cuh lane by lane: out = final exponentiation of a * b (the product section folds the inputs), 576 bytes each
+EXPORT int hs_final_warp(const uint8_t* a576, const uint8_t* b576, uint8_t* out576) {
+    using namespace fe;
+    Fp12 a, b2; fp12_in(a, a576); fp12_in(b2, b576);
+    std::vector<uint32_t> Rv(REGION_WORDS, 0xdeadbeefu);
+    uint32_t* R = Rv.data();
+    const mw::Tables T = tables();
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a); const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b2);
+    for (int w = 0; w < 12 * NL; w++) { R[reg_word(FE_S_F0_0, w)] = aw[w]; R[reg_word(FE_S_T00_0, w)] = bw[w]; }
+    FE_RUN(R, 0, MUL_F_F_T0);
+    Fp12 f, inv; uint32_t* fw = reinterpret_cast<uint32_t*>(&f);
+    for (int w = 0; w < 12 * NL; w++) fw[w] = R[reg_word(FE_S_F0_0, w)];
+    fp12_inv(inv, f);
+    put_consts(R);
+    const uint32_t* iw = reinterpret_cast<const uint32_t*>(&inv);
+    for (int w = 0; w < 12 * NL; w++) R[reg_word(FE_S_T10_0, w)] = iw[w];
+    FE_AFTER_INVERSION(R, 0);
+    Fp12 g; uint32_t* gw_ = reinterpret_cast<uint32_t*>(&g);
+    for (int w = 0; w < 12 * NL; w++) gw_[w] = R[reg_word(FE_S_F0_0, w)];
+    fp12_out(out576, g);
     return 0;
 }

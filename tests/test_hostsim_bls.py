@@ -397,3 +397,17 @@ def test_g2_warp_programs_match_oracle(L):
         for r in (1, 5, q, q + 1, (1 << 64) - 1):
             assert L.hs_sig_warp(B.g2_compress(t), r, o) == 0, (q, r)
     assert L.hs_clear_cofactor_warp(B.g2_compress((x, y)), o) == 0 and o.raw == B.g2_compress(B.g2_mul((x, y), B.H_EFF))
+
+
+def test_final_exponentiation_warp_program_matches_single_thread(L):
+    """bls/fe_warp.cuh lane by lane: product of two Miller values, then f^(3 (p^12 - 1) / r) — equal to the single-thread
+    final_exp of pairing.cuh (hs_pairing) and to the oracle's GT value cubed."""
+    L.hs_final_warp.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    p1, q1 = B.g1_mul(B.G1_GEN, 4242), B.g2_mul(B.G2_GEN, 777)
+    p2, q2 = B.g1_mul(B.G1_GEN, 99), B.g2_mul(B.G2_GEN, 31)
+    m1, m2, o = C.create_string_buffer(576), C.create_string_buffer(576), C.create_string_buffer(576)
+    assert L.hs_pairing(B.g1_uncompressed(p1), B.g2_compress(q1), 0, 0, m1) == 0      # Miller values, no final exp
+    assert L.hs_pairing(B.g1_uncompressed(p2), B.g2_compress(q2), 0, 0, m2) == 0
+    assert L.hs_final_warp(m1.raw, m2.raw, o) == 0
+    g = B.final_exp(B.f12_mul(B.miller_loop(p1, q1), B.miller_loop(p2, q2)))
+    assert f12_from(o.raw) == B.f12_mul(B.f12_sqr(g), g)
