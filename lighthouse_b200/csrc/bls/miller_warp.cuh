@@ -137,6 +137,27 @@ __device__ __noinline__ void run_section(uint32_t* R, int lane, int first, int c
 #endif
 
 LHB_HD LHB_INLINE Tables miller_tables() { return Tables{MW_PHASES, MW_MUL, MW_LIN}; }
+// words of shared memory a block needs for a copy of a program's tables (stage_tables)
+constexpr int table_words(int n_mul, int n_lin, int n_phases) { return n_mul * 4 + n_lin * 3 + n_phases; }
+#if !defined(LHB_HOSTSIM)
+// Copy a program's tables next to the working sets: every phase starts with a dependent phase -> row fetch, ~0.4 us from
+// global memory against ~2-4 us of arithmetic; from shared memory it is a few dozen cycles.  All threads of the block.
+__device__ __forceinline__ Tables stage_tables(uint32_t* dst, const Tables& g, int n_mul, int n_lin, int n_phases) {
+    static_assert(sizeof(MwMulOp) == 16 && sizeof(MwLinOp) == 12 && sizeof(MwPhase) == 4, "table row sizes");
+    uint32_t* d_mul = dst;
+    uint32_t* d_lin = d_mul + n_mul * 4;
+    uint32_t* d_ph = d_lin + n_lin * 3;
+    const uint32_t* s_mul = reinterpret_cast<const uint32_t*>(g.mul);
+    const uint32_t* s_lin = reinterpret_cast<const uint32_t*>(g.lin);
+    const uint32_t* s_ph = reinterpret_cast<const uint32_t*>(g.ph);
+    for (int i = threadIdx.x; i < n_mul * 4; i += blockDim.x) d_mul[i] = s_mul[i];
+    for (int i = threadIdx.x; i < n_lin * 3; i += blockDim.x) d_lin[i] = s_lin[i];
+    for (int i = threadIdx.x; i < n_phases; i += blockDim.x) d_ph[i] = s_ph[i];
+    __syncthreads();
+    return Tables{reinterpret_cast<const MwPhase*>(d_ph), reinterpret_cast<const MwMulOp*>(d_mul),
+                  reinterpret_cast<const MwLinOp*>(d_lin)};
+}
+#endif
 #ifdef LHB_HOSTSIM
 #define MW_RUN(R, lane, SEC) run_section(R, MW_SEC_##SEC##_FIRST, MW_SEC_##SEC##_COUNT, T)
 #else
@@ -152,17 +173,18 @@ LHB_HD LHB_INLINE void set_one_words(uint32_t* R, int word) {   // word < 24 * S
     R[(MW_S_F0_0 + slot) * SL + limb] = one ? FP_ONE.v[limb] : 0u;
 }
 
+constexpr size_t smem_bytes(int warps) { return ((size_t)warps * REGION_WORDS + table_words(MW_N_MUL, MW_N_LIN, MW_N_PHASES)) * 4; }
 #if !defined(LHB_HOSTSIM)
 // One warp per pair (P_i, H_i), i < n, plus the pair (extra_p, extra_q) = (-g1, sum r sig) as pair n.  Invalid sets
 // (status != 0, H at infinity) contribute f = 1, like k_miller_coop.  The warps of a block multiply their values
-// (dense section) and the block writes ONE Fp12.  Dynamic shared memory: warps_per_block * REGION_WORDS words.
+// (dense section) and the block writes ONE Fp12.  Dynamic shared memory: smem_bytes(warps_per_block).
 __global__ void __launch_bounds__(256, 1) k_miller_warp(const G1Proj3* __restrict__ P, const G2Jac* __restrict__ H,
                                                         const uint8_t* __restrict__ status, uint32_t n,
                                                         const G2Jac* __restrict__ extra_q, const G1Proj3* __restrict__ extra_p,
                                                         Fp12* __restrict__ out_f) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     uint32_t* R = lhb_dyn_smem + (size_t)wib * REGION_WORDS;
-    const Tables T = miller_tables();
+    const Tables T = stage_tables(lhb_dyn_smem + (size_t)nw * REGION_WORDS, miller_tables(), MW_N_MUL, MW_N_LIN, MW_N_PHASES);
     const uint32_t n_total = n + (extra_q ? 1u : 0u);
     const uint32_t set = blockIdx.x * nw + wib;
     for (int w = lane; w < 24 * SL; w += 32) set_one_words(R, w);

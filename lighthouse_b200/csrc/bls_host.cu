@@ -560,7 +560,15 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     static const int g2_warp_env = [] { const char* e = getenv("LHB_G2_WARP"); return e ? atoi(e) : 1; }();
     const bool g2_warp = g2_warp_env && n <= 4u * (uint32_t)n_sm;
     constexpr uint32_t GW_WPB = 4;
-    const size_t gw_smem = (size_t)GW_WPB * gw::REGION_WORDS * 4;
+    const size_t gw_smem = gw::smem_bytes(GW_WPB);
+    if (g2_warp) {   // working sets + a shared-memory copy of the phase tables: above the 48 KB default
+        static const bool gw_attr_ok = [&] {
+            return cudaFuncSetAttribute(gw::k_sig_prepare_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem) == cudaSuccess &&
+                   cudaFuncSetAttribute(gw::k_hash_to_g2_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem) == cudaSuccess &&
+                   cudaFuncSetAttribute(gw::k_g2_sum_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem) == cudaSuccess;
+        }();
+        if (!gw_attr_ok) { set_error("g2 warp kernels: cannot reserve %zu B of shared memory", gw_smem); return LHB200_ECUDA; }
+    }
     if (g2_warp)
         gw::k_sig_prepare_warp<<<cdiv(n, GW_WPB), 32 * GW_WPB, gw_smem, b->s2>>>(b->in_sigs, b->in_rands, n, b->d_sigr,
                                                                                b->d_status, b->d_fail);
@@ -672,14 +680,14 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         if (miller_warp_env && n_total <= max_warps) {
             static const bool mw_attr_ok = [] {
                 return cudaFuncSetAttribute(mw::k_miller_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(mc::MC_WARPS * mw::REGION_WORDS * 4)) == cudaSuccess;
+                                            (int)mw::smem_bytes(mc::MC_WARPS)) == cudaSuccess;
             }();
             if (!mw_attr_ok) { set_error("k_miller_warp: cannot reserve shared memory"); return LHB200_ECUDA; }
             const uint32_t wpb = n_total <= 4 * COOP_TAIL ? 4 : mc::MC_WARPS;
             const uint32_t mgrid = cdiv(n_total, wpb);
             LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));   // sum r sig (and -g1) ready
             LHB_CUDA(cudaEventRecord(b->e_k0, s));
-            mw::k_miller_warp<<<mgrid, 32 * wpb, (size_t)wpb * mw::REGION_WORDS * 4, s>>>(b->d_p, b->d_h, b->d_status, n,
+            mw::k_miller_warp<<<mgrid, 32 * wpb, mw::smem_bytes((int)wpb), s>>>(b->d_p, b->d_h, b->d_status, n,
                                                                                          b->d_sig_sum, b->d_neg_g1, b->d_f);
             LHB_CUDA(cudaEventRecord(b->e_k1, s));
             launches += 1;
@@ -777,10 +785,13 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaStreamWaitEvent(s, b->e_join, 0));
     }
     static const int final_warp_env = [] { const char* e = getenv("LHB_FINAL_WARP"); return e ? atoi(e) : 1; }();
-    if (final_warp_env && !f_last)   // phase-interpreter tail (bls/fe_warp.cuh): 1.1 ms instead of 2.2
-        fe::k_final_warp<<<1, 32 * fe::FE_WARPS, (size_t)fe::FE_WARPS * fe::REGION_WORDS * 4, s>>>(cur, n_tail, b->d_fail, b->d_ok,
-                                                                                                 b->d_gt);
-    else
+    if (final_warp_env && !f_last) {   // phase-interpreter tail (bls/fe_warp.cuh)
+        static const bool fe_attr_ok = [] {
+            return cudaFuncSetAttribute(fe::k_final_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe::smem_bytes()) == cudaSuccess;
+        }();
+        if (!fe_attr_ok) { set_error("k_final_warp: cannot reserve shared memory"); return LHB200_ECUDA; }
+        fe::k_final_warp<<<1, 32 * fe::FE_WARPS, fe::smem_bytes(), s>>>(cur, n_tail, b->d_fail, b->d_ok, b->d_gt);
+    } else
         k_final_coop<<<1, COOP_THREADS, sizeof(CoopFinalSmem), s>>>(cur, n_tail, f_last, b->d_fail, b->d_ok, b->d_gt);
     launches++;
     LHB_CUDA(cudaGetLastError());

@@ -740,7 +740,7 @@ def emit(pr, path, PX="MW", exported=("f0.0", "X.0", "Y.0", "Z.0", "HX.0", "HY.0
                         terms = list(terms) + [(X_ZERO, dummy, dummy)] * (KMAX - len(terms))
                     else:
                         d, terms = dummy, [(X_ZERO, dummy, dummy)] * KMAX
-                    mul_rows.append("{%d, {%s}, {%s}, {%s}}" % (d, ",".join(str(t[0]) for t in terms),
+                    mul_rows.append("{%d, {%s}, {%s}, {%s}, {0,0,0}}" % (d, ",".join(str(t[0]) for t in terms),
                                                                ",".join(str(t[1]) for t in terms),
                                                                ",".join(str(t[2]) for t in terms)))
                 phases.append("{1, %d, %d}" % (K, base // NLANES))
@@ -753,17 +753,18 @@ def emit(pr, path, PX="MW", exported=("f0.0", "X.0", "Y.0", "Z.0", "HX.0", "HY.0
                         d, terms, h = dummy, [(1, dummy)], 0
                     n = len(terms)
                     terms = list(terms) + [(0, dummy)] * (4 - n)
-                    lin_rows.append("{%d, %d, %d, {%s}, {%s}}" % (d, n, h, ",".join(str(t[0]) for t in terms),
+                    lin_rows.append("{%d, %d, %d, {%s}, {%s}, 0}" % (d, n, h, ",".join(str(t[0]) for t in terms),
                                                                  ",".join(str(t[1]) for t in terms)))
                 phases.append("{0, 0, %d}" % (base // NLANES))
         sect.append((name, first, len(phases) - first))
     if structs:
-        out.append("struct MwMulOp { uint8_t d; uint8_t xm[4]; uint8_t xs[4]; uint8_t ys[4]; };")
-        out.append("struct MwLinOp { uint8_t d; uint8_t n; uint8_t h; int8_t c[4]; uint8_t s[4]; };")
+        out.append("struct MwMulOp { uint8_t d; uint8_t xm[4]; uint8_t xs[4]; uint8_t ys[4]; uint8_t pad[3]; };   // 16 B")
+        out.append("struct MwLinOp { uint8_t d; uint8_t n; uint8_t h; int8_t c[4]; uint8_t s[4]; uint8_t pad; };   // 12 B")
         out.append("struct MwPhase { uint8_t is_mul; uint8_t k; uint16_t table; };")
     out.append(f"MW_TABLE MwMulOp {PX}_MUL[{len(mul_rows)}] = {{\n" + ",\n".join(mul_rows) + "};")
     out.append(f"MW_TABLE MwLinOp {PX}_LIN[{len(lin_rows)}] = {{\n" + ",\n".join(lin_rows) + "};")
     out.append(f"MW_TABLE MwPhase {PX}_PHASES[{len(phases)}] = {{" + ", ".join(phases) + "};")
+    out.append(f"constexpr int {PX}_N_MUL = {len(mul_rows)}, {PX}_N_LIN = {len(lin_rows)}, {PX}_N_PHASES = {len(phases)};")
     for name, first, cnt in sect:
         out.append(f"constexpr int {PX}_SEC_{name.upper()}_FIRST = {first}, {PX}_SEC_{name.upper()}_COUNT = {cnt};")
     assert len(pr.slots) < 256
