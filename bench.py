@@ -322,6 +322,23 @@ def run_ours(args):
                 "latency_ms_e2e": ms0_e2e, "sets_per_s_e2e": CFG0_SETS / ms0_e2e * 1e3, "launches": int(b0.launches),
                 "verdict": True}
         b0.destroy()
+        # the reference's steady state: gossip batches of <= 64 sets (beacon_processor/src/lib.rs:202-203), here 64 single-key
+        # sets (unaggregated attestations) and 64 aggregates of 128 keys, through the plugin call with pinned buffers
+        gossip = {}
+        for label, kps in (("64_sets_x_1_key", 1), ("64_sets_x_128_keys", KEYS_PER_SET)):
+            ag = S.attestation_batch(64, keys_per_set=kps, n_validators=N_VALIDATORS_BLS, seed=SEED_CFG0 + kps, pk_table=pk_table)
+            rg = np.random.default_rng(9).integers(1, 2 ** 63, size=64, dtype=np.uint64) * 2 + 1
+            bg = bls.Batch(64, 64 * kps)
+            bg.upload(ag.sigs, ag.msgs, ag.pks, ag.offsets, rg)
+            time_resident(bg, 3, collective=False)
+            msg_, okg = time_resident(bg, max(K, 10), collective=False)
+            assert okg
+            pg = [pin(ag.sigs), pin(ag.msgs), pin(ag.pks), torch.from_numpy(ag.offsets.copy()).pin_memory(),
+                  torch.from_numpy(rg.copy()).pin_memory()]
+            msg_e2e = time_wall(lambda: plugin_call(*[vp(t) for t in pg], 64), max(K, 10))
+            gossip[label] = {"latency_ms_resident": msg_, "latency_ms_e2e": msg_e2e, "launches": int(bg.launches)}
+            bg.destroy()
+        cfg0["gossip_batch"] = gossip
 
     # ------------------------------------------------------------------ tree-hash workload (per rank)
     ssz = S.beacon_state_deneb_ssz(N_VALIDATORS_STATE, seed=42 + rank)
@@ -472,10 +489,17 @@ def run_ours(args):
         ms4 = max_over_ranks(e0.elapsed_time(e1)) / n4
         torch.cuda.synchronize()
         got4 = bytes(roots4.cpu().tolist())
-        for i in range(CFG4_STATES):             # every slot (mine and the ones the all-reduce brought) is the cold root
-            if got4[32 * i:32 * i + 32] != root0:
+        want4 = [root0]                          # rank r hashes its own state (seed 42 + r): slot i holds rank (i % world)'s root
+        if world > 1:
+            mine = torch.tensor(list(root0), dtype=torch.uint8, device=dev)
+            allr = torch.zeros(world * 32, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allr, mine)
+            flat = bytes(allr.cpu().tolist())
+            want4 = [flat[32 * r:32 * r + 32] for r in range(world)]
+        for i in range(CFG4_STATES):             # every slot: mine and the ones the all-reduce brought
+            if got4[32 * i:32 * i + 32] != want4[i % world]:
                 raise RuntimeError(f"cfg4: state root slot {i} on rank {rank} is {got4[32 * i:32 * i + 32].hex()}, "
-                                   f"expected {root0.hex()}")
+                                   f"expected {want4[i % world].hex()}")
         ideal_bls = CFG4_SETS / bls_value * 1e3 * 1.0          # ms at the cfg2 rate of this run (all ranks)
         cfg4 = {"workload": f"mixed epoch: {CFG4_SETS} aggregate attestations x {KEYS_PER_SET} keys + {CFG4_STATES} cold "
                             f"{N_VALIDATORS_STATE}-validator state roots, sets sharded and whole states round-robin over "
