@@ -115,7 +115,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mark_at = index, [], None, 0
+
+    def mark(self):
+        """the timed region starts here (nvidia-smi needs a second or two to come up on an 8-GPU box, so it is started
+        before the warm-up; rows before the mark are dropped if any arrive after it)"""
+        self.mark_at = len(self.rows)
 
     def start(self):
         try:
@@ -132,13 +137,18 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        window = "timed region"
+        if len(self.rows) > self.mark_at:
+            self.rows = self.rows[self.mark_at:]
+        elif self.rows:
+            window = "warm-up (same kernels; no sample landed inside the timed region)"
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active")
                                                           for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -230,12 +240,13 @@ def run_ours(args):
     rands = rng.integers(1, 2 ** 63, size=N_SETS, dtype=np.uint64) * 2 + 1          # nonzero 64-bit scalars
     batch = bls.Batch(N_SETS, n_keys)
     batch.upload(ab.sigs, ab.msgs, ab.pks, ab.offsets, rands)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         ms, ok = time_resident(batch, 1)
         assert ok, "synthetic batch must verify"
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     l0 = lib.lhb200_launch_count()
     dom_ms = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
