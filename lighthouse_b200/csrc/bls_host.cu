@@ -556,9 +556,9 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
     LHB_CUDA(cudaStreamWaitEvent(b->s2, b->e_fork, 0));
     LHB_CUDA(cudaStreamWaitEvent(b->s3, b->e_fork, 0));
     // latency mode of the two G2 stages (bls/g2_warp.cuh): one warp per signature / message while the batch is small
-    // enough for every warp to have a scheduler of its own (four per block, n / 4 blocks <= SMs)
+    // enough for the warps of one wave (four per block, at most two blocks per SM)
     static const int g2_warp_env = [] { const char* e = getenv("LHB_G2_WARP"); return e ? atoi(e) : 1; }();
-    const bool g2_warp = g2_warp_env && n <= 4u * (uint32_t)n_sm;
+    const bool g2_warp = g2_warp_env && n <= 6u * (uint32_t)n_sm;   // measured crossover with the lane-per-set kernels: ~1 000 sets
     constexpr uint32_t GW_WPB = 4;
     const size_t gw_smem = gw::smem_bytes(GW_WPB);
     if (g2_warp) {   // working sets + a shared-memory copy of the phase tables: above the 48 KB default
