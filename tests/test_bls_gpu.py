@@ -388,6 +388,27 @@ def test_every_key_aggregation_variant(bls):
         assert not ok and st[7] != 0 and not np.delete(st, 7).any()
 
 
+def test_latency_and_lane_modes_agree(bls):
+    """Small batches run on the warp-per-item kernels, large ones on the lane-per-set kernels; the selection
+    switches are read once per process, so scripts/mode_probe.py runs in two subprocesses: same verdicts, same statuses and
+    the SAME GT BYTES (the value after the final exponentiation is unique) from both families of kernels."""
+    import os
+    import subprocess
+    import sys
+    probe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "mode_probe.py")
+
+    def run(extra):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, probe], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [l for l in out.stdout.splitlines() if l.split()[0] in ("valid", "swapped", "negated", "infinity")]
+
+    fast = run({})
+    lane = run({"LHB_G2_WARP": "0", "LHB_MILLER_WARP": "0", "LHB_FINAL_WARP": "0"})
+    assert fast == lane and len(fast) == 4
+    assert fast[0].split()[1] == "True" and all(l.split()[1] == "False" for l in fast[1:])
+
+
 def test_block_signature_batch_shape(bls):
     """BASELINE configs[3] shape at reduced scale: the sets BlockSignatureVerifier::include_all_signatures collects
     for consecutive blocks (block_signature_verifier.rs:141-393) — 1-key sets (proposal, randao, exits,
