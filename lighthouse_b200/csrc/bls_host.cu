@@ -68,6 +68,7 @@ struct lhb200_bls_batch {
     cudaEvent_t e_h2c = nullptr, e_sig = nullptr;
     cudaEvent_t e_fork = nullptr, e_join = nullptr;
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around the dominant kernel (k_miller_multi), for the roofline
+    cudaEvent_t e_done = nullptr;                // cudaEventBlockingSync: the host wait of long steps
     uint64_t launches_last = 0;
     // cooperative Miller kernel (bls/miller_coop.cuh): parking area for T / Q between rounds, the -g1 argument
     uint32_t* d_mc_scratch = nullptr;
@@ -109,6 +110,7 @@ static void batch_free(lhb200_bls_batch* b) {
     if (b->e_join) cudaEventDestroy(b->e_join);
     if (b->e_k0) cudaEventDestroy(b->e_k0);
     if (b->e_k1) cudaEventDestroy(b->e_k1);
+    if (b->e_done) cudaEventDestroy(b->e_done);
     for (cudaStream_t st : b->s_pk)
         if (st) cudaStreamDestroy(st);
     for (cudaEvent_t e : b->e_pk)
@@ -122,6 +124,7 @@ constexpr uint32_t REDUCE_CHUNK = 8;
 // latency modes of the per-set stages (batches that do not fill the GPU): slice-parallel key sums, two threads per hash
 constexpr uint32_t PK_SPLIT_MAX_SETS = 8192;
 constexpr uint32_t HASH_PAIR_MAX_SETS = 4096;
+constexpr uint32_t BLOCKING_WAIT_MIN_SETS = 16384;   // lhb200_bls_batch_result: blocking wait for steps of >= ~15 ms
 
 // ---- pool of batch handles behind lhb200_verify_signature_sets -------------------------------------------------
 namespace {
@@ -219,6 +222,7 @@ int32_t lhb200_bls_batch_create(uint32_t max_sets, uint64_t max_keys, lhb200_bls
         (e = cudaEventCreateWithFlags(&b->e_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_join, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&b->e_k0)) != cudaSuccess || (e = cudaEventCreate(&b->e_k1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->e_done, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_small, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&b->e_copy_free, cudaEventDisableTiming)) != cudaSuccess) {
         batch_free(b);
@@ -816,7 +820,15 @@ int32_t lhb200_bls_batch_result(lhb200_bls_batch* b, void* stream, uint8_t* ok, 
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx().stream;
     LHB_CUDA(cudaMemcpyAsync(b->h_res, b->d_ok, 1, cudaMemcpyDeviceToHost, s));
     if (set_status) LHB_CUDA(cudaMemcpyAsync(b->h_res + 64, b->d_status, b->n, cudaMemcpyDeviceToHost, s));
-    LHB_CUDA(cudaStreamSynchronize(s));
+    if (b->n >= BLOCKING_WAIT_MIN_SETS && b->e_done) {
+        // a long step: sleep on a blocking event instead of spinning in cudaStreamSynchronize — with one process per GPU
+        // on a shared host (8 ranks + NCCL proxies under one cgroup CPU quota) eight spinning threads get throttled and
+        // the next step's launches start late; the ~30 us wake-up is noise against tens of milliseconds
+        LHB_CUDA(cudaEventRecord(b->e_done, s));
+        LHB_CUDA(cudaEventSynchronize(b->e_done));
+    } else {
+        LHB_CUDA(cudaStreamSynchronize(s));
+    }
     *ok = b->h_res[0];
     if (set_status) memcpy(set_status, b->h_res + 64, b->n);
     return LHB200_OK;
