@@ -123,7 +123,8 @@ static void batch_free(lhb200_bls_batch* b) {
 constexpr uint32_t REDUCE_CHUNK = 8;
 // latency modes of the per-set stages (batches that do not fill the GPU): slice-parallel key sums, two threads per hash
 constexpr uint32_t PK_SPLIT_MAX_SETS = 8192;
-constexpr uint32_t HASH_PAIR_MAX_SETS = 4096;
+constexpr uint32_t HASH_PAIR_MAX_SETS = 4096;    // (measured: 10 000 sets 16.4 ms with the plain kernel, 17.6 ms with the paired one)
+constexpr uint32_t FINAL_WARP_TAIL = 160;             // Miller block products k_final_warp takes directly (one per SM + slack)
 constexpr uint32_t BLOCKING_WAIT_MIN_SETS = 16384;   // lhb200_bls_batch_result: blocking wait for steps of >= ~15 ms
 
 // ---- pool of batch handles behind lhb200_verify_signature_sets -------------------------------------------------
@@ -744,7 +745,10 @@ int32_t lhb200_bls_batch_verify_enqueue(lhb200_bls_batch* b, void* stream) {
         launches += 1;
         uint32_t m = mgrid;   // the kernel multiplies groups and warps together: one value per block
         int flip = 0;
-        while (m > COOP_TAIL) {
+        // k_final_warp folds the block products itself (8 warps x ~19 products of 7 us): no single-thread product level
+        static const int fw_env = [] { const char* e = getenv("LHB_FINAL_WARP"); return e ? atoi(e) : 1; }();
+        const uint32_t tail_max = fw_env ? FINAL_WARP_TAIL : COOP_TAIL;
+        while (m > tail_max) {
             const uint32_t mo = cdiv(m, REDUCE_CHUNK);
             k_fp12_reduce<<<cdiv(mo, BLS_BLOCK), BLS_BLOCK, 0, s>>>(cur, m, REDUCE_CHUNK, b->d_f_tmp[flip]);
             launches++;
