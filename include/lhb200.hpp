@@ -51,13 +51,46 @@ class PublicKey {
         std::memcpy(pk.compressed_.data(), bytes, 48);
         return pk;
     }
+    /// TPublicKey::deserialize_uncompressed (blst.rs:142-150; generic_public_key.rs:96-102): curve check, no subgroup
+    /// check, infinity rejected like deserialize.
+    static PublicKey deserialize_uncompressed(const uint8_t* bytes, size_t len) {
+        if (len != PUBLIC_KEY_UNCOMPRESSED_BYTES_LEN) throw Error(LHB200_EINVAL, "InvalidByteLength");
+        PublicKey pk;
+        uint8_t st = 0;
+        check(lhb200_g1_deserialize_uncompressed(bytes, 1, pk.compressed_.data(), &st), "lhb200_g1_deserialize_uncompressed");
+        if (st == 1) throw Error(LHB200_EDECODE, "InvalidInfinityPublicKey");
+        if (st != 0) throw Error(LHB200_EDECODE, "BlstError(bad G1 encoding)");
+        std::memcpy(pk.uncompressed_.data(), bytes, 96);
+        return pk;
+    }
     const std::array<uint8_t, 48>& serialize() const { return compressed_; }
     const std::array<uint8_t, 96>& serialize_uncompressed() const { return uncompressed_; }
     bool operator==(const PublicKey& o) const { return compressed_ == o.compressed_; }
 
   private:
+    friend class AggregatePublicKey;
     std::array<uint8_t, 48> compressed_{};
     std::array<uint8_t, 96> uncompressed_{};
+};
+
+/// GenericAggregatePublicKey::aggregate (generic_aggregate_public_key.rs:9-15, blst.rs:178-184): the sum of validated
+/// keys; an empty list is an error, an infinite sum is reported like the reference's `InvalidInfinityPublicKey`.
+class AggregatePublicKey {
+  public:
+    static AggregatePublicKey aggregate(const std::vector<const PublicKey*>& pks) {
+        if (pks.empty()) throw Error(LHB200_EINVAL, "EmptyAggregate");
+        std::vector<uint8_t> flat;
+        for (const PublicKey* pk : pks) flat.insert(flat.end(), pk->uncompressed_.begin(), pk->uncompressed_.end());
+        AggregatePublicKey a;
+        check(lhb200_g1_aggregate(flat.data(), static_cast<uint32_t>(pks.size()), a.pk_.compressed_.data(),
+                                  a.pk_.uncompressed_.data()), "lhb200_g1_aggregate");
+        if (a.pk_.compressed_[0] & 0x40) throw Error(LHB200_EDECODE, "InvalidInfinityPublicKey");
+        return a;
+    }
+    const PublicKey& to_public_key() const { return pk_; }
+
+  private:
+    PublicKey pk_;
 };
 
 /// GenericSignature / GenericAggregateSignature: canonical bytes; all-zero = the "empty" signature (point None).
@@ -95,11 +128,52 @@ class Signature {
   private:
     std::array<uint8_t, 96> bytes_{};
 };
-using AggregateSignature = Signature;
+struct SignatureSet;
+/// GenericAggregateSignature (generic_aggregate_signature.rs:60-235): a Signature that can absorb others.
+/// add_assign / add_assign_aggregate are point additions on the device (blst.rs:230-237); the infinity encoding is the
+/// identity and the "empty" (all-zero) aggregate takes the value of the first signature added (:111-124).
+class AggregateSignature : public Signature {
+  public:
+    AggregateSignature() : Signature(Signature::infinity()) {}
+    explicit AggregateSignature(const Signature& s) : Signature(s) {}
+    static AggregateSignature deserialize(const uint8_t* bytes, size_t len) {
+        return AggregateSignature(Signature::deserialize(bytes, len));
+    }
+    void add_assign(const Signature& other) {
+        if (other.is_empty()) return;
+        if (is_empty()) { static_cast<Signature&>(*this) = other; return; }
+        uint8_t two[192], out[96];
+        std::memcpy(two, serialize().data(), 96);
+        std::memcpy(two + 96, other.serialize().data(), 96);
+        check(lhb200_g2_aggregate(two, 2, out), "lhb200_g2_aggregate");
+        static_cast<Signature&>(*this) = Signature::deserialize(out, 96);
+    }
+    void add_assign_aggregate(const AggregateSignature& other) { add_assign(other); }
+    /// AggregateSignature::aggregate of many signatures in ONE device call
+    static AggregateSignature aggregate(const std::vector<const Signature*>& sigs) {
+        std::vector<uint8_t> flat;
+        for (const Signature* s : sigs)
+            if (!s->is_empty()) flat.insert(flat.end(), s->serialize().begin(), s->serialize().end());
+        uint8_t out[96];
+        check(lhb200_g2_aggregate(flat.empty() ? nullptr : flat.data(), static_cast<uint32_t>(flat.size() / 96), out),
+              "lhb200_g2_aggregate");
+        return AggregateSignature(Signature::deserialize(out, 96));
+    }
+    /// aggregate_verify (generic_aggregate_signature.rs:212-235, blst.rs:263-273): distinct messages, one key each
+    bool aggregate_verify(const std::vector<Hash256>& msgs, const std::vector<const PublicKey*>& pks) const {
+        if (msgs.empty() || msgs.size() != pks.size() || is_empty()) return false;
+        std::vector<uint8_t> m, k;
+        for (const Hash256& h : msgs) m.insert(m.end(), h.begin(), h.end());
+        for (const PublicKey* pk : pks) k.insert(k.end(), pk->serialize_uncompressed().begin(), pk->serialize_uncompressed().end());
+        uint8_t ok = 0;
+        const int32_t rc = lhb200_aggregate_verify(serialize().data(), m.data(), k.data(), static_cast<uint32_t>(msgs.size()), &ok);
+        return rc == LHB200_OK && ok == 1;
+    }
+};
 
 /// GenericSignatureSet {signature, signing_keys, message} — borrows, like the Cow<'a, ..> fields of the reference.
 struct SignatureSet {
-    const Signature* signature;
+    const Signature* signature;   // a Signature or an AggregateSignature (GenericSignatureSet holds the aggregate form)
     std::vector<const PublicKey*> signing_keys;
     Hash256 message;
     static SignatureSet single_pubkey(const Signature& s, const PublicKey& pk, const Hash256& m) {
@@ -134,11 +208,11 @@ inline bool verify_signature_sets(It begin, It end) {
 inline bool SignatureSet::verify() const { return verify_signature_sets(this, this + 1); }
 
 /// fast_aggregate_verify / eth_fast_aggregate_verify (generic_aggregate_signature.rs:187-210)
-inline bool fast_aggregate_verify(const AggregateSignature& sig, const Hash256& msg, const std::vector<const PublicKey*>& pks) {
+inline bool fast_aggregate_verify(const Signature& sig, const Hash256& msg, const std::vector<const PublicKey*>& pks) {
     if (pks.empty()) return false;
     return SignatureSet::multiple_pubkeys(sig, pks, msg).verify();
 }
-inline bool eth_fast_aggregate_verify(const AggregateSignature& sig, const Hash256& msg, const std::vector<const PublicKey*>& pks) {
+inline bool eth_fast_aggregate_verify(const Signature& sig, const Hash256& msg, const std::vector<const PublicKey*>& pks) {
     if (pks.empty() && sig.is_infinity()) return true;
     return fast_aggregate_verify(sig, msg, pks);
 }
@@ -190,6 +264,13 @@ inline Hash256 mix_in_length(const Hash256& root, uint64_t length) {
 inline Hash256 beacon_state_root_deneb(const uint8_t* ssz, size_t len) {
     Hash256 out;
     check(lhb200_beacon_state_root_deneb(ssz, len, out.data(), nullptr), "lhb200_beacon_state_root_deneb");
+    return out;
+}
+
+/// the same for any post-Altair fork id (LHB200_FORK_ALTAIR .. LHB200_FORK_DENEB; beacon_state.rs:224-571)
+inline Hash256 beacon_state_root(const uint8_t* ssz, size_t len, int32_t fork) {
+    Hash256 out;
+    check(lhb200_beacon_state_root(ssz, len, fork, out.data(), nullptr), "lhb200_beacon_state_root");
     return out;
 }
 

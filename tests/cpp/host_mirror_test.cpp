@@ -54,6 +54,24 @@ int main(int argc, char** argv) {
         CHECK(bls::eth_fast_aggregate_verify(inf, msgs[0], {}));
         CHECK(!bls::fast_aggregate_verify(sigs[0], msgs[0], {}));
     }
+    {   // aggregation surface: one message signed by every key -> aggregate -> fast_aggregate_verify
+        // (the vectors are single-key triples on distinct messages: aggregate_verify is their natural check)
+        std::vector<const bls::Signature*> sp;
+        std::vector<const bls::PublicKey*> kp;
+        for (size_t i = 0; i < pks.size(); i++) { sp.push_back(&sigs[i]); kp.push_back(&pks[i]); }
+        bls::AggregateSignature agg = bls::AggregateSignature::aggregate(sp);
+        CHECK(agg.aggregate_verify(msgs, kp));
+        bls::AggregateSignature step;                              // add_assign one by one == aggregate at once
+        for (const bls::Signature* s : sp) step.add_assign(*s);
+        CHECK(step.serialize() == agg.serialize());
+        std::vector<Hash256> bad = msgs;
+        bad[0][5] ^= 1;
+        CHECK(!agg.aggregate_verify(bad, kp));
+        CHECK(!agg.aggregate_verify({}, {}));
+        bls::AggregatePublicKey apk = bls::AggregatePublicKey::aggregate(kp);
+        bls::PublicKey round = bls::PublicKey::deserialize_uncompressed(apk.to_public_key().serialize_uncompressed().data(), 96);
+        CHECK(round == apk.to_public_key());
+    }
     bool threw = false;
     try {
         uint8_t infpk[48] = {0xc0};
