@@ -30,6 +30,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before torch creates the CUDA context (see lhb200_init)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -350,6 +352,29 @@ def run_ours(args):
             gossip[label] = {"latency_ms_resident": msg_, "latency_ms_e2e": msg_e2e, "launches": int(bg.launches)}
             bg.destroy()
         cfg0["gossip_batch"] = gossip
+        # ... and the same from several blocking workers at once (beacon_processor/src/lib.rs:256): throughput of the boundary
+        conc = {}
+        gb = [S.attestation_batch(64, keys_per_set=1, n_validators=N_VALIDATORS_BLS, seed=SEED_CFG0 + 100 + t, pk_table=pk_table)
+              for t in range(16)]
+        for T_ in (8, 16):
+            def one(t):
+                return bls.verify_signature_sets_raw(gb[t].sigs, gb[t].msgs, gb[t].pks, gb[t].offsets)
+            warm = [threading.Thread(target=one, args=(t,)) for t in range(T_)]
+            [w.start() for w in warm]; [w.join() for w in warm]
+            counts, t_end = [0] * T_, time.perf_counter() + 1.0
+
+            def work(t):
+                while time.perf_counter() < t_end:
+                    assert one(t)
+                    counts[t] += 1
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(t,)) for t in range(T_)]
+            [x.start() for x in th]; [x.join() for x in th]
+            dt = time.perf_counter() - t0
+            conc[f"{T_}_workers"] = {"batches_per_s": sum(counts) / dt, "sets_per_s": sum(counts) * 64 / dt,
+                                     "mean_latency_ms": dt * T_ / max(sum(counts), 1) * 1e3}
+        cfg0["gossip_concurrent"] = {"workload": "T host threads, each verifying its own 64-set x 1-key batch through "
+                                                 "lhb200_verify_signature_sets back to back (pooled handles)", **conc}
 
     # ------------------------------------------------------------------ tree-hash workload (per rank)
     ssz = S.beacon_state_deneb_ssz(N_VALIDATORS_STATE, seed=42 + rank)

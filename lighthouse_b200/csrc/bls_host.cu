@@ -131,7 +131,7 @@ constexpr uint32_t BLOCKING_WAIT_MIN_SETS = 16384;   // lhb200_bls_batch_result:
 namespace {
 std::mutex g_pool_mu;
 std::vector<lhb200_bls_batch*> g_pool_free;
-constexpr size_t POOL_MAX_IDLE = 16;
+constexpr size_t POOL_MAX_IDLE = 64;   // idle handles kept (a 64-set handle is ~0.5 MB of device memory)
 
 lhb200_bls_batch* pool_acquire(uint32_t n_sets, uint64_t n_keys) {
     lhb200_bls_batch* b = nullptr;

@@ -1,6 +1,7 @@
 // lib.cu — lifecycle and error plumbing of liblhb200.so.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "ctx.h"
 
 namespace lhb200 {
@@ -83,6 +84,11 @@ int32_t lhb200_init(int32_t device) {
         set_error("already initialised on device %d (one process per GPU)", c.device);
         return LHB200_EINVAL;
     }
+    // Every verify call drives three streams of its own handle; with the default 8 hardware work queues the streams of
+    // concurrent callers alias and serialise (8 gossip workers: 830 batches/s; with 32 queues: 1 350, and 2 140 from 16
+    // workers — profiles/r2_gossip_concurrency.jsonl).  Read by the driver when the context is created, so it only takes
+    // effect if this is the process's first CUDA call (a host that creates the context earlier sets it itself).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
