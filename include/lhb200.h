@@ -89,6 +89,7 @@ LHB200_API int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t l
 #define LHB200_FORK_BELLATRIX 2
 #define LHB200_FORK_CAPELLA 3
 #define LHB200_FORK_DENEB 4
+#define LHB200_FORK_ELECTRA 5   /* 37 fields (19-field header, six u64s, three pending_* lists): field_roots is 37 x 32 B */
 LHB200_API int32_t lhb200_beacon_state_root(const uint8_t* ssz, uint64_t len, int32_t fork, uint8_t out[32],
                                             uint8_t* field_roots);
 LHB200_API int32_t lhb200_state_stage(const uint8_t* ssz, uint64_t len, int32_t fork, struct lhb200_state** out);

@@ -267,7 +267,7 @@ inline Hash256 beacon_state_root_deneb(const uint8_t* ssz, size_t len) {
     return out;
 }
 
-/// the same for any post-Altair fork id (LHB200_FORK_ALTAIR .. LHB200_FORK_DENEB; beacon_state.rs:224-571)
+/// the same for any post-Altair fork id (LHB200_FORK_ALTAIR .. LHB200_FORK_ELECTRA; beacon_state.rs:224-571)
 inline Hash256 beacon_state_root(const uint8_t* ssz, size_t len, int32_t fork) {
     Hash256 out;
     check(lhb200_beacon_state_root(ssz, len, fork, out.data(), nullptr), "lhb200_beacon_state_root");

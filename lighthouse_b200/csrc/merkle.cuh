@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(VAL_PER_CTA) k_validator_roots(const uint8_t* 
 
 // ---------------------------------------------------------------------------------------------
 // Small fixed-size records -> roots.  kind 0: 48-byte pubkey.  kind 1: 72-byte Eth1Data {H256,u64,H256}.
+// kind 2: 16-byte {u64, u64} (PendingBalanceDeposit, PendingConsolidation).  kind 3: 24-byte {u64, u64, u64}
+// (PendingPartialWithdrawal): the Electra state lists, beacon_state.rs:515-525.
 __global__ void __launch_bounds__(128) k_record_roots(const uint8_t* __restrict__ in, uint64_t n, int kind,
                                                       uint8_t* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,6 +128,19 @@ __global__ void __launch_bounds__(128) k_record_roots(const uint8_t* __restrict_
         for (int k = 0; k < 4; k++) b[k] = be_word(p + 32 + 4 * k);
         b[4] = b[5] = b[6] = b[7] = 0;
         hash_pair(a, b, a);
+    } else if (kind == 2 || kind == 3) {
+        const uint8_t* p = in + (kind == 2 ? 16 : 24) * i;
+        for (int k = 0; k < 8; k++) a[k] = b[k] = 0;
+        le64_words(p, a[0], a[1]);
+        le64_words(p + 8, b[0], b[1]);
+        hash_pair(a, b, a);                       // H(field 0, field 1)
+        if (kind == 3) {
+            uint32_t c[8];
+            for (int k = 0; k < 8; k++) c[k] = b[k] = 0;
+            le64_words(p + 16, c[0], c[1]);
+            hash_pair(c, b, c);                   // H(field 2, zero chunk)
+            hash_pair(a, c, a);
+        }
     } else {
         const uint8_t* p = in + 72 * i;
         uint32_t c[8];

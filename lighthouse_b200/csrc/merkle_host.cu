@@ -210,7 +210,7 @@ struct Plan {
     uint8_t* leaf_kernel(int kind, const uint8_t* in, uint64_t n) {
         uint8_t* out = alloc(std::max<uint64_t>(n, 1) * 32);
         if (n) leaves.push_back({kind, in, out, n});
-        static const int units[4] = {8, 1, 3, 1};
+        static const int units[6] = {8, 1, 3, 1, 1, 3};
         hash_units += (uint64_t)units[kind] * n;
         return out;
     }
@@ -231,6 +231,12 @@ static int32_t plan_enqueue(Plan& pl, cudaStream_t s, cudaEvent_t e0 = nullptr, 
                 break;
             case 2:
                 k_record_roots<<<(unsigned)ceil_div(L.n, 128), 128, 0, s>>>(L.in, L.n, 1, L.out);
+                break;
+            case 4:
+                k_record_roots<<<(unsigned)ceil_div(L.n, 128), 128, 0, s>>>(L.in, L.n, 2, L.out);
+                break;
+            case 5:
+                k_record_roots<<<(unsigned)ceil_div(L.n, 128), 128, 0, s>>>(L.in, L.n, 3, L.out);
                 break;
             default:
                 k_hash_pairs<<<(unsigned)ceil_div(L.n, 256), 256, 0, s>>>(L.in, L.out, L.n);
@@ -423,7 +429,8 @@ constexpr uint32_t O_GENESIS_TIME = 0, O_GVR = 8, O_SLOT = 40, O_FORK = 48, O_LB
                    O_DEPOSIT_INDEX = 524544, O_VAL_OFF = 524552, O_BAL_OFF = 524556, O_RANDAO = 524560,
                    O_SLASHINGS = 2621712, O_PP_OFF = 2687248, O_CP_OFF = 2687252, O_JUST = 2687256,
                    O_PJC = 2687257, O_CJC = 2687297, O_FC = 2687337, O_INACT_OFF = 2687377, O_CSC = 2687381,
-                   O_NSC = 2712005, O_LEPH_OFF = 2736629, O_NWI = 2736633, O_NWVI = 2736641, O_HS_OFF = 2736649;
+                   O_NSC = 2712005, O_LEPH_OFF = 2736629, O_NWI = 2736633, O_NWVI = 2736641, O_HS_OFF = 2736649,
+                   O_ELECTRA_U64 = 2736653, O_PBD_OFF = 2736701, O_PPW_OFF = 2736705, O_PC_OFF = 2736709;
 constexpr uint32_t SYNC_COMMITTEE_BYTES = 513 * 48;
 }  // namespace deneb
 
@@ -447,7 +454,7 @@ struct ShardCfg {
     int32_t fork = LHB200_FORK_DENEB;   // which BeaconState variant the SSZ is (fork_spec)
 };
 struct ShardedList {
-    int field;            // index in the 28-field container
+    int field;            // index in the state container
     uint32_t s;           // height of the per-rank subtree
     uint32_t limit_depth; // chunk-tree depth of the list limit
     uint64_t mix_len;     // length to mix in (lists); UINT64_MAX = vector (no mix-in)
@@ -472,9 +479,9 @@ struct lhb200_state {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     lhb200::Plan plan;
-    uint64_t field_ops[28];
+    uint64_t field_ops[40];   // MAX_FIELDS (declared below) rounded up
     uint64_t root_op = 0;
-    uint8_t* d_result = nullptr;  // 29 * 32 bytes: root + field roots gathered
+    uint8_t* d_result = nullptr;  // (1 + MAX_FIELDS) * 32 bytes: root + field roots gathered
     cudaEvent_t e_k0 = nullptr, e_k1 = nullptr;  // around k_validator_roots
     lhb200::ShardCfg shard;
     std::vector<lhb200::ShardedList> sharded;
@@ -512,8 +519,9 @@ namespace lhb200 {
 //              historical_summaries                                             2 736 653 B
 //   Deneb      header + blob_gas_used, excess_blob_gas (17 fields, 584 B)       2 736 653 B
 // so one describer covers them all; the kernels are fork-agnostic.
+constexpr int MAX_FIELDS = 37;   // BeaconStateElectra; the field-root block of a handle is root + MAX_FIELDS chunks
 struct ForkSpec {
-    int n_fields;        // 24 / 25 / 28 / 28
+    int n_fields;        // 24 / 25 / 28 / 28 / 37
     uint32_t fixed;      // bytes of the fixed part
     uint32_t hdr_fixed;  // fixed part of the execution payload header (0: no header)
     int hdr_fields;
@@ -524,12 +532,13 @@ static bool fork_spec(int32_t fork, ForkSpec* f) {
         case LHB200_FORK_BELLATRIX: *f = {25, 2736633, 536, 14}; return true;
         case LHB200_FORK_CAPELLA: *f = {28, 2736653, 568, 15}; return true;
         case LHB200_FORK_DENEB: *f = {28, 2736653, 584, 17}; return true;
+        case LHB200_FORK_ELECTRA: *f = {37, 2736713, 648, 19}; return true;
     }
     return false;
 }
 
 static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vector<StageCopy>* copies,
-                              uint64_t field_ops[28], uint64_t* root_op, ShardCfg sh = ShardCfg(),
+                              uint64_t* field_ops, uint64_t* root_op, ShardCfg sh = ShardCfg(),
                               std::vector<ShardedList>* sharded = nullptr) {
     using namespace deneb;
     ForkSpec fk;
@@ -540,17 +549,23 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
                    o_bal = rd32(s + O_BAL_OFF), o_pp = rd32(s + O_PP_OFF), o_cp = rd32(s + O_CP_OFF),
                    o_inact = rd32(s + O_INACT_OFF);
     const uint32_t o_leph = fk.hdr_fields ? rd32(s + O_LEPH_OFF) : (uint32_t)len;
-    const uint32_t o_hs = fk.n_fields == 28 ? rd32(s + O_HS_OFF) : (uint32_t)len;
+    const uint32_t o_hs = fk.n_fields >= 28 ? rd32(s + O_HS_OFF) : (uint32_t)len;
+    const bool electra = fk.n_fields == 37;
+    const uint32_t o_pbd = electra ? rd32(s + O_PBD_OFF) : (uint32_t)len, o_ppw = electra ? rd32(s + O_PPW_OFF) : (uint32_t)len,
+                   o_pc = electra ? rd32(s + O_PC_OFF) : (uint32_t)len;
     if (o_hist != FIXED || !(o_hist <= o_votes && o_votes <= o_val && o_val <= o_bal && o_bal <= o_pp &&
-                             o_pp <= o_cp && o_cp <= o_inact && o_inact <= o_leph && o_leph <= o_hs && o_hs <= len)) {
+                             o_pp <= o_cp && o_cp <= o_inact && o_inact <= o_leph && o_leph <= o_hs && o_hs <= o_pbd &&
+                             o_pbd <= o_ppw && o_ppw <= o_pc && o_pc <= len)) {
         set_error("BeaconState SSZ: inconsistent variable-part offsets");
         return LHB200_EINVAL;
     }
     const uint64_t n_hist = (o_votes - o_hist) / 32, n_votes = (o_val - o_votes) / 72, n_val = (o_bal - o_val) / 121,
                    n_bal = (o_pp - o_bal) / 8, n_pp = o_cp - o_pp, n_cp = o_inact - o_cp,
-                   n_inact = (o_leph - o_inact) / 8, leph_len = o_hs - o_leph, n_hs = (len - o_hs) / 64;
+                   n_inact = (o_leph - o_inact) / 8, leph_len = o_hs - o_leph, n_hs = (o_pbd - o_hs) / 64,
+                   n_pbd = (o_ppw - o_pbd) / 16, n_ppw = (o_pc - o_ppw) / 24, n_pc = (len - o_pc) / 16;
     if ((o_votes - o_hist) % 32 || (o_val - o_votes) % 72 || (o_bal - o_val) % 121 || (o_pp - o_bal) % 8 ||
-        (o_leph - o_inact) % 8 || (len - o_hs) % 64 ||
+        (o_leph - o_inact) % 8 || (o_pbd - o_hs) % 64 || (o_ppw - o_pbd) % 16 || (o_pc - o_ppw) % 24 || (len - o_pc) % 16 ||
+        n_pbd > (1u << 27) || n_ppw > (1u << 27) || n_pc > (1u << 18) ||
         (fk.hdr_fields && (leph_len < fk.hdr_fixed || leph_len > fk.hdr_fixed + 32 || rd32(s + o_leph + 436) != fk.hdr_fixed)) ||
         n_votes > 2048 || n_hist > (1u << 24) || n_hs > (1u << 24)) {
         set_error("BeaconState SSZ: malformed variable part");
@@ -652,14 +667,21 @@ static int32_t describe_deneb(Plan& p, const uint8_t* s, uint64_t len, std::vect
                                     p.literal(h + 440), p.literal(h + 472), p.literal(h + 504)};
         if (fk.hdr_fields >= 15) hf.push_back(p.literal(h + 536));                       // withdrawals_root (Capella)
         if (fk.hdr_fields >= 17) { hf.push_back(p.literal_bytes(h + 568, 8)); hf.push_back(p.literal_bytes(h + 576, 8)); }
+        if (fk.hdr_fields >= 19) { hf.push_back(p.literal(h + 584)); hf.push_back(p.literal(h + 616)); }   // request roots (Electra)
         f[24] = p.container(hf);
     }
-    if (fk.n_fields == 28) {
+    if (fk.n_fields >= 28) {
         f[25] = p.literal_bytes(s + O_NWI, 8);
         f[26] = p.literal_bytes(s + O_NWVI, 8);
         f[27] = p.mix_in_length(p.merkle_list(p.leaf_kernel(3, place(o_hs, n_hs * 64), n_hs), n_hs, 24), n_hs);
     }
-    for (int k = fk.n_fields; k < 28; k++) f[k] = Plan::zero_op(0);   // absent in this fork (not part of its container)
+    if (electra) {   // beacon_state.rs:487-525
+        for (int k = 0; k < 6; k++) f[28 + k] = p.literal_bytes(s + O_ELECTRA_U64 + 8 * k, 8);
+        f[34] = p.mix_in_length(p.merkle_list(p.leaf_kernel(4, place(o_pbd, n_pbd * 16), n_pbd), n_pbd, 27), n_pbd);
+        f[35] = p.mix_in_length(p.merkle_list(p.leaf_kernel(5, place(o_ppw, n_ppw * 24), n_ppw), n_ppw, 27), n_ppw);
+        f[36] = p.mix_in_length(p.merkle_list(p.leaf_kernel(4, place(o_pc, n_pc * 16), n_pc), n_pc, 18), n_pc);
+    }
+    for (int k = fk.n_fields; k < MAX_FIELDS; k++) f[k] = Plan::zero_op(0);   // absent in this fork (not part of its container)
     *root_op = p.container(std::vector<uint64_t>(f, f + fk.n_fields));
     return LHB200_OK;
 }
@@ -819,13 +841,13 @@ static int32_t stage_deneb(const uint8_t* ssz, uint64_t len, ShardCfg sh, lhb200
     std::lock_guard<std::recursive_mutex> g(c.mu);
     const size_t lit_cap = 16384;
     Plan dry;
-    uint64_t fops[28], rop;
+    uint64_t fops[MAX_FIELDS], rop;
     int32_t rc = LHB200_OK;
     std::vector<ShardedList> dry_sh;
     build_plan(dry, nullptr, 0, lit_cap, [&](Plan& p) { rc = describe_deneb(p, ssz, len, nullptr, fops, &rop, sh, &dry_sh); });
     if (rc) return rc;
     size_t prog = align_up(dry.ops.size() * sizeof(HashOp), 256) + align_up((dry.ops.size() + 2) * 4, 256) + 512;
-    size_t need = align_up(dry.bump, 256) + prog + 29 * 32 + 29 * sizeof(HashOp) + 1024;
+    size_t need = align_up(dry.bump, 256) + prog + (1 + MAX_FIELDS) * 32 + (1 + MAX_FIELDS) * sizeof(HashOp) + 1024;
     std::unique_ptr<lhb200_state> st(new lhb200_state());
     if (g_spare_arena && g_spare_bytes >= need) {       // recycled from the last released handle (no cudaMalloc)
         st->arena = g_spare_arena;
@@ -854,7 +876,7 @@ static int32_t stage_deneb(const uint8_t* ssz, uint64_t len, ShardCfg sh, lhb200
     std::vector<HashOp> ops_sorted;
     std::vector<int32_t> waves;
     plan_finalize_program(st->plan, ops_sorted, waves);
-    size_t stage_bytes = (pinned ? 0 : len) + lit_cap + prog + 29 * sizeof(HashOp) + 2048;
+    size_t stage_bytes = (pinned ? 0 : len) + lit_cap + prog + (1 + MAX_FIELDS) * sizeof(HashOp) + 2048;
     uint8_t* hst = static_cast<uint8_t*>(pinned_scratch(stage_bytes));
     if (!hst) { cudaFree(st->arena); return LHB200_ENOMEM; }
     size_t ho = 0;
@@ -871,14 +893,14 @@ static int32_t stage_deneb(const uint8_t* ssz, uint64_t len, ShardCfg sh, lhb200
     }
     rc = plan_upload(st->plan, c.stream, ops_sorted, waves, hst + ho);
     if (rc) { cudaFree(st->arena); return rc; }
-    // gather table: root + 28 field roots -> contiguous result block
-    HashOp gath[29];
+    // gather table: root + field roots -> contiguous result block
+    HashOp gath[1 + MAX_FIELDS];
     gath[0] = {0, st->root_op, 0};
-    for (int i = 0; i < 28; i++) gath[i + 1] = {0, st->field_ops[i], 0};
-    uint8_t* h_g = hst + stage_bytes - 29 * sizeof(HashOp) - 64;
+    for (int i = 0; i < MAX_FIELDS; i++) gath[i + 1] = {0, st->field_ops[i], 0};
+    uint8_t* h_g = hst + stage_bytes - (1 + MAX_FIELDS) * sizeof(HashOp) - 64;
     memcpy(h_g, gath, sizeof gath);
     uint8_t* d_g = st->plan.alloc(sizeof gath);
-    st->d_result = st->plan.alloc(29 * 32);
+    st->d_result = st->plan.alloc((1 + MAX_FIELDS) * 32);
     LHB_CUDA(cudaMemcpyAsync(d_g, h_g, sizeof gath, cudaMemcpyHostToDevice, c.stream));
     st->plan.root_addr = reinterpret_cast<uint64_t>(d_g);
     LHB_CUDA(cudaStreamSynchronize(c.stream));
@@ -940,7 +962,7 @@ static int32_t state_combine_impl(lhb200_state* st, const uint8_t* gathered, uin
     uint32_t lg = 0;
     while ((1u << lg) < world) lg++;
     return run_simple(gathered, (size_t)world * n * 32, out, [&](Plan& p, uint8_t* d_in) {
-        std::vector<uint64_t> f(st->field_ops, st->field_ops + 28);
+        std::vector<uint64_t> f(st->field_ops, st->field_ops + 28);   // (sharded handles are Deneb: 28 fields)
         for (uint32_t l = 0; l < n; l++) {
             const ShardedList& L = st->sharded[l];
             std::vector<uint64_t> nodes;
@@ -1289,7 +1311,7 @@ int32_t lhb200_state_root_enqueue(lhb200_state* st, void* stream, const void** d
         if (!rc && st->incremental) rc = state_build_levels(st, s);   // a cold root leaves the level arrays stale
     }
     if (rc) return rc;
-    k_gather_nodes<<<1, 32, 0, s>>>(reinterpret_cast<const HashOp*>(st->plan.root_addr), 29, st->d_result);
+    k_gather_nodes<<<1, 64, 0, s>>>(reinterpret_cast<const HashOp*>(st->plan.root_addr), 1 + MAX_FIELDS, st->d_result);
     count_launch();
     LHB_CUDA(cudaGetLastError());
     if (d_root) *d_root = st->d_result;
@@ -1303,12 +1325,13 @@ int32_t lhb200_state_root(lhb200_state* st, uint8_t out[32], uint8_t* field_root
     std::lock_guard<std::recursive_mutex> g(c.mu);
     int32_t rc = lhb200_state_root_enqueue(st, c.stream, nullptr);
     if (rc) return rc;
-    uint8_t* h = static_cast<uint8_t*>(pinned_scratch(29 * 32));
+    uint8_t* h = static_cast<uint8_t*>(pinned_scratch((1 + MAX_FIELDS) * 32));
     if (!h) return LHB200_ENOMEM;
-    LHB_CUDA(cudaMemcpyAsync(h, st->d_result, 29 * 32, cudaMemcpyDeviceToHost, c.stream));
+    LHB_CUDA(cudaMemcpyAsync(h, st->d_result, (1 + MAX_FIELDS) * 32, cudaMemcpyDeviceToHost, c.stream));
     LHB_CUDA(cudaStreamSynchronize(c.stream));
     memcpy(out, h, 32);
-    if (field_roots) memcpy(field_roots, h + 32, 28 * 32);
+    // 28 field roots for every fork up to Deneb (the unused tail is zero chunks), 37 for an Electra handle
+    if (field_roots) memcpy(field_roots, h + 32, (st->shard.fork == LHB200_FORK_ELECTRA ? MAX_FIELDS : 28) * 32);
     return LHB200_OK;
 }
 
@@ -1343,7 +1366,7 @@ int32_t lhb200_beacon_state_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t
     return lhb200_beacon_state_root(ssz, len, LHB200_FORK_DENEB, out, field_roots);
 }
 // BeaconState::update_tree_hash_cache for any post-Altair variant of the superstruct (beacon_state.rs:224-571).
-// field_roots (optional): 28 x 32 bytes; entries beyond the fork's field count are the zero chunk.
+// field_roots (optional): 28 x 32 bytes (entries beyond the fork's field count are the zero chunk); 37 x 32 for Electra.
 int32_t lhb200_beacon_state_root(const uint8_t* ssz, uint64_t len, int32_t fork, uint8_t out[32], uint8_t* field_roots) {
     LHB_REQUIRE_READY();
     lhb200_state* st = nullptr;

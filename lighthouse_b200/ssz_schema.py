@@ -164,8 +164,21 @@ _f = BeaconStateDeneb[1]
 BeaconStateAltair = C(*_f[:24])
 BeaconStateBellatrix = C(*(_f[:24] + [("latest_execution_payload_header", ExecutionPayloadHeaderBellatrix)]))
 BeaconStateCapella = C(*(_f[:24] + [("latest_execution_payload_header", ExecutionPayloadHeaderCapella)] + _f[25:]))
+# ---- Electra as in this revision of the reference (beacon_state.rs:487-525, execution_payload_header.rs:88-93,
+# pending_balance_deposit.rs:21, pending_partial_withdrawal.rs:22, pending_consolidation.rs:21; limits eth_spec.rs:433-435)
+ExecutionPayloadHeaderElectra = C(*(ExecutionPayloadHeaderDeneb[1] + [("deposit_requests_root", B32),
+                                                                     ("withdrawal_requests_root", B32)]))
+PendingBalanceDeposit = C(("index", U64), ("amount", U64))
+PendingPartialWithdrawal = C(("index", U64), ("amount", U64), ("withdrawable_epoch", U64))
+PendingConsolidation = C(("source_index", U64), ("target_index", U64))
+BeaconStateElectra = C(*(_f[:24] + [("latest_execution_payload_header", ExecutionPayloadHeaderElectra)] + _f[25:] + [
+    ("deposit_requests_start_index", U64), ("deposit_balance_to_consume", U64), ("exit_balance_to_consume", U64),
+    ("earliest_exit_epoch", U64), ("consolidation_balance_to_consume", U64), ("earliest_consolidation_epoch", U64),
+    ("pending_balance_deposits", ("list", PendingBalanceDeposit, 1 << 27)),
+    ("pending_partial_withdrawals", ("list", PendingPartialWithdrawal, 1 << 27)),
+    ("pending_consolidations", ("list", PendingConsolidation, 1 << 18))]))
 BEACON_STATE_BY_FORK = {"altair": BeaconStateAltair, "bellatrix": BeaconStateBellatrix, "capella": BeaconStateCapella,
-                        "deneb": BeaconStateDeneb}
+                        "deneb": BeaconStateDeneb, "electra": BeaconStateElectra}
 
 
 # BlindedBeaconBlock (beacon_block.rs:80; payload.rs BlindedPayload): the body carries the payload HEADER

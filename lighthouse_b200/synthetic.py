@@ -25,12 +25,14 @@ def validators_ssz(n, rng, pubkeys=None):
 
 
 def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots=758, n_votes=1024,
-                           n_summaries=600, extra_data_len=14, fork="deneb"):
-    """SSZ(BeaconState<fork>), mainnet preset; fork in altair / bellatrix / capella / deneb (beacon_state.rs:224-571: later
-    forks append fields and widen the execution payload header).  all_default=True leaves every non-validator field
-    zero so the ZERO_HASHES ladder paths are exercised."""
-    hdr_fixed = {"altair": 0, "bellatrix": 536, "capella": 568, "deneb": 584}[fork]
-    has_tail = fork in ("capella", "deneb")
+                           n_summaries=600, extra_data_len=14, fork="deneb", n_pending=(700, 333, 45)):
+    """SSZ(BeaconState<fork>), mainnet preset; fork in altair / bellatrix / capella / deneb / electra
+    (beacon_state.rs:224-571: later forks append fields and widen the execution payload header; n_pending = lengths of
+    Electra's pending_balance_deposits / pending_partial_withdrawals / pending_consolidations).  all_default=True leaves
+    every non-validator field zero so the ZERO_HASHES ladder paths are exercised."""
+    hdr_fixed = {"altair": 0, "bellatrix": 536, "capella": 568, "deneb": 584, "electra": 648}[fork]
+    has_tail = fork in ("capella", "deneb", "electra")
+    electra = fork == "electra"
     rng = np.random.default_rng(seed)
     V = n_validators
 
@@ -41,6 +43,7 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
 
     if all_default:
         n_hist_roots = n_votes = n_summaries = extra_data_len = 0
+        n_pending = (0, 0, 0)
     hist = rnd(32 * n_hist_roots)
     votes = rnd(72 * n_votes)
     vals = validators_ssz(V, rng)
@@ -56,11 +59,12 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
         inact = rng.integers(0, 64, size=V, dtype="<u8").tobytes()
         slash = rng.integers(0, 1 << 40, size=8192, dtype="<u8").tobytes()
     leph = (rnd(32) + rnd(20) + rnd(32) + rnd(32) + rnd(256) + rnd(32) + rnd(8) + rnd(8) + rnd(8) + rnd(8)
-            + struct.pack("<I", hdr_fixed) + rnd(32) + rnd(32) + rnd(32) + rnd(32) + rnd(8) + rnd(8))
+            + struct.pack("<I", hdr_fixed) + rnd(32) + rnd(32) + rnd(32) + rnd(32) + rnd(8) + rnd(8) + rnd(32) + rnd(32))
     leph = (leph[:hdr_fixed] + rnd(extra_data_len)) if hdr_fixed else b""
     assert len(leph) == (hdr_fixed + extra_data_len if hdr_fixed else 0)
     summ = rnd(64 * n_summaries) if has_tail else b""
-    fixed_len = DENEB_FIXED - (0 if has_tail else 20) - (0 if hdr_fixed else 4)
+    pend = [rnd(sz * n) if electra else b"" for sz, n in zip((16, 24, 16), n_pending)]
+    fixed_len = DENEB_FIXED - (0 if has_tail else 20) - (0 if hdr_fixed else 4) + (60 if electra else 0)
 
     o_hist = fixed_len
     o_votes = o_hist + len(hist)
@@ -71,6 +75,9 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
     o_inact = o_cp + len(cp)
     o_leph = o_inact + len(inact)
     o_hs = o_leph + len(leph)
+    o_pbd = o_hs + len(summ)
+    o_ppw = o_pbd + len(pend[0])
+    o_pc = o_ppw + len(pend[1])
     u32 = lambda x: struct.pack("<I", x)
     fixed = b"".join([
         rnd(8), rnd(32), rnd(8),                       # genesis_time, genesis_validators_root, slot
@@ -87,9 +94,10 @@ def beacon_state_deneb_ssz(n_validators, seed=1, all_default=False, n_hist_roots
         (vals[:48] * 1 if False else rnd(513 * 48)),   # current_sync_committee (512 pubkeys + aggregate)
         rnd(513 * 48),                                 # next_sync_committee
         (u32(o_leph) if hdr_fixed else b""), ((rnd(8) + rnd(8) + u32(o_hs)) if has_tail else b""),
+        ((rnd(48) + u32(o_pbd) + u32(o_ppw) + u32(o_pc)) if electra else b""),   # six u64s, three list offsets
     ])
     assert len(fixed) == fixed_len, len(fixed)
-    return b"".join([fixed, hist, votes, vals, bal, pp, cp, inact, leph, summ])
+    return b"".join([fixed, hist, votes, vals, bal, pp, cp, inact, leph, summ] + pend)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -116,19 +116,20 @@ def beacon_state_root_deneb(ssz, want_field_roots=False):
     return out.raw
 
 
-FORKS = {"altair": 1, "bellatrix": 2, "capella": 3, "deneb": 4}   # LHB200_FORK_*
+FORKS = {"altair": 1, "bellatrix": 2, "capella": 3, "deneb": 4, "electra": 5}   # LHB200_FORK_*
 
 
 def beacon_state_root(ssz, fork="deneb", want_field_roots=False):
     """BeaconState::update_tree_hash_cache (cold) for any post-Altair variant of the superstruct
     (consensus/types/src/beacon_state.rs:224-571): lhb200_beacon_state_root."""
     out = C.create_string_buffer(32)
-    fr = C.create_string_buffer(28 * 32) if want_field_roots else None
+    n_fr = 37 if fork == "electra" else 28
+    fr = C.create_string_buffer(n_fr * 32) if want_field_roots else None
     p, keep = buf(ssz)
     n = len(ssz) if isinstance(ssz, (bytes, bytearray)) else keep.nbytes
     check(lib.lhb200_beacon_state_root(p, n, FORKS[fork], out, fr), "lhb200_beacon_state_root")
     if want_field_roots:
-        return out.raw, [fr.raw[32 * i: 32 * i + 32] for i in range(28)]
+        return out.raw, [fr.raw[32 * i: 32 * i + 32] for i in range(n_fr)]
     return out.raw
 
 

@@ -308,7 +308,7 @@ def test_signing_root_and_domain_helpers(gpu):
     assert T.container_root(leaves) == O.merkleize(b"".join(leaves), 3)
 
 
-@pytest.mark.parametrize("fork", ["altair", "bellatrix", "capella", "deneb"])
+@pytest.mark.parametrize("fork", ["altair", "bellatrix", "capella", "deneb", "electra"])
 @pytest.mark.parametrize("nv,kw", [(0, {"all_default": True}), (37, {}), (1500, {"n_hist_roots": 3, "n_votes": 5, "n_summaries": 2})])
 def test_beacon_state_root_every_post_altair_fork(gpu, fork, nv, kw):
     """BeaconState superstruct variants (consensus/types/src/beacon_state.rs:224-571) through the fork-parametrised
@@ -327,8 +327,12 @@ def test_beacon_state_root_every_post_altair_fork(gpu, fork, nv, kw):
     assert root == ssz_spec.hash_tree_root(typ, value)
     if fork == "deneb":
         assert root == T.beacon_state_root_deneb(ssz)
+    if fork == "electra" and nv == 37:               # pending_* lists at other lengths, incl. empty and one element
+        for n_pending in ((0, 0, 0), (1, 1, 1), (4097, 2, 300)):
+            ssz2 = beacon_state_deneb_ssz(nv, seed=7, fork=fork, n_pending=n_pending)
+            assert T.beacon_state_root(ssz2, fork) == ssz_spec.hash_tree_root(typ, ssz_spec.deserialize(typ, ssz2)), n_pending
     # the wrong fork id must not silently produce a root of the same bytes' other interpretation
-    other = {"altair": "deneb", "bellatrix": "capella", "capella": "deneb", "deneb": "capella"}[fork]
+    other = {"altair": "deneb", "bellatrix": "capella", "capella": "deneb", "deneb": "capella", "electra": "deneb"}[fork]
     try:
         assert T.beacon_state_root(ssz, other) != root
     except Exception:
