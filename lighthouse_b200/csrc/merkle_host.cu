@@ -1487,7 +1487,9 @@ struct BlockDescriber {
     const uint8_t* s;
     const uint8_t* d;
     bool bad = false;
-    bool blinded = false;   // BlindedBeaconBlock: field 9 of the body is an ExecutionPayloadHeaderDeneb
+    bool blinded = false;   // BlindedBeaconBlock: field 9 of the body is an ExecutionPayloadHeader
+    int32_t fork = LHB200_FORK_DENEB;   // beacon_block_body.rs superstruct variant: Altair 9 body fields (no payload),
+                                        // Bellatrix 10 (14-field payload), Capella 11 (+ withdrawals, BLS changes), Deneb 12
 
     uint64_t u64(uint64_t off) { return p.literal_bytes(s + off, 8); }
     uint64_t h256(uint64_t off) { return p.literal_bytes(s + off, 32); }
@@ -1558,11 +1560,14 @@ struct BlockDescriber {
         return true;
     }
     uint64_t payload(uint64_t off, uint64_t len) {
-        if (len < 528) { bad = true; return 0; }
-        const uint32_t o_extra = rd32(s + off + 436), o_tx = rd32(s + off + 504), o_wd = rd32(s + off + 508);
-        if (o_extra != 528 || o_tx < o_extra || o_tx - o_extra > 32 || o_wd < o_tx || o_wd > len || (len - o_wd) % 44 ||
+        // fixed part: 508 B (Bellatrix: ... transactions offset), 512 (Capella: + withdrawals offset), 528 (Deneb: + blob gas)
+        const bool has_wd = fork >= LHB200_FORK_CAPELLA, has_blob = fork >= LHB200_FORK_DENEB;
+        const uint32_t fixed = has_blob ? 528 : has_wd ? 512 : 508;
+        if (len < fixed) { bad = true; return 0; }
+        const uint32_t o_extra = rd32(s + off + 436), o_tx = rd32(s + off + 504), o_wd = has_wd ? rd32(s + off + 508) : (uint32_t)len;
+        if (o_extra != fixed || o_tx < o_extra || o_tx - o_extra > 32 || o_wd < o_tx || o_wd > len || (len - o_wd) % 44 ||
             (len - o_wd) / 44 > 16) { bad = true; return 0; }
-        std::vector<uint64_t> f(17);
+        std::vector<uint64_t> f(14);
         f[0] = h256(off); f[1] = addr20(off + 32); f[2] = h256(off + 52); f[3] = h256(off + 84);
         f[4] = blob(off + 116, 256, 3);
         f[5] = h256(off + 372); f[6] = u64(off + 404); f[7] = u64(off + 412); f[8] = u64(off + 420); f[9] = u64(off + 428);
@@ -1573,32 +1578,38 @@ struct BlockDescriber {
         for (size_t i = 0; i + 1 < b.size(); i++)  // ByteList[2^30]: 2^25 chunks
             roots.push_back(p.bytes_item(d + off + o_tx + b[i], b[i + 1] - b[i], 25, true, b[i + 1] - b[i]));
         f[13] = list_of(roots, 20);
-        f[14] = fixed_list(off + o_wd, len - o_wd, 44, 4, [&](uint64_t o) { return withdrawal(o); });
-        f[15] = u64(off + 512); f[16] = u64(off + 520);
+        if (has_wd) f.push_back(fixed_list(off + o_wd, len - o_wd, 44, 4, [&](uint64_t o) { return withdrawal(o); }));
+        if (has_blob) { f.push_back(u64(off + 512)); f.push_back(u64(off + 520)); }
         return p.container(f);
     }
     // ExecutionPayloadHeaderDeneb (execution_payload_header.rs:46-87): 584-byte fixed part + extra_data
     uint64_t payload_header(uint64_t off, uint64_t len) {
-        if (len < 584 || len > 584 + 32 || rd32(s + off + 436) != 584) { bad = true; return 0; }
-        std::vector<uint64_t> f(17);
+        // 536-byte fixed part (Bellatrix, 14 fields), 568 (Capella: + withdrawals_root), 584 (Deneb: + blob gas)
+        const bool has_wd = fork >= LHB200_FORK_CAPELLA, has_blob = fork >= LHB200_FORK_DENEB;
+        const uint32_t fixed = has_blob ? 584 : has_wd ? 568 : 536;
+        if (len < fixed || len > fixed + 32 || rd32(s + off + 436) != fixed) { bad = true; return 0; }
+        std::vector<uint64_t> f(14);
         f[0] = h256(off); f[1] = addr20(off + 32); f[2] = h256(off + 52); f[3] = h256(off + 84);
         f[4] = blob(off + 116, 256, 3);
         f[5] = h256(off + 372); f[6] = u64(off + 404); f[7] = u64(off + 412); f[8] = u64(off + 420); f[9] = u64(off + 428);
-        f[10] = p.bytes_item(d + off + 584, len - 584, 0, true, len - 584);
+        f[10] = p.bytes_item(d + off + fixed, len - fixed, 0, true, len - fixed);
         f[11] = h256(off + 440); f[12] = h256(off + 472);
         f[13] = h256(off + 504);            // transactions_root
-        f[14] = h256(off + 536);            // withdrawals_root
-        f[15] = u64(off + 568); f[16] = u64(off + 576);
+        if (has_wd) f.push_back(h256(off + 536));            // withdrawals_root
+        if (has_blob) { f.push_back(u64(off + 568)); f.push_back(u64(off + 576)); }
         return p.container(f);
     }
     uint64_t body(uint64_t off, uint64_t len, uint64_t dst) {
-        if (len < 392) { bad = true; return 0; }
+        const bool has_ep = fork >= LHB200_FORK_BELLATRIX, has_bc = fork >= LHB200_FORK_CAPELLA, has_kz = fork >= LHB200_FORK_DENEB;
+        const uint32_t fixed = 380 + (has_ep ? 4 : 0) + (has_bc ? 4 : 0) + (has_kz ? 4 : 0);
+        if (len < fixed) { bad = true; return 0; }
         const uint32_t o_ps = rd32(s + off + 200), o_as = rd32(s + off + 204), o_at = rd32(s + off + 208),
-                       o_dp = rd32(s + off + 212), o_ex = rd32(s + off + 216), o_ep = rd32(s + off + 380),
-                       o_bc = rd32(s + off + 384), o_kz = rd32(s + off + 388);
-        if (o_ps != 392 || o_as < o_ps || o_at < o_as || o_dp < o_at || o_ex < o_dp || o_ep < o_ex || o_bc < o_ep ||
+                       o_dp = rd32(s + off + 212), o_ex = rd32(s + off + 216),
+                       o_ep = has_ep ? rd32(s + off + 380) : (uint32_t)len, o_bc = has_bc ? rd32(s + off + 384) : (uint32_t)len,
+                       o_kz = has_kz ? rd32(s + off + 388) : (uint32_t)len;
+        if (o_ps != fixed || o_as < o_ps || o_at < o_as || o_dp < o_at || o_ex < o_dp || o_ep < o_ex || o_bc < o_ep ||
             o_kz < o_bc || o_kz > len) { bad = true; return 0; }
-        std::vector<uint64_t> f(12), b, roots;
+        std::vector<uint64_t> f(9), b, roots;
         f[0] = sig(off);
         f[1] = p.container({h256(off + 96), u64(off + 128), h256(off + 136)});  // eth1_data.rs:27
         f[2] = h256(off + 168);
@@ -1624,9 +1635,9 @@ struct BlockDescriber {
         f[6] = fixed_list(off + o_dp, o_ex - o_dp, 1240, 4, [&](uint64_t o) { return deposit(o); });
         f[7] = fixed_list(off + o_ex, o_ep - o_ex, 112, 4, [&](uint64_t o) { return voluntary_exit(o); });
         f[8] = p.op_hash(blob(off + 220, 64, 1), sig(off + 284));  // sync_aggregate.rs:38
-        f[9] = blinded ? payload_header(off + o_ep, o_bc - o_ep) : payload(off + o_ep, o_bc - o_ep);
-        f[10] = fixed_list(off + o_bc, o_kz - o_bc, 172, 4, [&](uint64_t o) { return bls_change(o); });
-        f[11] = fixed_list(off + o_kz, len - o_kz, 48, 12, [&](uint64_t o) { return pubkey(o); });  // kzg_commitment.rs:51
+        if (has_ep) f.push_back(blinded ? payload_header(off + o_ep, o_bc - o_ep) : payload(off + o_ep, o_bc - o_ep));
+        if (has_bc) f.push_back(fixed_list(off + o_bc, o_kz - o_bc, 172, 4, [&](uint64_t o) { return bls_change(o); }));
+        if (has_kz) f.push_back(fixed_list(off + o_kz, len - o_kz, 48, 12, [&](uint64_t o) { return pubkey(o); }));  // kzg_commitment.rs:51
         if (bad) return 0;
         return p.container(f, dst);
     }
@@ -1643,19 +1654,20 @@ extern "C" {
 constexpr int32_t LHB200_ERETRY = -1000;   // internal: the plan did not fit the arena bound of this attempt
 
 // transactions in one BeaconBlockDeneb blob (0 when the offsets are not plausible — the describer reports that)
-static uint64_t prescan_transactions(const uint8_t* blk, uint64_t len) {
+static uint64_t prescan_transactions(const uint8_t* blk, uint64_t len, int32_t fork) {
     auto rd = [&](uint64_t o) { uint32_t v; memcpy(&v, blk + o, 4); return (uint64_t)v; };
-    if (len < 84 + 392) return 0;
-    const uint64_t body = 84, o_ep = rd(body + 380), o_bc = rd(body + 384);
+    if (fork < LHB200_FORK_BELLATRIX || len < 84 + 392) return 0;
+    const uint64_t body = 84, o_ep = rd(body + 380), o_bc = fork >= LHB200_FORK_CAPELLA ? rd(body + 384) : len - body;
     if (o_ep > o_bc || body + o_bc > len || o_bc - o_ep < 528) return 0;
-    const uint64_t pay = body + o_ep, plen = o_bc - o_ep, o_tx = rd(pay + 504), o_wd = rd(pay + 508);
+    const uint64_t pay = body + o_ep, plen = o_bc - o_ep, o_tx = rd(pay + 504),
+                   o_wd = fork >= LHB200_FORK_CAPELLA ? rd(pay + 508) : plen;
     if (o_tx > o_wd || o_wd > plen || o_wd - o_tx < 4) return 0;
     const uint64_t first = rd(pay + o_tx);
     return first <= o_wd - o_tx ? first / 4 : 0;
 }
 
 static int32_t block_roots_attempt(Ctx& c, const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
-                                   uint8_t* body_roots, bool blinded, uint64_t base, uint64_t total, size_t in_pad,
+                                   uint8_t* body_roots, bool blinded, int32_t fork, uint64_t base, uint64_t total, size_t in_pad,
                                    size_t max_nodes, size_t lit_cap) {
     uint8_t *d_in = nullptr, *d_roots = nullptr, *d_body = nullptr;
     bool bad = false;
@@ -1667,6 +1679,7 @@ static int32_t block_roots_attempt(Ctx& c, const uint8_t* ssz, const uint64_t* o
         p.forced_wave.assign(2ull * n, -1);
         BlockDescriber bd{p, ssz + base, d_in};
         bd.blinded = blinded;
+        bd.fork = fork;
         for (uint32_t i = 0; i < n && !bd.bad; i++)
             bd.block(offsets[i] - base, offsets[i + 1] - offsets[i], reinterpret_cast<uint64_t>(d_roots + 32ull * i),
                      reinterpret_cast<uint64_t>(d_body + 32ull * i));
@@ -1683,7 +1696,7 @@ static int32_t block_roots_attempt(Ctx& c, const uint8_t* ssz, const uint64_t* o
     if (!arena || !hst) return LHB200_ENOMEM;
     Plan pl;
     int32_t rc = build_plan(pl, arena, need, lit_cap, build, max_nodes);
-    if (bad) { set_error("BeaconBlockDeneb SSZ: malformed offsets or lengths"); return LHB200_EINVAL; }
+    if (bad) { set_error("BeaconBlock SSZ: malformed offsets or lengths for this fork"); return LHB200_EINVAL; }
     if (pl.node_overflow || pl.lit.size() > lit_cap || pl.ops.size() + pl.items.size() > max_nodes ||
         pl.bump + prog_bytes > need) {
         set_error("internal: block plan exceeds its arena bound (%zu ops + %zu items of %zu nodes, %zu of %zu literal bytes, "
@@ -1713,8 +1726,12 @@ static int32_t block_roots_attempt(Ctx& c, const uint8_t* ssz, const uint64_t* o
 
 // n BeaconBlockDeneb SSZ blobs, concatenated; offsets[n+1]; roots n*32; body_roots n*32 or NULL.
 static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,
-                                 uint8_t* body_roots, bool blinded) {
+                                 uint8_t* body_roots, bool blinded, int32_t fork = LHB200_FORK_DENEB) {
     LHB_REQUIRE_READY();
+    if (fork < LHB200_FORK_ALTAIR || fork > LHB200_FORK_DENEB || (blinded && fork < LHB200_FORK_BELLATRIX)) {
+        set_error("beacon_block_roots: fork id %d not supported (Altair .. Deneb; blinded blocks from Bellatrix)", fork);
+        return LHB200_EINVAL;
+    }
     if (!ssz || !offsets || !roots || n == 0) { set_error("beacon_block_roots: null argument or zero blocks"); return LHB200_EINVAL; }
     for (uint32_t i = 0; i < n; i++)
         if (offsets[i] > offsets[i + 1]) { set_error("beacon_block_roots: offsets not monotone"); return LHB200_EINVAL; }
@@ -1727,14 +1744,14 @@ static int32_t block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, ui
     // (three offset reads) so the arena bound is tight for real blocks and still holds for that shape.
     uint64_t n_tx = 0;
     if (!blinded)
-        for (uint32_t i = 0; i < n; i++) n_tx += prescan_transactions(ssz + offsets[i], offsets[i + 1] - offsets[i]);
+        for (uint32_t i = 0; i < n; i++) n_tx += prescan_transactions(ssz + offsets[i], offsets[i + 1] - offsets[i], fork);
     int32_t rc = LHB200_OK;
     for (int attempt = 0; attempt < 2; attempt++) {
         // attempt 0: transactions counted, everything else <= one node per 12 bytes and one literal per 8 bytes;
         // attempt 1 (only if a plan ever exceeds that): the unconditional bound of one node and literal per 2 bytes.
         const size_t max_nodes = attempt == 0 ? 2 * n_tx + total / 12 + 512ull * n : total / 2 + 512ull * n;
         const size_t lit_cap = align_up(32 * (attempt == 0 ? n_tx + total / 8 + 128ull * n : total / 2 + 128ull * n), 256);
-        rc = block_roots_attempt(c, ssz, offsets, n, roots, body_roots, blinded, base, total, in_pad, max_nodes, lit_cap);
+        rc = block_roots_attempt(c, ssz, offsets, n, roots, body_roots, blinded, fork, base, total, in_pad, max_nodes, lit_cap);
         if (rc != LHB200_ERETRY) break;
     }
     return rc == LHB200_ERETRY ? LHB200_EINVAL : rc;
@@ -1746,6 +1763,12 @@ int32_t lhb200_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offs
 int32_t lhb200_beacon_block_root_deneb(const uint8_t* ssz, uint64_t len, uint8_t out[32], uint8_t* body_root) {
     const uint64_t offs[2] = {0, len};
     return block_roots_deneb(ssz, offs, 1, out, body_root, false);
+}
+// The earlier variants of the BeaconBlock superstruct (beacon_block.rs:41-90, beacon_block_body.rs:43-110): fork is
+// LHB200_FORK_ALTAIR .. LHB200_FORK_DENEB; blinded != 0 selects the BlindedBeaconBlock form (Bellatrix and later).
+int32_t lhb200_beacon_block_roots(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, int32_t fork, int32_t blinded,
+                                  uint8_t* roots, uint8_t* body_roots) {
+    return block_roots_deneb(ssz, offsets, n, roots, body_roots, blinded != 0, fork);
 }
 // BlindedBeaconBlock (beacon_block.rs:80): the body carries the ExecutionPayloadHeader; the root equals the full block's.
 int32_t lhb200_blinded_beacon_block_roots_deneb(const uint8_t* ssz, const uint64_t* offsets, uint32_t n, uint8_t* roots,

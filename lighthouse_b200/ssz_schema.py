@@ -181,6 +181,29 @@ BEACON_STATE_BY_FORK = {"altair": BeaconStateAltair, "bellatrix": BeaconStateBel
                         "deneb": BeaconStateDeneb, "electra": BeaconStateElectra}
 
 
+# ---- the earlier variants of the BeaconBlock superstruct (beacon_block.rs:41-90, beacon_block_body.rs:43-110)
+def _block_of(body):
+    return C(("slot", U64), ("proposer_index", U64), ("parent_root", B32), ("state_root", B32), ("body", body))
+
+
+_pf, _bf = ExecutionPayloadDeneb[1], BeaconBlockBodyDeneb[1]
+ExecutionPayloadBellatrix = C(*_pf[:14])
+ExecutionPayloadCapella = C(*_pf[:15])
+BeaconBlockBodyAltair = C(*_bf[:9])
+BeaconBlockBodyBellatrix = C(*(_bf[:9] + [("execution_payload", ExecutionPayloadBellatrix)]))
+BeaconBlockBodyCapella = C(*(_bf[:9] + [("execution_payload", ExecutionPayloadCapella)] + _bf[10:11]))
+BEACON_BLOCK_BODY_BY_FORK = {"altair": BeaconBlockBodyAltair, "bellatrix": BeaconBlockBodyBellatrix,
+                             "capella": BeaconBlockBodyCapella, "deneb": BeaconBlockBodyDeneb}
+BEACON_BLOCK_BY_FORK = {k: _block_of(v) for k, v in BEACON_BLOCK_BODY_BY_FORK.items()}
+EXECUTION_PAYLOAD_BY_FORK = {"bellatrix": ExecutionPayloadBellatrix, "capella": ExecutionPayloadCapella,
+                             "deneb": ExecutionPayloadDeneb}
+EXECUTION_PAYLOAD_HEADER_BY_FORK = {"bellatrix": ExecutionPayloadHeaderBellatrix, "capella": ExecutionPayloadHeaderCapella,
+                                    "deneb": ExecutionPayloadHeaderDeneb}
+BLINDED_BEACON_BLOCK_BODY_BY_FORK = {
+    f: C(*[(n, EXECUTION_PAYLOAD_HEADER_BY_FORK[f]) if n == "execution_payload" else (n, t) for n, t in b[1]])
+    for f, b in BEACON_BLOCK_BODY_BY_FORK.items() if f != "altair"}
+BLINDED_BEACON_BLOCK_BY_FORK = {k: _block_of(v) for k, v in BLINDED_BEACON_BLOCK_BODY_BY_FORK.items()}
+
 # BlindedBeaconBlock (beacon_block.rs:80; payload.rs BlindedPayload): the body carries the payload HEADER
 BlindedBeaconBlockBodyDeneb = C(*[(n, ExecutionPayloadHeaderDeneb) if n == "execution_payload" else (n, t)
                                  for n, t in BeaconBlockBodyDeneb[1]])

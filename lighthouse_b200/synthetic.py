@@ -251,8 +251,9 @@ def block_signature_key_counts(n_blocks=32, n_validators=524288):
 # Synthetic Deneb BeaconBlock (mainnet preset) — values + SSZ bytes.
 def beacon_block_deneb(seed=1, n_attestations=128, n_transactions=150, n_proposer_slashings=1,
                        n_attester_slashings=1, n_deposits=2, n_exits=3, n_bls_changes=4, n_withdrawals=16,
-                       n_blobs=6, tx_sizes=None, committee=244, extra_data_len=13):
-    """-> (value, ssz_bytes) of a BeaconBlockDeneb filled with seeded pseudo-random content of mainnet shape."""
+                       n_blobs=6, tx_sizes=None, committee=244, extra_data_len=13, fork="deneb"):
+    """-> (value, ssz_bytes) of a BeaconBlock<fork> (altair / bellatrix / capella / deneb: the later forks' fields are
+    dropped, beacon_block_body.rs:43-110) filled with seeded pseudo-random content of mainnet shape."""
     from . import ssz_schema as S
     rng = np.random.default_rng(seed)
 
@@ -314,11 +315,17 @@ def beacon_block_deneb(seed=1, n_attestations=128, n_transactions=150, n_propose
         "blob_kzg_commitments": [rb(48) for _ in range(n_blobs)]}
     block = {"slot": u64(), "proposer_index": u64() % 500_000, "parent_root": rb(32), "state_root": rb(32),
              "body": body}
-    return block, S.serialize(S.BeaconBlockDeneb, block)
+    if fork != "deneb":
+        body_t = S.BEACON_BLOCK_BODY_BY_FORK[fork]
+        if fork != "altair":
+            pt = S.EXECUTION_PAYLOAD_BY_FORK[fork]
+            body["execution_payload"] = {n: payload[n] for n, _ in pt[1]}
+        block["body"] = {n: body[n] for n, _ in body_t[1]}
+    return block, S.serialize(S.BEACON_BLOCK_BY_FORK[fork], block)
 
 
-def blind_block_deneb(block, transactions_root: bytes, withdrawals_root: bytes):
-    """BlindedBeaconBlockDeneb value + SSZ of `block` (as produced by beacon_block_deneb) given the two list roots
+def blind_block_deneb(block, transactions_root: bytes, withdrawals_root: bytes, fork="deneb"):
+    """BlindedBeaconBlock<fork> value + SSZ of `block` (as produced by beacon_block_deneb) given the two list roots
     of its payload (computed by whoever has a hasher: the CUDA library, the oracle or the spec restatement)."""
     import copy
     from . import ssz_schema as S
@@ -326,5 +333,5 @@ def blind_block_deneb(block, transactions_root: bytes, withdrawals_root: bytes):
     p = v["body"]["execution_payload"]
     hdr = {k: p[k] for k in p if k not in ("transactions", "withdrawals")}
     hdr["transactions_root"], hdr["withdrawals_root"] = transactions_root, withdrawals_root
-    v["body"]["execution_payload"] = {n: hdr[n] for n, _ in S.ExecutionPayloadHeaderDeneb[1]}
-    return v, S.serialize(S.BlindedBeaconBlockDeneb, v)
+    v["body"]["execution_payload"] = {n: hdr[n] for n, _ in S.EXECUTION_PAYLOAD_HEADER_BY_FORK[fork][1]}
+    return v, S.serialize(S.BLINDED_BEACON_BLOCK_BY_FORK[fork], v)

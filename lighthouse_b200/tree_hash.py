@@ -152,6 +152,25 @@ def beacon_block_roots_deneb(blocks, want_body_roots=False, blinded=False):
     return roots
 
 
+def beacon_block_roots(blocks, fork="deneb", want_body_roots=False, blinded=False):
+    """canonical_root of a batch of BeaconBlock<fork> (or BlindedBeaconBlock<fork>) SSZ blobs, fork in altair / bellatrix /
+    capella / deneb (beacon_block.rs:41-90): lhb200_beacon_block_roots."""
+    blocks = [bytes(b) for b in blocks]
+    n = len(blocks)
+    offs = (C.c_uint64 * (n + 1))()
+    for i, b in enumerate(blocks):
+        offs[i + 1] = offs[i] + len(b)
+    p, keep = buf(b"".join(blocks))
+    out = C.create_string_buffer(32 * max(n, 1))
+    body = C.create_string_buffer(32 * max(n, 1)) if want_body_roots else None
+    check(lib.lhb200_beacon_block_roots(p, C.cast(offs, C.c_void_p), n, FORKS[fork], 1 if blinded else 0, out, body),
+          "lhb200_beacon_block_roots")
+    roots = [out.raw[32 * i: 32 * i + 32] for i in range(n)]
+    if want_body_roots:
+        return roots, [body.raw[32 * i: 32 * i + 32] for i in range(n)]
+    return roots
+
+
 def beacon_block_root_deneb(ssz, want_body_root=False, blinded=False):
     """canonical_root of one BeaconBlockDeneb; optionally also hash_tree_root(body) (BeaconBlockHeader.body_root)."""
     r = beacon_block_roots_deneb([ssz], want_body_root, blinded)

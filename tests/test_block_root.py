@@ -147,3 +147,39 @@ def test_gpu_blinded_block_root_matches_oracle(gpu, name):
     want = O.blinded_beacon_block_root_deneb(bssz)
     assert tree_hash.beacon_block_root_deneb(bssz, want_body_root=True, blinded=True) == want
     assert want[0] == tree_hash.beacon_block_root_deneb(ssz)   # == the full block's root on the device as well
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fork", ["altair", "bellatrix", "capella", "deneb"])
+def test_gpu_block_roots_every_fork(gpu, fork):
+    """The BeaconBlock superstruct variants (beacon_block.rs:41-90, beacon_block_body.rs:43-110) through the
+    fork-parametrised describer, full and blinded, single and as a batch: roots and body roots against the GENERIC
+    from-spec merkleization of tests/ssz_spec.py over the value (type descriptors in lighthouse_b200/ssz_schema.py)."""
+    from lighthouse_b200 import tree_hash
+    from lighthouse_b200._ffi import EINVAL
+    from lighthouse_b200 import Lhb200Error
+    t, bt = S.BEACON_BLOCK_BY_FORK[fork], S.BEACON_BLOCK_BODY_BY_FORK[fork]
+    shapes = [dict(seed=31), dict(seed=32, **EMPTY), dict(seed=33, n_attestations=5, tx_sizes=[0, 31, 32, 33, 4097], committee=2048)]
+    values, blobs = zip(*[synthetic.beacon_block_deneb(fork=fork, **kw) for kw in shapes])
+    want = [ssz_spec.hash_tree_root(t, v) for v in values]
+    want_body = [ssz_spec.hash_tree_root(bt, v["body"]) for v in values]
+    roots, bodies = tree_hash.beacon_block_roots(blobs, fork, want_body_roots=True)
+    assert roots == want and bodies == want_body
+    assert tree_hash.beacon_block_roots(blobs[1:2], fork) == want[1:2]
+    if fork == "deneb":
+        assert tree_hash.beacon_block_roots_deneb(blobs) == want
+    if fork != "altair":
+        pt = dict(S.EXECUTION_PAYLOAD_BY_FORK[fork][1])
+        blinded = []
+        for v in values:
+            ep = v["body"]["execution_payload"]
+            wr = ssz_spec.hash_tree_root(pt["withdrawals"], ep["withdrawals"]) if "withdrawals" in pt else bytes(32)
+            blinded.append(synthetic.blind_block_deneb(v, ssz_spec.hash_tree_root(pt["transactions"], ep["transactions"]), wr,
+                                                       fork=fork)[1])
+        assert tree_hash.beacon_block_roots(blinded, fork, blinded=True) == want
+    # the bytes of one fork are not silently hashed as another
+    other = {"altair": "capella", "bellatrix": "deneb", "capella": "bellatrix", "deneb": "capella"}[fork]
+    try:
+        assert tree_hash.beacon_block_roots(blobs[:1], other) != want[:1]
+    except Lhb200Error as e:
+        assert e.code == EINVAL
