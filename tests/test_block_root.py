@@ -183,3 +183,32 @@ def test_gpu_block_roots_every_fork(gpu, fork):
         assert tree_hash.beacon_block_roots(blobs[:1], other) != want[:1]
     except Lhb200Error as e:
         assert e.code == EINVAL
+
+
+@pytest.mark.parametrize("fork", ["altair", "bellatrix", "capella", "deneb"])
+def test_block_fork_schemas_roundtrip_and_blinded_root(fork):
+    """Host side of the fork variants (no GPU): the generator's SSZ decodes and re-encodes under the fork's type descriptor,
+    and the blinded block (payload replaced by its header) has the full block's root under the generic merkleization."""
+    t = S.BEACON_BLOCK_BY_FORK[fork]
+    v, ssz = synthetic.beacon_block_deneb(seed=41, n_attestations=3, n_transactions=5, fork=fork)
+    assert S.serialize(t, ssz_spec.deserialize(t, ssz)) == ssz
+    assert len(S.BEACON_BLOCK_BODY_BY_FORK[fork][1]) == {"altair": 9, "bellatrix": 10, "capella": 11, "deneb": 12}[fork]
+    if fork != "altair":
+        pt = dict(S.EXECUTION_PAYLOAD_BY_FORK[fork][1])
+        ep = v["body"]["execution_payload"]
+        wr = ssz_spec.hash_tree_root(pt["withdrawals"], ep["withdrawals"]) if "withdrawals" in pt else bytes(32)
+        bv, _ = synthetic.blind_block_deneb(v, ssz_spec.hash_tree_root(pt["transactions"], ep["transactions"]), wr, fork=fork)
+        assert ssz_spec.hash_tree_root(S.BLINDED_BEACON_BLOCK_BY_FORK[fork], bv) == ssz_spec.hash_tree_root(t, v)
+
+
+def test_electra_state_schema_roundtrip():
+    """BeaconStateElectra as in this reference revision (beacon_state.rs:487-525): 37 fields, fixed part 2 736 713 bytes,
+    generator output decodes and re-encodes under the type descriptor."""
+    from lighthouse_b200.synthetic import beacon_state_deneb_ssz
+    typ = S.BEACON_STATE_BY_FORK["electra"]
+    assert len(typ[1]) == 37
+    ssz = beacon_state_deneb_ssz(3, seed=5, fork="electra", n_pending=(2, 1, 3))
+    value = ssz_spec.deserialize(typ, ssz)
+    assert S.serialize(typ, value) == ssz
+    assert [len(value[k]) for k in ("pending_balance_deposits", "pending_partial_withdrawals", "pending_consolidations")] == [2, 1, 3]
+    assert len(beacon_state_deneb_ssz(0, fork="electra", all_default=True)) == 2736713 + 648
