@@ -616,7 +616,7 @@ def run_ours(args):
                     "call": "lhb200_verify_signature_sets (the plugin entry point), pinned host buffers",
                     "timer": "perf_counter around synchronised calls"},
             "e2e_pageable": {"value": N_SETS * world / (bls_e2e_pg_ms / 1e3), "unit": "sets/s", "ms_per_step": bls_e2e_pg_ms,
-                             "h2d_bytes_per_step": int(h2d), "call": "lhb200_verify_signature_sets, pageable host buffers"},
+                             "h2d_bytes_per_step": int(h2d), "call": "lhb200_verify_signature_sets, pageable host buffers (keys staged by the library's pinned ring + copy threads)"},
             "e2e_indexed": {"value": N_SETS * world / (bls_e2e_idx_ms / 1e3), "unit": "sets/s",
                             "h2d_bytes_per_step": int(h2d_idx), "d2h_bytes_per_step": 1, "ms_per_step": bls_e2e_idx_ms,
                             "note": "keys referenced by u32 index into the device-resident pubkey table (ValidatorPubkeyCache mirror)"},
