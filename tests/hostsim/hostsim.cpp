@@ -430,3 +430,31 @@ EXPORT int hs_final_warp(const uint8_t* a576, const uint8_t* b576, uint8_t* out5
     fp12_out(out576, g);
     return 0;
 }
+
+// the sum tree step of k_g2_sum_warp lane by lane: sum of n compressed G2 points (infinity encodings skipped), each fed as a
+// Jacobian point with Z != 1; out96 = compressed sum (the infinity encoding if nothing was added)
+EXPORT int hs_g2_sum_warp(const uint8_t* pts96, int n, uint8_t* out96) {
+    using namespace gw;
+    std::vector<uint32_t> Rv(REGION_WORDS, 0xdeadbeefu);
+    uint32_t* R = Rv.data();
+    const mw::Tables T = tables();
+    put_consts(R);
+    bool have = false;
+    for (int j = 0; j < n; j++) {
+        G2Affine a; const int rc = g2_decompress(a, pts96 + 96 * j);
+        if (rc == DEC_BAD) return -1;
+        if (rc == DEC_INFINITY) continue;
+        G2Jac h; jac_from_affine(h, a); jac_dbl(h, h); G2Jac na; jac_from_affine(na, a); jac_neg(na, na); jac_add(h, h, na);   // same point, Z != 1
+        put_fp2(R, GW_S_HX_0, h.X); put_fp2(R, GW_S_HX_0 + 2, h.Y); put_fp2(R, GW_S_HX_0 + 4, h.Z);
+        if (!have) { GW_RUN(R, 0, HINIT); have = true; }
+        else { GW_RUN(R, 0, HBP); GW_RUN(R, 0, ADDA); }
+    }
+    G2Affine o;
+    if (have) {
+        GW_RUN(R, 0, TOJAC);
+        G2Jac jj; get_fp2(jj.X, R, GW_S_JX_0); get_fp2(jj.Y, R, GW_S_JX_0 + 2); get_fp2(jj.Z, R, GW_S_JX_0 + 4);
+        jac_to_affine(o, jj);
+    } else { f_set_zero(o.x); f_set_zero(o.y); o.inf = 1; }
+    g2_compress(out96, o);
+    return 0;
+}

@@ -411,3 +411,20 @@ def test_final_exponentiation_warp_program_matches_single_thread(L):
     assert L.hs_final_warp(m1.raw, m2.raw, o) == 0
     g = B.final_exp(B.f12_mul(B.miller_loop(p1, q1), B.miller_loop(p2, q2)))
     assert f12_from(o.raw) == B.f12_mul(B.f12_sqr(g), g)
+
+
+def test_g2_sum_warp_program_matches_oracle(L):
+    """The point-sum step of k_g2_sum_warp (sum r_i sig_i tree in latency mode) lane by lane: sums with infinity entries
+    skipped == the oracle's g2_add chain; nothing but infinities gives the infinity encoding."""
+    L.hs_g2_sum_warp.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
+    rnd = random.Random(123)
+    o = C.create_string_buffer(96)
+    pts = [B.g2_mul(B.G2_GEN, rnd.randrange(1, B.R)) for _ in range(5)]
+    for pick in ([0], [0, 1], [None, 0, 1, 2, None, 3, 4], [None, None]):
+        enc = b"".join(B.g2_compress(None if k is None else pts[k]) for k in pick)
+        assert L.hs_g2_sum_warp(enc, len(pick), o) == 0
+        acc = None
+        for k in pick:
+            if k is not None:
+                acc = B.g2_add(acc, pts[k])
+        assert o.raw == B.g2_compress(acc), pick
